@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Headline benchmark: traced rays/s (forward + backward) on the C3 workload of BASELINE.md --
+300k-surfel lego-shaped scene, 800 x 800 pixels x 256 Fibonacci-hemisphere secondary rays = 163.84 M rays per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's tracer (one rank per GPU, torchrun for N>1)
+    python bench.py --impl reference [...]                         # the reference tracer (OptiX) or, failing that, the CPU oracle
+
+A step = one forward + backward pass of the tracer over ALL rays of the workload (processed in chunks of --chunk rays,
+like the reference's renderer chunks its pixels, gaussian_renderer/__init__.py:314-322) followed by the single
+all-reduce of the fused per-surfel gradient buffer.  Rays are sharded contiguously over ranks (strong scaling: the total
+is fixed), surfels and the acceleration structure are replicated.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SURFELS, IMG, SPP = 300000, 800, 256
+METRIC = "traced rays/sec (fwd+bwd), 300k surfels, 800x800x256 secondary rays"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--chunk", type=int, default=1 << 22, help="rays per trace call")
+    p.add_argument("--surfels", type=int, default=N_SURFELS)
+    p.add_argument("--img", type=int, default=IMG)
+    p.add_argument("--spp", type=int, default=SPP)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    p.add_argument("--ref-rays", type=int, default=1 << 22, help="rays per step of the reference arm's bounded sample")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_workload(args, device, rank, world, tracer_factory):
+    """Scene, tracer inputs and this rank's secondary rays, resident on `device`."""
+    from irgs_b200 import parallel, synth
+    sc = synth.make_scene(args.surfels, device=device)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    tracer = tracer_factory(sc, inp)
+    # primary pass (this repo's tracer or the reference, whichever arm runs) -> one shading point per pixel
+    o, d = synth.primary_rays(args.img, args.img, device=device)
+    with torch.no_grad():
+        outs = tracer.trace(o, d, inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"],
+                            synth.ALPHA_MIN)
+    pts, nrm = synth.shading_points_from_primary(o, d, outs[3], outs[4], outs[1])
+    pb, pe = parallel.shard_range(args.img * args.img, rank, world)
+    n_pix = pe - pb
+    rays_o = torch.empty(n_pix * args.spp, 3, device=device)
+    rays_d = torch.empty(n_pix * args.spp, 3, device=device)
+    gen = torch.Generator().manual_seed(synth.RAY_SEED)
+    azim = torch.rand(args.img * args.img, 1, generator=gen)[pb:pe].to(device)
+    step_pix = 1 << 14
+    for b in range(0, n_pix, step_pix):
+        e = min(b + step_pix, n_pix)
+        dirs = synth.fibonacci_hemisphere(nrm[pb + b:pb + e], args.spp, False)
+        # random azimuth per pixel (training mode of utils/graphics_utils.py:31-32), applied as a rotation about the normal
+        dirs = _rotate_about(dirs, nrm[pb + b:pb + e], azim[b:e] * 2 * np.pi)
+        rays_d[b * args.spp:e * args.spp] = dirs.reshape(-1, 3)
+        rays_o[b * args.spp:e * args.spp] = (pts[pb + b:pb + e, None] + dirs * synth.LIGHT_T_MIN).reshape(-1, 3)
+    return sc, inp, tracer, rays_o, rays_d
+
+
+def _rotate_about(v, axis, ang):
+    """Rodrigues rotation of v[B,S,3] about unit axis[B,3] by ang[B,1]."""
+    a = axis[:, None]
+    c, s = torch.cos(ang)[:, None], torch.sin(ang)[:, None]
+    return v * c + torch.cross(a.expand_as(v), v, dim=-1) * s + a * (a * v).sum(-1, keepdim=True) * (1 - c)
+
+
+def make_gout(chunk, device):
+    from irgs_b200 import synth
+    g = torch.Generator(device).manual_seed(synth.GRAD_SEED)
+    return (torch.randn(chunk, 3, device=device, generator=g), torch.randn(chunk, 3, device=device, generator=g),
+            torch.zeros(chunk, 0, device=device), torch.randn(chunk, device=device, generator=g),
+            torch.randn(chunk, device=device, generator=g))
+
+
+def canonical_counters(inp, rays_o, rays_d, n_sample=1 << 16):
+    """V (boxes tested), P (surfel tests), H (composited hits) per ray on the oracle's canonical LBVH."""
+    import oracle
+    S = oracle.Scene(*(inp[k].cpu() for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")))
+    g = torch.Generator().manual_seed(5678)
+    sel = torch.randint(0, rays_o.shape[0], (n_sample,), generator=g).to(rays_o.device)
+    r = oracle.trace_forward(S, rays_o[sel].cpu(), rays_d[sel].cpu(), use_bvh=True, hit_cap=4)
+    return S, (r["counters"] / float(n_sample)).tolist()
+
+
+def cpu_baseline(S, rays_o, rays_d, seconds):
+    """The CPU oracle (port of the reference math + canonical LBVH, OpenMP over all host threads) timed on a bounded
+    contiguous sample of the same rays, forward + backward."""
+    import oracle
+    n = 1 << 15
+    o, d = rays_o[:n].cpu(), rays_d[:n].cpu()
+    t0 = time.time()
+    f = oracle.trace_forward(S, o, d, use_bvh=True, hit_cap=4)
+    rate = n / max(time.time() - t0, 1e-6)
+    n = int(min(max(rate * seconds / 2.5, 1 << 15), rays_o.shape[0], 1 << 24))
+    o, d = rays_o[:n].cpu(), rays_d[:n].cpu()
+    g = torch.Generator().manual_seed(9012)
+    gout = dict(color=torch.randn(n, 3, generator=g).numpy(), normal=torch.randn(n, 3, generator=g).numpy(),
+                feature=np.zeros((n, 0), np.float32), depth=torch.randn(n, generator=g).numpy(),
+                alpha=torch.randn(n, generator=g).numpy())
+    t0 = time.time()
+    f = oracle.trace_forward(S, o, d, use_bvh=True, hit_cap=4)
+    oracle.trace_backward(S, o, d, f, gout, use_bvh=True)
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "rays/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"first {n} rays of rank 0's shard, forward+backward, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    from irgs_b200 import _lib, parallel, synth
+    from irgs_b200.raytracer import GaussianTracer, _ptr
+    rank, local, world = parallel.init_from_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    lib = _lib.load()
+
+    def factory(sc, inp):
+        tr = GaussianTracer(transmittance_min=synth.T_MIN, device=device)
+        tr.build_from_surfels(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], synth.ALPHA_MIN)
+        return tr
+
+    sc, inp, tracer, rays_o, rays_d = build_workload(args, device, rank, world, factory)
+    n_local = rays_o.shape[0]
+    n_total = args.img * args.img * args.spp
+    chunk = min(args.chunk, n_local)
+    gout = make_gout(chunk, device)
+    leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
+    tracer.accumulate_grads = True
+    fwd_events = []
+
+    def step(record):
+        for b in range(0, n_local, chunk):
+            e = min(b + chunk, n_local)
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            outs = tracer.trace(rays_o[b:e], rays_d[b:e], leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"],
+                                leaf["normals"], None, leaf["shs"], synth.ALPHA_MIN)
+            if record:
+                e1.record()
+                fwd_events.append((e0, e1, e - b))
+            torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]],
+                                    [gout[0][:e - b], gout[1][:e - b], gout[3][:e - b], gout[4][:e - b]])
+        return tracer.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape))  # the one all-reduce
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    lib.irgs_reset_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t0.record()
+    for _ in range(args.steps):
+        grads = step(True)
+    t1.record()
+    sync_all()
+    launches = int(lib.irgs_launch_count())
+    ms = parallel.max_over_ranks(t0.elapsed_time(t1), device) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in fwd_events)
+    fwd_rays = sum(n for _, _, n in fwd_events)
+    checksum = float(grads["shs"].abs().sum().item())
+
+    # end to end through the C ABI on HOST buffers: rays pinned on the host, copied in per chunk inside the timed region;
+    # the step's result (fused per-surfel gradients after the all-reduce) is read back to the host
+    e2e = None
+    if not args.no_e2e:
+        oh, dh = rays_o.cpu().pin_memory(), rays_d.cpu().pin_memory()
+        fused = torch.zeros(args.surfels, 64, device=device)
+        fused_h = torch.empty(args.surfels, 64).pin_memory()
+        e2e_chunk = min(1 << 21, n_local)
+        ge = make_gout(e2e_chunk, device)
+
+        def e2e_step():
+            fused.zero_()
+            _lib.check(lib.irgs_trace_fwd_bwd_host(
+                tracer.impl.h, n_local, 0, 16, 3, _ptr(oh), _ptr(dh), _ptr(inp["means3D"]), _ptr(inp["opacity"]),
+                _ptr(inp["ru"]), _ptr(inp["rv"]), _ptr(inp["normals"]), None, _ptr(inp["shs"]), _ptr(ge[0]), _ptr(ge[1]),
+                None, _ptr(ge[3]), _ptr(ge[4]), e2e_chunk, None, None, None, _ptr(fused), None, synth.ALPHA_MIN, synth.T_MIN,
+                0, e2e_chunk))
+            parallel.allreduce_sum_(fused)
+            fused_h.copy_(fused, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        sync_all()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        sync_all()
+        e2e_s = parallel.max_over_ranks(time.perf_counter() - w0, device) / args.steps
+        e2e = {"value": n_total / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(n_local * 24),
+               "d2h_bytes_per_step": int(fused_h.numel() * 4), "ms_per_step": e2e_s * 1e3,
+               "api": "irgs_trace_fwd_bwd_host (C ABI, pinned host rays) + all-reduce + gradient read-back"}
+        del oh, dh
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    S, (V, P, H) = canonical_counters(inp, rays_o, rays_d)
+    bytes_per_ray = 24 + 32 + 32 * V + 64 * P + 192 * H  # BASELINE.md section 4, forward, S = 0
+    achieved = bytes_per_ray * fwd_rays / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None
+    out = {
+        "metric": METRIC, "value": n_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C3: {args.surfels} surfels, {args.img}x{args.img}x{args.spp} secondary rays, fwd+bwd",
+                   "rays_per_step": n_total, "chunk_rays": chunk, "sh_degree": 3, "features": 0,
+                   "parallelism": f"ray-sharded dp{world}, surfels+BVH replicated, one all-reduce of N x 64 floats",
+                   "l2": "inputs (3.9 GB of rays per step) exceed L2; no flush needed",
+                   "shading_points": "all 640k bundles start on the surface (missed pixels re-assigned to hit pixels)"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "algorithmic_bytes_per_ray": bytes_per_ray,
+                     "canonical_counters_per_ray": {"V_boxes": V, "P_surfel_tests": P, "H_hits": H},
+                     "kernel_ms_per_step": fwd_ms / args.steps, "kernel_share_of_step": fwd_ms / args.steps / ms,
+                     "note": "algorithmic bytes follow BASELINE.md section 4 on the oracle's canonical LBVH; most node and "
+                             "surfel traffic is L2-resident (working set ~100 MB), so achieved can exceed DRAM traffic"},
+        "grad_checksum": checksum,
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(S, rays_o, rays_d, args.cpu_seconds)
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The UNMODIFIED reference tracer from baseline/_ref through its own GaussianTracer API on a bounded sample of
+    the same workload; if it cannot run on this box (no libnvoptix / no build), the CPU oracle port on all host
+    threads stands in, as the tier contract allows."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from irgs_b200 import synth
+    device = torch.device("cuda", 0)
+    n_total = args.img * args.img * args.spp
+    base = {"impl": "reference", "metric": METRIC, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"C3: {args.surfels} surfels, {args.img}x{args.img}x{args.spp} secondary rays, fwd+bwd",
+                       "rays_per_step": n_total}}
+    why = None
+    ref_mod = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        for m in [m for m in sys.modules if m == "surfel_tracer" or m.startswith("surfel_tracer.")]:
+            del sys.modules[m]
+        import surfel_tracer as ref_mod  # noqa
+        if "baseline" not in ref_mod.__file__:
+            raise ImportError("baseline/_ref/surfel_tracer not found (run oracle/build_ref.sh)")
+        probe = ref_mod.GaussianTracer(transmittance_min=synth.T_MIN)
+        del probe
+    except Exception as e:  # OptiX runtime missing, build missing, ...
+        why = f"{type(e).__name__}: {e}"
+        ref_mod = None
+        sys.path.pop(0)
+
+    # the rays come from this repo's workload builder (same seeds); the primary pass uses whichever tracer is measured
+    if ref_mod is not None:
+        def factory(sc, inp):
+            tr = ref_mod.GaussianTracer(transmittance_min=synth.T_MIN)
+            tr.build_bvh(*synth.proxy_mesh(sc, synth.ALPHA_MIN))
+            return tr
+        torch.cuda.set_device(device)
+        sc, inp, tracer, rays_o, rays_d = build_workload(args, device, 0, max(args.gpus, 1), factory)
+        n = min(args.ref_rays, rays_o.shape[0])
+        call = 1 << 18  # trace_num_rays, the reference's own per-call size (arguments/__init__.py:154)
+        gout = make_gout(call, device)
+        leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
+
+        def step():
+            for b in range(0, n, call):
+                e = min(b + call, n)
+                outs = tracer.trace(rays_o[b:e], rays_d[b:e], leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"],
+                                    leaf["normals"], None, leaf["shs"], synth.ALPHA_MIN)
+                torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]],
+                                        [gout[0][:e - b], gout[1][:e - b], gout[3][:e - b], gout[4][:e - b]])
+            for v in leaf.values():
+                v.grad = None
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(0)
+        clocks.start()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            step()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / args.steps
+        value = n / (ms * 1e-3)
+        base.update(value=value, ms_per_step=ms, clocks=clocks.stop(),
+                    cpu_baseline={"value": value, "unit": "rays/s", "cores": 0, "kind": "reference",
+                                  "sample": f"first {n} rays of the workload per step in calls of 2^18 rays, OptiX tracer on the GPU "
+                                            "through its own GaussianTracer.trace + autograd backward"},
+                    e2e={"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        base["config"]["sample_rays_per_step"] = n
+        print(json.dumps(base), flush=True)
+        return
+
+    # CPU oracle port
+    import oracle
+    sc = synth.make_scene(args.surfels)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    S = oracle.Scene(*(inp[k] for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")))
+    o, d = synth.primary_rays(args.img, args.img)
+    prim = oracle.trace_forward(S, o, d, use_bvh=True, hit_cap=4)
+    pts, nrm = synth.shading_points_from_primary(o, d, torch.from_numpy(prim["depth"]), torch.from_numpy(prim["alpha"]),
+                                                 torch.from_numpy(prim["normal"]))
+    n_pix = max(64, min(args.ref_rays, 1 << 20) // args.spp)
+    ro, rd = synth.secondary_rays(pts[:n_pix], nrm[:n_pix], args.spp)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    n = ro.shape[0]
+    g = torch.Generator().manual_seed(synth.GRAD_SEED)
+    gout = dict(color=torch.randn(n, 3, generator=g).numpy(), normal=torch.randn(n, 3, generator=g).numpy(),
+                feature=np.zeros((n, 0), np.float32), depth=torch.randn(n, generator=g).numpy(),
+                alpha=torch.randn(n, generator=g).numpy())
+
+    def step():
+        f = oracle.trace_forward(S, ro, rd, use_bvh=True, hit_cap=4)
+        oracle.trace_backward(S, ro, rd, f, gout, use_bvh=True)
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    ms = (time.time() - t0) / args.steps * 1e3
+    value = n / (ms * 1e-3)
+    base.update(value=value, ms_per_step=ms, reference_tracer_not_runnable=why,
+                cpu_baseline={"value": value, "unit": "rays/s", "cores": oracle.num_threads(), "kind": "port",
+                              "sample": f"{n} secondary rays ({n_pix} pixels x {args.spp}) per step, forward+backward, CPU oracle "
+                                        "with the canonical LBVH on all host threads"},
+                e2e={"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    base["config"]["sample_rays_per_step"] = n
+    print(json.dumps(base), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,142 @@
+/*
+ * irgs_b200.h -- C ABI of the B200-native differentiable surfel ray tracer.
+ *
+ * This is the drop-in boundary for IRGS's `surfel_tracer` extension: every entry point below replaces one method
+ * of the reference's pybind11 class `surfel_tracer::GaussianTracer`
+ * (/root/reference/submodules/surfel_tracer/src/bindings.cu:24-116) or of the `TriangleBvh` it forwards to
+ * (src/bvh.cu:163-252).  Plain pointers and sizes only; no torch types.  All `const float*` / `float*` arguments
+ * are DEVICE pointers to contiguous row-major float32 arrays unless the name ends in `_host`; `stream` is a
+ * `cudaStream_t` passed as `void*` (0 = legacy default stream).  Every call is asynchronous with respect to the
+ * host and ordered on `stream`, exactly like the reference, which launches on at::cuda::getCurrentCUDAStream()
+ * (bindings.cu:32,38,49,66,82).
+ *
+ * Error convention: 0 = success; non-zero = failure, irgs_last_error() returns a thread-local message.  The
+ * reference throws std::runtime_error through pybind (gpu_memory.h:50-55); the Python layer maps a non-zero status
+ * to RuntimeError.  Unlike the reference (which validates nothing, bindings.cu:42-59) shape limits are checked.
+ *
+ * Array layouts (SURVEY.md 8a'):  rays_o, rays_d [R,3];  means3D, ru, rv, normals [N,3];  opacity [N] (the
+ * reference's [N,1]);  features [N,S], S <= 12;  shs [N,K,3], K >= (deg+1)^2;  outputs color, normal [R,3],
+ * feature [R,S], depth, alpha [R].
+ */
+#ifndef IRGS_B200_H
+#define IRGS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRGS_MAX_FEATURES 12      /* MAX_FEATURE_SIZE, src/optix/auxiliary.h:12 */
+#define IRGS_T_SCENE_MAX 100.0f   /* T_SCENE_MAX,      src/optix/auxiliary.h:11 */
+#define IRGS_GRAD_STRIDE 64       /* floats per surfel in the fused gradient buffer, see irgs_trace_backward */
+
+typedef struct irgs_tracer irgs_tracer_t;
+
+const char *irgs_last_error(void);
+int irgs_version(void);
+
+/* create_gaussiantracer() (bindings.cu:101-103) / TriangleBvh ctor+dtor (bvh.cu:165-178).  One handle per device
+ * (per rank); unlike the reference's process-global OptiX context the handle owns all of its state. */
+int irgs_tracer_create(irgs_tracer_t **out, int device);
+int irgs_tracer_destroy(irgs_tracer_t *h);
+
+/* GaussianTracer::build_bvh (bindings.cu:30-34 -> bvh.cu:231-234 -> optix::Gas ctor :71-111, optixAccelBuild BUILD).
+ * Takes the reference caller's proxy mesh vertices_b [verts_per_surfel*N, 3] (scene/gaussian_model.py:712-723:
+ * 12 icosahedron vertices per surfel) instead of the gathered 20N-triangle soup: the bound of surfel g is the AABB
+ * of its vertices (NaN vertices -- opacity < alpha_min -- give an empty bound that no ray can hit).
+ * Morton code (30 bit) of the AABB centroid -> radix sort -> Karras hierarchy -> bottom-up bounds. */
+int irgs_build_from_proxy(irgs_tracer_t *h, const float *vertices_b, int64_t n_surfels, int verts_per_surfel, void *stream);
+/* GaussianTracer::update_bvh (bindings.cu:36-40 -> bvh.cu:236-239 -> Gas::update :113-147, optixAccelBuild UPDATE):
+ * topology frozen, bounds recomputed bottom-up.  n_surfels must equal the built count. */
+int irgs_refit_from_proxy(irgs_tracer_t *h, const float *vertices_b, int64_t n_surfels, int verts_per_surfel, void *stream);
+
+/* Native variants of the two calls above that take the surfel parameters the tracer is given anyway and derive
+ * the exact elliptical bound { alpha >= alpha_min } analytically (no 12N-vertex proxy mesh needed). */
+int irgs_build_from_surfels(irgs_tracer_t *h, const float *means3D, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, int64_t n_surfels, float alpha_min, void *stream);
+int irgs_refit_from_surfels(irgs_tracer_t *h, const float *means3D, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, int64_t n_surfels, float alpha_min, void *stream);
+
+/* Introspection for tests: number of surfels in the structure; copy of the per-surfel bounds [N,6] (lo, hi) in
+ * surfel order and of the root bound [6] to DEVICE buffers. */
+int64_t irgs_num_surfels(const irgs_tracer_t *h);
+int irgs_get_bounds(irgs_tracer_t *h, float *surfel_bounds /* [N,6] or NULL */, float *root_bound /* [6] or NULL */, void *stream);
+
+/* GaussianTracer::intersection_test (bindings.cu:61-71 -> gaussiantrace_intersection_test.cu:12-35): out[r] = 1 if
+ * ray r crosses any surfel bound support within (FLT_EPSILON, 100), else 0.  Kept for API completeness; the native
+ * trace does not need the mask/compaction pre-pass of raytracer.py:103-112. */
+int irgs_intersection_test(irgs_tracer_t *h, int64_t n_rays, const float *rays_o, const float *rays_d,
+                           const float *means3D, const float *opacity, const float *ru, const float *rv,
+                           const float *normals, float alpha_min, uint8_t *out, void *stream);
+
+/* GaussianTracer::trace_forward (bindings.cu:42-59 -> gaussiantrace_forward.cu:12-141).
+ * Outputs are OVERWRITTEN for all R rays (rays that hit nothing get exact zeros).
+ *   out_hit_count [R] int32 or NULL : number of composited hits per ray (the north-star's "hit counts").
+ *   out_hits [R, hit_cap] int32 or NULL : surfel ids in compositing order (first min(count, hit_cap) entries of each
+ *     row are valid); saved for irgs_trace_backward's replay.  hit_cap must be a multiple of 4. */
+int irgs_trace_forward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
+                       const float *rays_d, const float *means3D, const float *opacity, const float *ru,
+                       const float *rv, const float *normals, const float *features, const float *shs,
+                       float *out_color, float *out_normal, float *out_feature, float *out_depth, float *out_alpha,
+                       int32_t *out_hit_count, int32_t *out_hits, int hit_cap, float alpha_min,
+                       float transmittance_min, int back_culling, void *stream);
+
+/* GaussianTracer::trace_backward (bindings.cu:73-94 -> gaussiantrace_backward.cu:11-171).
+ * color..alpha are the forward outputs, gout_* the incoming gradients.  grad_rays_o/grad_rays_d [R,3] are
+ * OVERWRITTEN; per-surfel gradients are ACCUMULATED (atomically) into
+ *   grad_fused [N, IRGS_GRAD_STRIDE]: floats 0-2 d/dmeans3D, 3 d/dopacity, 4-6 d/dru, 7-9 d/drv, 10-12 d/dnormals,
+ *       13-15 unused, 16.. d/dshs[k][c] at 16 + 3k + c for k < 16 (coefficients k >= 16 never receive gradient);
+ *   grad_features [N,S] (may be NULL when S == 0).
+ * One buffer so that the only collective of the multi-GPU path is a single all-reduce over it.
+ * If hit_count/hits are given, rays with hit_count <= hit_cap are replayed from the saved list without touching
+ * the acceleration structure; the others (and all rays when hits == NULL) re-trace like the reference does. */
+int irgs_trace_backward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
+                        const float *rays_d, const float *means3D, const float *opacity, const float *ru,
+                        const float *rv, const float *normals, const float *features, const float *shs,
+                        const float *color, const float *normal, const float *feature, const float *depth,
+                        const float *alpha, const int32_t *hit_count, const int32_t *hits, int hit_cap,
+                        const float *gout_color, const float *gout_normal, const float *gout_feature,
+                        const float *gout_depth, const float *gout_alpha, float *grad_rays_o, float *grad_rays_d,
+                        float *grad_fused, float *grad_features, float alpha_min, float transmittance_min,
+                        int back_culling, void *stream);
+
+/* De-interleave the fused gradient buffer into the nine-tensor form raytracer.py:27-66 returns.
+ * grad_shs [N,K,3] is fully overwritten (zeros for k >= 16). */
+int irgs_unpack_grads(const float *grad_fused, int64_t n_surfels, int K, float *grad_means3D, float *grad_opacity,
+                      float *grad_ru, float *grad_rv, float *grad_normals, float *grad_shs, void *stream);
+
+/* End-to-end entry points on HOST buffers (pinned or pageable): rays are copied host->device in chunks on internal
+ * streams, traced, and results copied device->host, overlapping copies with the kernels.  Surfel arrays and the
+ * incoming-gradient arrays stay DEVICE pointers (they live on the GPU in IRGS); gout_* are [chunk_rays]-periodic
+ * device arrays (row r uses gout[r % gout_period]).  Host outputs may be NULL to skip the copy back.
+ * irgs_trace_fwd_bwd_host runs forward + backward per chunk and accumulates into grad_fused (device). */
+int irgs_trace_forward_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o_host,
+                            const float *rays_d_host, const float *means3D, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, const float *features, const float *shs,
+                            float *out_color_host, float *out_normal_host, float *out_feature_host,
+                            float *out_depth_host, float *out_alpha_host, float alpha_min, float transmittance_min,
+                            int back_culling, int64_t chunk_rays);
+int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o_host,
+                            const float *rays_d_host, const float *means3D, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, const float *features, const float *shs,
+                            const float *gout_color, const float *gout_normal, const float *gout_feature,
+                            const float *gout_depth, const float *gout_alpha, int64_t gout_period,
+                            float *out_alpha_host, float *grad_rays_o_host, float *grad_rays_d_host,
+                            float *grad_fused, float *grad_features, float alpha_min, float transmittance_min,
+                            int back_culling, int64_t chunk_rays);
+
+/* Launch counter: number of kernels this library has launched since the last irgs_reset_launch_count()
+ * (bench.py's "gpu_launches"). */
+int64_t irgs_launch_count(void);
+void irgs_reset_launch_count(void);
+
+/* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with
+ * irgs_set_stats(h, 1): sums over rays of node visits, surfel tests, composited hits, traversal passes. */
+int irgs_set_stats(irgs_tracer_t *h, int enable);
+int irgs_get_stats(irgs_tracer_t *h, int64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRGS_B200_H */

@@ -1,0 +1,375 @@
+// C ABI of libirgs_b200.so (see include/irgs_b200.h for the contract and the reference interface each entry replaces).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.cuh"
+
+namespace irgs {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const std::string &msg) { g_err = msg; }
+bool check(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev) ok = check(cudaSetDevice(dev), "cudaSetDevice");
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int fail(const char *msg) {
+    set_error(msg);
+    return 1;
+}
+
+static int validate_trace(const irgs_tracer *h, int64_t n_rays, int S, int K, int deg, int hit_cap) {
+    if (!h) return fail("null tracer handle");
+    if (!h->built) return fail("trace called before build_bvh");
+    if (n_rays < 0) return fail("n_rays < 0");
+    if (S < 0 || S > IRGS_MAX_FEATURES) return fail("feature channels S must be in [0, 12] (MAX_FEATURE_SIZE)");
+    if (deg < 0 || deg > 3) return fail("SH degree must be in [0, 3]");
+    if (K < (deg + 1) * (deg + 1)) return fail("shs.size(1) must be >= (deg+1)^2");
+    if (hit_cap < 0 || (hit_cap & 3)) return fail("hit_cap must be a non-negative multiple of 4");
+    return 0;
+}
+
+}  // namespace irgs
+
+using namespace irgs;
+
+extern "C" {
+
+const char *irgs_last_error(void) { return g_err.c_str(); }
+int irgs_version(void) { return 100; }
+
+int irgs_tracer_create(irgs_tracer_t **out, int device) {
+    if (!out) return fail("null out pointer");
+    *out = nullptr;
+    int count = 0;
+    IRGS_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail("invalid CUDA device index");
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    irgs_tracer *h = new (std::nothrow) irgs_tracer();
+    if (!h) return fail("out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    IRGS_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete h;
+        return fail("libirgs_b200 is built for sm_100a (B200) only");
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (!check(cudaMalloc(&h->scene, 16 * sizeof(float)), "cudaMalloc") ||
+        !check(cudaMalloc(&h->counter, 4 * sizeof(unsigned long long)), "cudaMalloc") ||
+        !check(cudaMalloc(&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc")) {
+        irgs_tracer_destroy(h);
+        return 1;
+    }
+    cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long));
+    *out = h;
+    return 0;
+}
+
+int irgs_tracer_destroy(irgs_tracer_t *h) {
+    if (!h) return 0;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->nodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
+    cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
+    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats);
+    for (int i = 0; i < 2; ++i) {
+        if (h->stage[i]) cudaFree(h->stage[i]);
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+        if (h->hev[i]) cudaEventDestroy(h->hev[i]);
+    }
+    delete h;
+    return 0;
+}
+
+static int build_common(irgs_tracer_t *h, int64_t n, bool refit) {
+    if (!h) return fail("null tracer handle");
+    if (n <= 0) return fail("n_surfels must be positive");
+    if (n > (int64_t)1 << 30) return fail("n_surfels too large");
+    if (refit) {
+        if (!h->built) return fail("update_bvh called before build_bvh");
+        if (n != h->n) return fail("update_bvh must keep the number of surfels unchanged");
+    } else {
+        if (lbvh_reserve(h, n)) return 1;
+        h->n = n;
+    }
+    return 0;
+}
+
+int irgs_build_from_proxy(irgs_tracer_t *h, const float *vertices_b, int64_t n, int vps, void *stream) {
+    if (build_common(h, n, false)) return 1;
+    if (vps <= 0) return fail("verts_per_surfel must be positive");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (launch_bounds_from_proxy(h, vertices_b, vps, s)) return 1;
+    return lbvh_build(h, false, s);
+}
+
+int irgs_refit_from_proxy(irgs_tracer_t *h, const float *vertices_b, int64_t n, int vps, void *stream) {
+    if (build_common(h, n, true)) return 1;
+    if (vps <= 0) return fail("verts_per_surfel must be positive");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (launch_bounds_from_proxy(h, vertices_b, vps, s)) return 1;
+    return lbvh_build(h, true, s);
+}
+
+int irgs_build_from_surfels(irgs_tracer_t *h, const float *means, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, int64_t n, float alpha_min, void *stream) {
+    if (build_common(h, n, false)) return 1;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (launch_bounds_from_surfels(h, means, opacity, ru, rv, normals, alpha_min, s)) return 1;
+    return lbvh_build(h, false, s);
+}
+
+int irgs_refit_from_surfels(irgs_tracer_t *h, const float *means, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, int64_t n, float alpha_min, void *stream) {
+    if (build_common(h, n, true)) return 1;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (launch_bounds_from_surfels(h, means, opacity, ru, rv, normals, alpha_min, s)) return 1;
+    return lbvh_build(h, true, s);
+}
+
+int64_t irgs_num_surfels(const irgs_tracer_t *h) { return h && h->built ? h->n : 0; }
+
+int irgs_get_bounds(irgs_tracer_t *h, float *surfel_bounds, float *root_bound, void *stream) {
+    if (!h || !h->built) return fail("get_bounds called before build_bvh");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (surfel_bounds)
+        IRGS_CHECK(cudaMemcpyAsync(surfel_bounds, h->boxes, sizeof(float) * 6 * (size_t)h->n, cudaMemcpyDeviceToDevice, s));
+    if (root_bound) IRGS_CHECK(cudaMemcpyAsync(root_bound, h->scene + 6, sizeof(float) * 6, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+static TraceArgs make_args(int64_t n_rays, int n_surf, int S, int K, int deg, const float *rays_o, const float *rays_d,
+                           const float *means, const float *opacity, const float *ru, const float *rv,
+                           const float *normals, const float *features, const float *shs, float alpha_min, float T_min,
+                           int back_culling) {
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_rays = n_rays; a.n_surf = n_surf; a.S = S; a.K = K; a.deg = deg; a.back_culling = back_culling ? 1 : 0;
+    a.alpha_min = alpha_min; a.T_min = T_min;
+    a.rays_o = rays_o; a.rays_d = rays_d;
+    a.means = means; a.opacity = opacity; a.ru = ru; a.rv = rv; a.normals = normals; a.features = features; a.shs = shs;
+    return a;
+}
+
+int irgs_intersection_test(irgs_tracer_t *h, int64_t n_rays, const float *rays_o, const float *rays_d,
+                           const float *means, const float *opacity, const float *ru, const float *rv,
+                           const float *normals, float alpha_min, uint8_t *out, void *stream) {
+    if (validate_trace(h, n_rays, 0, 16, 3, 0)) return 1;
+    if (n_rays == 0) return 0;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TraceArgs a = make_args(n_rays, (int)h->n, 0, 16, 3, rays_o, rays_d, means, opacity, ru, rv, normals, nullptr, nullptr,
+                            alpha_min, 0.f, 0);
+    if (launch_pack_records(h, a, s)) return 1;
+    return launch_intersection_test(h, a, out, s);
+}
+
+int irgs_trace_forward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
+                       const float *rays_d, const float *means, const float *opacity, const float *ru,
+                       const float *rv, const float *normals, const float *features, const float *shs,
+                       float *out_color, float *out_normal, float *out_feature, float *out_depth, float *out_alpha,
+                       int32_t *out_hit_count, int32_t *out_hits, int hit_cap, float alpha_min, float T_min,
+                       int back_culling, void *stream) {
+    if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
+    if (n_rays == 0) return 0;
+    if (out_hits && hit_cap == 0) out_hits = nullptr;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
+                            alpha_min, T_min, back_culling);
+    a.color = out_color; a.normal = out_normal; a.feature = out_feature; a.depth = out_depth; a.alpha = out_alpha;
+    a.hit_count = out_hit_count; a.hits = out_hits; a.hit_cap = hit_cap;
+    if (launch_pack_records(h, a, s)) return 1;
+    return launch_trace_forward(h, a, s);
+}
+
+int irgs_trace_backward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
+                        const float *rays_d, const float *means, const float *opacity, const float *ru,
+                        const float *rv, const float *normals, const float *features, const float *shs,
+                        const float *color, const float *normal, const float *feature, const float *depth,
+                        const float *alpha, const int32_t *hit_count, const int32_t *hits, int hit_cap,
+                        const float *gout_color, const float *gout_normal, const float *gout_feature,
+                        const float *gout_depth, const float *gout_alpha, float *grad_rays_o, float *grad_rays_d,
+                        float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
+                        void *stream) {
+    if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
+    if (n_rays == 0) return 0;
+    if (!grad_fused) return fail("grad_fused must not be null");
+    if (S > 0 && !grad_features) return fail("grad_features must not be null when S > 0");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
+                            alpha_min, T_min, back_culling);
+    a.color = const_cast<float *>(color); a.normal = const_cast<float *>(normal);
+    a.feature = const_cast<float *>(feature); a.depth = const_cast<float *>(depth); a.alpha = const_cast<float *>(alpha);
+    if (hits && hit_count && hit_cap > 0) {
+        a.hit_count = const_cast<int32_t *>(hit_count); a.hits = const_cast<int32_t *>(hits); a.hit_cap = hit_cap;
+    }
+    a.gC = gout_color; a.gN = gout_normal; a.gF = gout_feature; a.gD = gout_depth; a.gO = gout_alpha;
+    a.g_rays_o = grad_rays_o; a.g_rays_d = grad_rays_d; a.grad_fused = grad_fused; a.grad_features = grad_features;
+    // the re-trace path needs records consistent with the arrays handed to this call
+    if (launch_pack_records(h, a, s)) return 1;
+    return launch_trace_backward(h, a, s);
+}
+
+int irgs_unpack_grads(const float *grad_fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,
+                      float *gn, float *gsh, void *stream) {
+    if (n <= 0) return 0;
+    if (K < 1) return fail("K must be positive");
+    return launch_unpack_grads(grad_fused, n, K, gm, go, gru, grv, gn, gsh, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer path
+static int host_prepare(irgs_tracer *h, int64_t floats_per_stream) {
+    for (int i = 0; i < 2; ++i) {
+        if (!h->hs[i]) IRGS_CHECK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+        if (!h->hev[i]) IRGS_CHECK(cudaEventCreateWithFlags(&h->hev[i], cudaEventDisableTiming));
+    }
+    if (floats_per_stream > h->stage_floats) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->stage[i]) cudaFree(h->stage[i]);
+            h->stage[i] = nullptr;
+            IRGS_CHECK(cudaMalloc(&h->stage[i], sizeof(float) * (size_t)floats_per_stream));
+        }
+        h->stage_floats = floats_per_stream;
+    }
+    return 0;
+}
+
+static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, int S, int K, int deg,
+                           const float *rays_o_host, const float *rays_d_host, const float *means,
+                           const float *opacity, const float *ru, const float *rv, const float *normals,
+                           const float *features, const float *shs, const float *gC, const float *gN, const float *gF,
+                           const float *gD, const float *gO, int64_t gout_period, float *out_color_host,
+                           float *out_normal_host, float *out_feature_host, float *out_depth_host,
+                           float *out_alpha_host, float *g_rays_o_host, float *g_rays_d_host, float *grad_fused,
+                           float *grad_features, float alpha_min, float T_min, int back_culling, int64_t chunk) {
+    const int hit_cap = with_backward ? 48 : 0;
+    if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
+    if (n_rays == 0) return 0;
+    if (chunk <= 0) chunk = (int64_t)1 << 21;
+    if (chunk > n_rays) chunk = n_rays;
+    if (with_backward && !grad_fused) return fail("grad_fused must not be null");
+    if (with_backward && gout_period <= 0) return fail("gout_period must be positive");
+    DeviceGuard guard(h->device);
+    // per-stream staging layout (floats): o[3c] d[3c] color[3c] normal[3c] feature[S c] depth[c] alpha[c]
+    //                                     hit_count[c] hits[cap c] g_o[3c] g_d[3c]
+    const int64_t per_ray = 3 + 3 + 3 + 3 + S + 1 + 1 + (with_backward ? 1 + hit_cap + 6 : 0);
+    if (host_prepare(h, per_ray * chunk)) return 1;
+    IRGS_CHECK(cudaDeviceSynchronize());
+    TraceArgs base = make_args(0, (int)h->n, S, K, deg, nullptr, nullptr, means, opacity, ru, rv, normals, features, shs,
+                               alpha_min, T_min, back_culling);
+    if (launch_pack_records(h, base, h->hs[0])) return 1;
+    IRGS_CHECK(cudaEventRecord(h->hev[0], h->hs[0]));
+    IRGS_CHECK(cudaStreamWaitEvent(h->hs[1], h->hev[0], 0));
+    int64_t done = 0;
+    for (int it = 0; done < n_rays; ++it) {
+        const int si = it & 1;
+        cudaStream_t s = h->hs[si];
+        const int64_t c = (n_rays - done < chunk) ? n_rays - done : chunk;
+        float *st = h->stage[si];
+        float *d_o = st, *d_d = d_o + 3 * chunk, *d_col = d_d + 3 * chunk, *d_nrm = d_col + 3 * chunk,
+              *d_feat = d_nrm + 3 * chunk, *d_dep = d_feat + S * chunk, *d_alp = d_dep + chunk;
+        int32_t *d_cnt = reinterpret_cast<int32_t *>(d_alp + chunk);
+        int32_t *d_hits = d_cnt + chunk;
+        float *d_go = reinterpret_cast<float *>(d_hits + (int64_t)hit_cap * chunk), *d_gd = d_go + 3 * chunk;
+        IRGS_CHECK(cudaMemcpyAsync(d_o, rays_o_host + 3 * done, sizeof(float) * 3 * c, cudaMemcpyHostToDevice, s));
+        IRGS_CHECK(cudaMemcpyAsync(d_d, rays_d_host + 3 * done, sizeof(float) * 3 * c, cudaMemcpyHostToDevice, s));
+        TraceArgs a = base;
+        a.n_rays = c; a.rays_o = d_o; a.rays_d = d_d;
+        a.color = d_col; a.normal = d_nrm; a.feature = d_feat; a.depth = d_dep; a.alpha = d_alp;
+        if (with_backward) { a.hit_count = d_cnt; a.hits = d_hits; a.hit_cap = hit_cap; }
+        h->counter += si;  // each stream has its own persistent-kernel work counter
+        int rc = launch_trace_forward(h, a, s);
+        if (!rc && with_backward) {
+            a.gC = gC; a.gN = gN; a.gF = gF; a.gD = gD; a.gO = gO; a.gout_period = gout_period;
+            a.g_rays_o = d_go; a.g_rays_d = d_gd; a.grad_fused = grad_fused; a.grad_features = grad_features;
+            rc = launch_trace_backward(h, a, s);
+        }
+        h->counter -= si;
+        if (rc) return 1;
+        if (out_color_host) IRGS_CHECK(cudaMemcpyAsync(out_color_host + 3 * done, d_col, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
+        if (out_normal_host) IRGS_CHECK(cudaMemcpyAsync(out_normal_host + 3 * done, d_nrm, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
+        if (out_feature_host && S > 0) IRGS_CHECK(cudaMemcpyAsync(out_feature_host + S * done, d_feat, sizeof(float) * S * c, cudaMemcpyDeviceToHost, s));
+        if (out_depth_host) IRGS_CHECK(cudaMemcpyAsync(out_depth_host + done, d_dep, sizeof(float) * c, cudaMemcpyDeviceToHost, s));
+        if (out_alpha_host) IRGS_CHECK(cudaMemcpyAsync(out_alpha_host + done, d_alp, sizeof(float) * c, cudaMemcpyDeviceToHost, s));
+        if (with_backward && g_rays_o_host) IRGS_CHECK(cudaMemcpyAsync(g_rays_o_host + 3 * done, d_go, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
+        if (with_backward && g_rays_d_host) IRGS_CHECK(cudaMemcpyAsync(g_rays_d_host + 3 * done, d_gd, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
+        done += c;
+    }
+    IRGS_CHECK(cudaStreamSynchronize(h->hs[0]));
+    IRGS_CHECK(cudaStreamSynchronize(h->hs[1]));
+    return 0;
+}
+
+int irgs_trace_forward_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o_host,
+                            const float *rays_d_host, const float *means, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, const float *features, const float *shs,
+                            float *out_color_host, float *out_normal_host, float *out_feature_host,
+                            float *out_depth_host, float *out_alpha_host, float alpha_min, float T_min,
+                            int back_culling, int64_t chunk_rays) {
+    return trace_host_impl(h, false, n_rays, S, K, deg, rays_o_host, rays_d_host, means, opacity, ru, rv, normals,
+                           features, shs, nullptr, nullptr, nullptr, nullptr, nullptr, 0, out_color_host,
+                           out_normal_host, out_feature_host, out_depth_host, out_alpha_host, nullptr, nullptr, nullptr,
+                           nullptr, alpha_min, T_min, back_culling, chunk_rays);
+}
+
+int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o_host,
+                            const float *rays_d_host, const float *means, const float *opacity, const float *ru,
+                            const float *rv, const float *normals, const float *features, const float *shs,
+                            const float *gout_color, const float *gout_normal, const float *gout_feature,
+                            const float *gout_depth, const float *gout_alpha, int64_t gout_period,
+                            float *out_alpha_host, float *grad_rays_o_host, float *grad_rays_d_host,
+                            float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
+                            int64_t chunk_rays) {
+    return trace_host_impl(h, true, n_rays, S, K, deg, rays_o_host, rays_d_host, means, opacity, ru, rv, normals,
+                           features, shs, gout_color, gout_normal, gout_feature, gout_depth, gout_alpha, gout_period,
+                           nullptr, nullptr, nullptr, nullptr, out_alpha_host, grad_rays_o_host, grad_rays_d_host,
+                           grad_fused, grad_features, alpha_min, T_min, back_culling, chunk_rays);
+}
+
+int64_t irgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void irgs_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+int irgs_set_stats(irgs_tracer_t *h, int enable) {
+    if (!h) return fail("null tracer handle");
+    h->stats_enabled = enable ? 1 : 0;
+    return 0;
+}
+
+int irgs_get_stats(irgs_tracer_t *h, int64_t out[4]) {
+    if (!h) return fail("null tracer handle");
+    DeviceGuard guard(h->device);
+    unsigned long long tmp[4];
+    IRGS_CHECK(cudaMemcpy(tmp, h->stats, sizeof tmp, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = (int64_t)tmp[i];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// Internal declarations shared by the translation units of libirgs_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/irgs_b200.h"
+
+namespace irgs {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Acceleration structure: binary LBVH, one surfel per leaf, 64-byte nodes that hold BOTH children's bounds so one
+// node visit is four 16-byte loads (replaces the closed-source OptiX GAS of src/bvh.cu:69-160).
+//   a = (L.lo.x, L.lo.y, L.lo.z, L.hi.x)  b = (L.hi.y, L.hi.z, R.lo.x, R.lo.y)  c = (R.lo.z, R.hi.x, R.hi.y, R.hi.z)
+//   d = (left, right, parent*2+side, unused); child >= 0: internal node index; child < 0: leaf, position ~child
+//   in Morton order.  An empty child bound is stored as the degenerate far-away box EMPTY_FAR so that the slab
+//   test can never pass for it.
+// ---------------------------------------------------------------------------------------------------------------
+struct __align__(16) Node {
+    float4 a, b, c;
+    int4 d;
+};
+static_assert(sizeof(Node) == 64, "node must be 64 bytes");
+
+// Per-leaf surfel record in Morton order, packed from the caller's arrays at every trace call (64 bytes):
+//   r0 = (mu.x, mu.y, mu.z, opacity)   r1 = (n.x, n.y, n.z, bits(surfel id))
+//   r2 = (ru.x, ru.y, ru.z, rv.x)      r3 = (rv.y, rv.z, 0, 0)
+struct __align__(16) SurfelRec {
+    float4 r0, r1, r2, r3;
+};
+static_assert(sizeof(SurfelRec) == 64, "record must be 64 bytes");
+
+#define IRGS_EMPTY_FAR 1.0e30f
+
+}  // namespace irgs
+
+struct irgs_tracer {
+    int device = 0;
+    int sm_count = 148;
+    int64_t n = 0;         // surfels in the structure
+    int64_t cap = 0;       // allocated capacity (surfels)
+    irgs::Node *nodes = nullptr;        // [max(n-1,1)]
+    float *boxes = nullptr;             // [n,6] unpadded per-surfel bounds, surfel order
+    uint32_t *codes = nullptr, *codes_alt = nullptr;  // [n]
+    int *order = nullptr, *order_alt = nullptr;       // [n] leaf position -> surfel id
+    int *leaf_parent = nullptr;         // [n]   parent*2+side
+    int *node_parent = nullptr;         // [n]   parent*2+side, -1 for the root
+    int *flags = nullptr;               // [n]   bottom-up arrival counters
+    int *radix_hist = nullptr;          // [256 * n_tiles]
+    int64_t radix_tiles_cap = 0;
+    float *scene = nullptr;             // [16]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats), 12 pad
+    irgs::SurfelRec *recs = nullptr;    // [n] leaf order
+    unsigned long long *counter = nullptr;  // persistent-kernel work counter [4]
+    unsigned long long *stats = nullptr;    // [4]
+    int stats_enabled = 0;
+    bool built = false;
+    // host-streaming resources
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaEvent_t hev[2] = {nullptr, nullptr};
+    float *stage[2] = {nullptr, nullptr};
+    int64_t stage_floats = 0;
+};
+
+namespace irgs {
+
+void set_error(const std::string &msg);
+bool check(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+
+#define IRGS_CHECK(call)                                   \
+    do {                                                   \
+        if (!irgs::check((call), #call)) return 1;         \
+    } while (0)
+
+// lbvh.cu
+int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s);  // boxes[] already filled
+int lbvh_reserve(irgs_tracer *h, int64_t n);
+int launch_bounds_from_proxy(irgs_tracer *h, const float *verts, int vps, cudaStream_t s);
+int launch_bounds_from_surfels(irgs_tracer *h, const float *means, const float *opacity, const float *ru,
+                               const float *rv, const float *normals, float alpha_min, cudaStream_t s);
+
+// trace.cu
+struct TraceArgs {
+    int64_t n_rays;
+    int n_surf, S, K, deg, back_culling;
+    float alpha_min, T_min;
+    const float *rays_o, *rays_d;
+    const float *means, *opacity, *ru, *rv, *normals, *features, *shs;
+    // forward outputs / backward saved outputs
+    float *color, *normal, *feature, *depth, *alpha;
+    int32_t *hit_count, *hits;
+    int hit_cap;
+    // backward
+    const float *gC, *gN, *gF, *gD, *gO;
+    int64_t gout_period;  // 0: gout arrays have n_rays rows; >0: row r reads r % period
+    float *g_rays_o, *g_rays_d, *grad_fused, *grad_features;
+};
+int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
+int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
+int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
+int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s);
+int launch_unpack_grads(const float *fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,
+                        float *gn, float *gsh, cudaStream_t s);
+
+}  // namespace irgs

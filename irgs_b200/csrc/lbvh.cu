@@ -1,0 +1,430 @@
+// LBVH build / refit over per-surfel bounds (sm_100a).
+//
+// Replaces optix::Gas (BUILD and UPDATE) of /root/reference/submodules/surfel_tracer/src/bvh.cu:69-160, which hands a
+// 20-triangles-per-surfel soup to the closed-source optixAccelBuild.  Here the primitive is the surfel itself:
+//   1. per-surfel AABB (from the caller's proxy vertices, or analytically from the surfel parameters) + scene bounds
+//   2. 30-bit Morton code of the AABB centroid
+//   3. hand-written LSD radix sort (4 passes x 8 bits, stable; histogram -> scan -> ranked scatter)
+//   4. Karras-2012 hierarchy, one thread per internal node
+//   5. bottom-up bound propagation with arrival counters; refit (update_bvh) re-runs only steps 1 and 5.
+// All work is HBM-bound integer/float streaming over N surfels; no tensor-core shaped work exists here.
+#include <cfloat>
+#include <climits>
+
+#include "internal.cuh"
+
+namespace irgs {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void scene_init_kernel(int *scene_i) {
+    int t = threadIdx.x;
+    if (t < 3) scene_i[t] = INT_MAX;
+    else if (t < 6) scene_i[t] = INT_MIN;
+    else if (t < 16) scene_i[t] = 0;
+}
+
+__device__ __forceinline__ void scene_reduce(int *scene_i, bool valid, const float lo[3], const float hi[3]) {
+    // centroid bounds, warp-reduced before the six atomics
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float c = 0.5f * (lo[k] + hi[k]);
+        int vmin = valid ? f2ord(c) : INT_MAX, vmax = valid ? f2ord(c) : INT_MIN;
+        vmin = __reduce_min_sync(0xffffffffu, vmin);
+        vmax = __reduce_max_sync(0xffffffffu, vmax);
+        if ((threadIdx.x & 31) == 0) {
+            if (vmin != INT_MAX) atomicMin(&scene_i[k], vmin);
+            if (vmax != INT_MIN) atomicMax(&scene_i[3 + k], vmax);
+        }
+    }
+}
+
+// Step 1a: bounds from the reference caller's proxy vertices (scene/gaussian_model.py:712-723): AABB of the
+// `vps` vertices of surfel g.  fminf/fmaxf drop NaNs, so an all-NaN proxy (opacity < alpha_min) stays empty.
+__global__ void bounds_from_proxy_kernel(const float *__restrict__ verts, int vps, int n, float *__restrict__ boxes,
+                                         int *scene_i) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool valid = false;
+    if (g < n) {
+        const float *v = verts + (size_t)g * vps * 3;
+        for (int i = 0; i < vps; ++i) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float x = v[3 * i + k];
+                lo[k] = fminf(lo[k], x);
+                hi[k] = fmaxf(hi[k], x);
+            }
+        }
+        valid = lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2] && hi[0] < FLT_MAX && lo[0] > -FLT_MAX &&
+                hi[1] < FLT_MAX && lo[1] > -FLT_MAX && hi[2] < FLT_MAX && lo[2] > -FLT_MAX;
+        if (!valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { boxes[6 * (size_t)g + k] = lo[k]; boxes[6 * (size_t)g + 3 + k] = hi[k]; }
+    }
+    scene_reduce(scene_i, valid, lo, hi);
+}
+
+// Step 1b: analytic bound of { x : (ru.(x-mu))^2 + (rv.(x-mu))^2 <= 2 ln(opacity/alpha_min), n.(x-mu) = 0 }, the
+// support on which alpha >= alpha_min (the set the reference's proxy icosahedron is scaled to cover).
+__global__ void bounds_from_surfels_kernel(const float *__restrict__ means, const float *__restrict__ opacity,
+                                           const float *__restrict__ ru, const float *__restrict__ rv,
+                                           const float *__restrict__ normals, float alpha_min, int n,
+                                           float *__restrict__ boxes, int *scene_i) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool valid = false;
+    if (g < n) {
+        float op = opacity[g];
+        float nx = normals[3 * (size_t)g], ny = normals[3 * (size_t)g + 1], nz = normals[3 * (size_t)g + 2];
+        float nn = sqrtf(nx * nx + ny * ny + nz * nz);
+        if (op > alpha_min && nn > 0.0f) {
+            float r = sqrtf(2.0f * logf(op / alpha_min));
+            nx /= nn; ny /= nn; nz /= nn;
+            float e1[3], e2[3];
+            if (fabsf(nx) < 0.6f) { e1[0] = 0.f; e1[1] = -nz; e1[2] = ny; } else { e1[0] = -nz; e1[1] = 0.f; e1[2] = nx; }
+            float l1 = rsqrtf(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+            e1[0] *= l1; e1[1] *= l1; e1[2] *= l1;
+            e2[0] = ny * e1[2] - nz * e1[1]; e2[1] = nz * e1[0] - nx * e1[2]; e2[2] = nx * e1[1] - ny * e1[0];
+            const float *a = ru + 3 * (size_t)g, *b = rv + 3 * (size_t)g;
+            float m00 = a[0] * e1[0] + a[1] * e1[1] + a[2] * e1[2], m01 = a[0] * e2[0] + a[1] * e2[1] + a[2] * e2[2];
+            float m10 = b[0] * e1[0] + b[1] * e1[1] + b[2] * e1[2], m11 = b[0] * e2[0] + b[1] * e2[1] + b[2] * e2[2];
+            float det = m00 * m11 - m01 * m10;
+            if (fabsf(det) > 1e-30f) {
+                float i00 = m11 / det, i01 = -m01 / det, i10 = -m10 / det, i11 = m00 / det;
+                valid = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float c0 = e1[k] * i00 + e2[k] * i10, c1 = e1[k] * i01 + e2[k] * i11;
+                    float hk = r * sqrtf(c0 * c0 + c1 * c1);
+                    float mu = means[3 * (size_t)g + k];
+                    lo[k] = mu - hk; hi[k] = mu + hk;
+                    valid = valid && (hk < FLT_MAX) && (fabsf(mu) < FLT_MAX);
+                }
+            }
+        }
+        if (!valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { boxes[6 * (size_t)g + k] = lo[k]; boxes[6 * (size_t)g + 3 + k] = hi[k]; }
+    }
+    scene_reduce(scene_i, valid, lo, hi);
+}
+
+// Step 2: 30-bit Morton codes of the AABB centroids; invalid (empty) surfels sort to the end.
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void morton_kernel(const float *__restrict__ boxes, const int *__restrict__ scene_i, int n,
+                              uint32_t *__restrict__ codes, int *__restrict__ order) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t code = 0x3fffffffu;
+    const float *bx = boxes + 6 * (size_t)g;
+    if (bx[0] <= bx[3]) {
+        uint32_t q[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float clo = ord2f(scene_i[k]), chi = ord2f(scene_i[3 + k]);
+            float c = 0.5f * (bx[k] + bx[3 + k]);
+            float ext = chi - clo;
+            float u = ext > 0.f ? (c - clo) / ext : 0.f;
+            int v = (int)(u * 1024.0f);
+            q[k] = (uint32_t)min(max(v, 0), 1023);
+        }
+        code = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    }
+    codes[g] = code;
+    order[g] = g;
+}
+
+// Step 3: LSD radix sort, 8 bits per pass, stable.  Tile = 256 threads x 16 keys; each warp owns a contiguous
+// 512-key segment of the tile so that ranking by (warp, round, lane) preserves input order.
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t *__restrict__ keys, int n, int shift,
+                                                                int n_tiles, int *__restrict__ hist) {
+    __shared__ int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    int base = blockIdx.x * RS_TILE;
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        int idx = base + i;
+        if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & 0xff], 1);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan over hist[256 * n_tiles] (digit-major), single block
+__global__ void __launch_bounds__(1024) radix_scan_kernel(int *hist, int total) {
+    __shared__ int part[1024];
+    int per = (total + 1023) / 1024;
+    int b = threadIdx.x * per, e = min(b + per, total);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += hist[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+        int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int i = b; i < e; ++i) { int v = hist[i]; hist[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
+                                                                   const int *__restrict__ vals_in, int n, int shift,
+                                                                   int n_tiles, const int *__restrict__ hist,
+                                                                   uint32_t *__restrict__ keys_out,
+                                                                   int *__restrict__ vals_out) {
+    __shared__ int warp_hist[RS_THREADS / 32][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int seg = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS];
+    int rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int idx = seg + r * 32 + lane;
+        bool ok = idx < n;
+        key[r] = ok ? keys_in[idx] : 0u;
+        uint32_t digit = ok ? ((key[r] >> shift) & 0xff) : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        int before = __popc(peers & ((1u << lane) - 1u));
+        int basecnt = ok ? warp_hist[warp][digit] : 0;
+        __syncwarp();
+        if (ok && before == 0) warp_hist[warp][digit] = basecnt + __popc(peers);
+        __syncwarp();
+        rank[r] = basecnt + before;
+    }
+    __syncthreads();
+    {   // exclusive scan over warps per digit, plus the tile's global base
+        int d = threadIdx.x;  // 256 threads == 256 digits
+        int run = hist[d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) { int v = warp_hist[w][d]; warp_hist[w][d] = run; run += v; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int idx = seg + r * 32 + lane;
+        if (idx < n) {
+            int dst = warp_hist[warp][(key[r] >> shift) & 0xff] + rank[r];
+            keys_out[dst] = key[r];
+            vals_out[dst] = vals_in[idx];
+        }
+    }
+}
+
+// Step 4: Karras 2012.  Keys are made unique by appending the sorted position.
+__device__ __forceinline__ int lcp(const uint32_t *__restrict__ codes, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = codes[i], b = codes[j];
+    return a == b ? 32 + __clz(i ^ j) : __clz(a ^ b);
+}
+__global__ void hierarchy_kernel(const uint32_t *__restrict__ codes, int n, Node *__restrict__ nodes,
+                                 int *__restrict__ leaf_parent, int *__restrict__ node_parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 1) {
+        if (i == 0) {
+            nodes[0].d = make_int4(~0, ~0, -1, 1 /* right slot unused */);
+            leaf_parent[0] = 0;
+            node_parent[0] = -1;
+        }
+        return;
+    }
+    if (i >= n - 1) return;
+    int d = (lcp(codes, n, i, i + 1) - lcp(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lcp(codes, n, i, i - d);
+    int lmax = 2;
+    while (lcp(codes, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (lcp(codes, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lcp(codes, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (lcp(codes, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? ~gamma : gamma;
+    int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    if (left < 0) leaf_parent[gamma] = 2 * i; else node_parent[gamma] = 2 * i;
+    if (right < 0) leaf_parent[gamma + 1] = 2 * i + 1; else node_parent[gamma + 1] = 2 * i + 1;
+    if (i == 0) node_parent[0] = -1;
+    nodes[i].d = make_int4(left, right, 0, 0);
+}
+
+// Step 5: bottom-up bounds.  Each leaf thread writes its (padded) bound into its parent's slot and climbs; the
+// second arrival at a node reads the sibling slot, forms the union and continues.
+__device__ __forceinline__ void store_slot(Node *nd, int side, const float lo[3], const float hi[3]) {
+    float l[3], h[3];
+    bool empty = !(lo[0] <= hi[0]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { l[k] = empty ? IRGS_EMPTY_FAR : lo[k]; h[k] = empty ? IRGS_EMPTY_FAR : hi[k]; }
+    float *f = reinterpret_cast<float *>(nd);
+    if (side == 0) { f[0] = l[0]; f[1] = l[1]; f[2] = l[2]; f[3] = h[0]; f[4] = h[1]; f[5] = h[2]; }
+    else { f[6] = l[0]; f[7] = l[1]; f[8] = l[2]; f[9] = h[0]; f[10] = h[1]; f[11] = h[2]; }
+}
+__device__ __forceinline__ void load_slot(const Node *nd, int side, float lo[3], float hi[3]) {
+    const float *f = reinterpret_cast<const float *>(nd) + (side ? 6 : 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = __ldcg(f + k); hi[k] = __ldcg(f + 3 + k); }
+    if (lo[0] >= IRGS_EMPTY_FAR) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+    }
+}
+
+__global__ void refit_kernel(const float *__restrict__ boxes, const int *__restrict__ order,
+                             const int *__restrict__ leaf_parent, const int *__restrict__ node_parent, int n,
+                             const int *__restrict__ scene_i, Node *nodes, int *flags, float *root_bound) {
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    // absolute pad: a few float ulps of the scene scale, so that the slab test can never reject a surfel whose
+    // plane-hit arithmetic (trace.cu eval_surfel) accepts it; relative pad covers the proxy's 0.999993 in-radius
+    float scale = 1e-3f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float clo = ord2f(scene_i[k]), chi = ord2f(scene_i[3 + k]);
+        if (clo <= chi) scale = fmaxf(scale, fmaxf(chi - clo, fmaxf(fabsf(clo), fabsf(chi))));
+    }
+    const float pad_abs = 4e-6f * scale;
+    const float *bx = boxes + 6 * (size_t)order[leaf];
+    float lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = bx[k], b = bx[3 + k];
+        float pad = 1e-4f * (b - a) + pad_abs;
+        lo[k] = a - pad; hi[k] = b + pad;
+    }
+    if (!(bx[0] <= bx[3])) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+    }
+    int p = leaf_parent[leaf];
+    if (n == 1) {
+        store_slot(&nodes[0], 0, lo, hi);
+        float e_lo[3] = {INFINITY, INFINITY, INFINITY}, e_hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        store_slot(&nodes[0], 1, e_lo, e_hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { root_bound[k] = lo[k]; root_bound[3 + k] = hi[k]; }
+        return;
+    }
+    while (true) {
+        int parent = p >> 1, side = p & 1;
+        store_slot(&nodes[parent], side, lo, hi);
+        __threadfence();
+        int old = atomicAdd(&flags[parent], 1);
+        if (old == 0) return;  // first arrival: the sibling subtree is still in flight
+        float slo[3], shi[3];
+        load_slot(&nodes[parent], side ^ 1, slo, shi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], slo[k]); hi[k] = fmaxf(hi[k], shi[k]); }
+        p = node_parent[parent];
+        if (p < 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { root_bound[k] = lo[k]; root_bound[3 + k] = hi[k]; }
+            return;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <typename T>
+static bool realloc_dev(T *&p, size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return check(cudaMalloc(&p, sizeof(T) * (count ? count : 1)), "cudaMalloc");
+}
+
+int lbvh_reserve(irgs_tracer *h, int64_t n) {
+    if (n <= h->cap) return 0;
+    int64_t c = n;
+    if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
+        !realloc_dev(h->codes_alt, (size_t)c) || !realloc_dev(h->order, (size_t)c) || !realloc_dev(h->order_alt, (size_t)c) ||
+        !realloc_dev(h->leaf_parent, (size_t)c) || !realloc_dev(h->node_parent, (size_t)c) ||
+        !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c))
+        return 1;
+    int64_t tiles = (c + RS_TILE - 1) / RS_TILE;
+    if (!realloc_dev(h->radix_hist, (size_t)tiles * 256)) return 1;
+    h->radix_tiles_cap = tiles;
+    h->cap = c;
+    return 0;
+}
+
+int launch_bounds_from_proxy(irgs_tracer *h, const float *verts, int vps, cudaStream_t s) {
+    int n = (int)h->n;
+    scene_init_kernel<<<1, 32, 0, s>>>(reinterpret_cast<int *>(h->scene));
+    bounds_from_proxy_kernel<<<(n + 255) / 256, 256, 0, s>>>(verts, vps, n, h->boxes, reinterpret_cast<int *>(h->scene));
+    count_launch(2);
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_bounds_from_surfels(irgs_tracer *h, const float *means, const float *opacity, const float *ru,
+                               const float *rv, const float *normals, float alpha_min, cudaStream_t s) {
+    int n = (int)h->n;
+    scene_init_kernel<<<1, 32, 0, s>>>(reinterpret_cast<int *>(h->scene));
+    bounds_from_surfels_kernel<<<(n + 255) / 256, 256, 0, s>>>(means, opacity, ru, rv, normals, alpha_min, n, h->boxes,
+                                                               reinterpret_cast<int *>(h->scene));
+    count_launch(2);
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
+    const int n = (int)h->n;
+    int *scene_i = reinterpret_cast<int *>(h->scene);
+    if (!refit_only) {
+        morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, scene_i, n, h->codes, h->order);
+        count_launch();
+        int n_tiles = (n + RS_TILE - 1) / RS_TILE;
+        for (int pass = 0; pass < 4; ++pass) {
+            int shift = 8 * pass;
+            radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(h->codes, n, shift, n_tiles, h->radix_hist);
+            radix_scan_kernel<<<1, 1024, 0, s>>>(h->radix_hist, 256 * n_tiles);
+            radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(h->codes, h->order, n, shift, n_tiles, h->radix_hist,
+                                                               h->codes_alt, h->order_alt);
+            count_launch(3);
+            uint32_t *tc = h->codes; h->codes = h->codes_alt; h->codes_alt = tc;
+            int *to = h->order; h->order = h->order_alt; h->order_alt = to;
+        }
+        int n_int = n > 1 ? n - 1 : 1;
+        hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
+        count_launch();
+    }
+    IRGS_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(int) * (size_t)n, s));
+    refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, scene_i, h->nodes,
+                                                 h->flags, h->scene + 6);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    h->built = true;
+    return 0;
+}
+
+}  // namespace irgs

@@ -1,0 +1,676 @@
+// Forward / backward surfel tracing kernels (sm_100a, compute-only BVH traversal: B200 has no RT cores).
+//
+// Replaces the three OptiX programs of /root/reference/submodules/surfel_tracer/src/optix/:
+//   gaussiantrace_forward.cu:12-141   raygen (16-hit chunks, compositing) + any-hit (sorted k-buffer)
+//   gaussiantrace_backward.cu:11-200  raygen (re-trace, analytic gradients, 74 scalar atomics per hit)
+//   gaussiantrace_intersection_test.cu:12-35
+// and auxiliary.h:52-143 (SH colour and its backward).
+//
+// Design (DESIGN.md has the long form):
+//   * persistent warps pull 32 consecutive rays at a time from a global counter; one thread owns one ray;
+//   * per pass, a near-first stack traversal collects the K=16 nearest candidates strictly after the last
+//     composited hit into a sorted k-buffer in shared memory ([slot][thread] layout: bank-conflict free), culling
+//     nodes whose entry distance exceeds the current K-th best depth; the hits are composited front to back with
+//     early termination at T < T_min, and only rays that exhaust a full buffer without terminating start another
+//     pass.  Unlike the reference, whose any-hit sees every proxy triangle within 100 units until 16 are buffered,
+//     traversal here shrinks its range as soon as the buffer is full;
+//   * the forward optionally saves the ordered surfel ids of the composited hits; the backward replays that list
+//     (no second traversal) and adds per-surfel gradients with 16-byte vector atomics into one fused buffer.
+//   * the depth of a hit is computed with the same explicit sequence of IEEE operations as oracle/surfel_oracle.c,
+//     so the hit order is bit-identical to the oracle's.
+#include <cfloat>
+#include <climits>
+
+#include "internal.cuh"
+
+namespace irgs {
+
+constexpr int TB = 128;     // threads per block
+constexpr int KBUF = 16;    // k-buffer depth (MAX_BUFFER_SIZE, auxiliary.h:10)
+constexpr int STACK = 64;   // traversal stack entries (LBVH depth <= 30 code bits + 32 index bits)
+constexpr float T_EPS = 1.1920929e-07f;  // FLT_EPSILON tmin, gaussiantrace_forward.cu:38
+constexpr int NFMAX = IRGS_MAX_FEATURES;
+
+// auxiliary.h:16-33
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
+                           SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
+__device__ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
+                           SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
+                           SH_C3_6 = -0.5900435899266435f;
+
+struct KParams {
+    TraceArgs a;
+    const Node *nodes;
+    const SurfelRec *recs;
+    unsigned long long *counter;
+    unsigned long long *stats;
+};
+
+// fixed-order dot product, bit-identical to dot3() of oracle/surfel_oracle.c
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+}
+
+// SH basis Y_k(d), zero beyond (deg+1)^2  (auxiliary.h:52-89)
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float Y[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) Y[k] = 0.f;
+    Y[0] = SH_C0;
+    if (deg > 0) {
+        Y[1] = -SH_C1 * y; Y[2] = SH_C1 * z; Y[3] = -SH_C1 * x;
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            Y[4] = SH_C2_0 * xy; Y[5] = SH_C2_1 * yz; Y[6] = SH_C2_2 * (2.0f * zz - xx - yy);
+            Y[7] = SH_C2_3 * xz; Y[8] = SH_C2_4 * (xx - yy);
+            if (deg > 2) {
+                Y[9] = SH_C3_0 * y * (3.0f * xx - yy);
+                Y[10] = SH_C3_1 * xy * z;
+                Y[11] = SH_C3_2 * y * (4.0f * zz - xx - yy);
+                Y[12] = SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                Y[13] = SH_C3_4 * x * (4.0f * zz - xx - yy);
+                Y[14] = SH_C3_5 * z * (xx - yy);
+                Y[15] = SH_C3_6 * x * (xx - 3.0f * yy);
+            }
+        }
+    }
+}
+
+// colour = max(0, 0.5 + sum_k Y_k sh[g,k])   (auxiliary.h:52-89).  K == 16: twelve 16-byte loads at most.
+__device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, int deg, int g, const float Y[16],
+                                         float c[3]) {
+    const int nb = (deg + 1) * (deg + 1);
+    float acc[3] = {0.f, 0.f, 0.f};
+    if (K == 16) {
+        const float4 *p = reinterpret_cast<const float4 *>(shs + (size_t)g * 48);
+        const int nvec = (nb * 3 + 3) >> 2;
+#pragma unroll
+        for (int v = 0; v < 12; ++v) {
+            if (v < nvec) {
+                float4 q = __ldg(p + v);
+                acc[(4 * v) % 3] += Y[(4 * v) / 3] * q.x;
+                acc[(4 * v + 1) % 3] += Y[(4 * v + 1) / 3] * q.y;
+                acc[(4 * v + 2) % 3] += Y[(4 * v + 2) / 3] * q.z;
+                acc[(4 * v + 3) % 3] += Y[(4 * v + 3) / 3] * q.w;
+            }
+        }
+    } else {
+        const float *p = shs + (size_t)g * K * 3;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k < nb) {
+                acc[0] += Y[k] * __ldg(p + 3 * k);
+                acc[1] += Y[k] * __ldg(p + 3 * k + 1);
+                acc[2] += Y[k] * __ldg(p + 3 * k + 2);
+            }
+        }
+    }
+    c[0] = fmaxf(acc[0] + 0.5f, 0.f);
+    c[1] = fmaxf(acc[1] + 0.5f, 0.f);
+    c[2] = fmaxf(acc[2] + 0.5f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ pack
+// Gather the caller's five per-surfel arrays into 64-byte records in leaf (Morton) order, once per trace call,
+// so that one leaf test is two (early reject) or four 16-byte loads from adjacent lines.
+__global__ void pack_records_kernel(const int *__restrict__ order, int n, const float *__restrict__ means,
+                                    const float *__restrict__ opacity, const float *__restrict__ ru,
+                                    const float *__restrict__ rv, const float *__restrict__ normals,
+                                    SurfelRec *__restrict__ recs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int g = order[i];
+    const float *m = means + 3 * (size_t)g, *nn = normals + 3 * (size_t)g, *a = ru + 3 * (size_t)g, *b = rv + 3 * (size_t)g;
+    SurfelRec r;
+    r.r0 = make_float4(m[0], m[1], m[2], opacity[g]);
+    r.r1 = make_float4(nn[0], nn[1], nn[2], __int_as_float(g));
+    r.r2 = make_float4(a[0], a[1], a[2], b[0]);
+    r.r3 = make_float4(b[1], b[2], 0.f, 0.f);
+    recs[i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------ traversal
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz;
+    float idx, idy, idz, oodx, oody, oodz;
+    float slack;
+};
+
+__device__ __forceinline__ void ray_setup(RayCtx &r) {
+    // a zero direction component would give inf * 0 = NaN in the slab test: nudge it (the slack term below then
+    // disables culling along that axis instead of producing garbage)
+    const float tiny = 1e-30f;
+    float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
+    float sy = fabsf(r.dy) > tiny ? r.dy : copysignf(tiny, r.dy);
+    float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
+    r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
+    r.oodx = r.ox * r.idx; r.oody = r.oy * r.idy; r.oodz = r.oz * r.idz;
+    // fma(lo, id, -ood) carries an absolute error of ~ulp(ood): widen the interval test by 4 ulp of the largest
+    float m = fmaxf(fmaxf(fabsf(r.oodx), fabsf(r.oody)), fmaxf(fabsf(r.oodz), 1.0f));
+    r.slack = m * 4.8e-7f;
+}
+
+__device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                     float t_lo, float t_hi, float &tn) {
+    float x0 = __fmaf_rn(lox, r.idx, -r.oodx), x1 = __fmaf_rn(hix, r.idx, -r.oodx);
+    float y0 = __fmaf_rn(loy, r.idy, -r.oody), y1 = __fmaf_rn(hiy, r.idy, -r.oody);
+    float z0 = __fmaf_rn(loz, r.idz, -r.oodz), z1 = __fmaf_rn(hiz, r.idz, -r.oodz);
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+    return tn <= tf + r.slack;
+}
+
+// Plane hit of a packed record.  Arithmetic order == eval_surfel() of oracle/surfel_oracle.c
+// (gaussiantrace_forward.cu:61-81).  Returns true for a compositing candidate.
+__device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
+                                          int back_culling, float &t_out, int &g_out, float &alpha_out) {
+    const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1);
+    float relx = __fsub_rn(r.ox, r0.x), rely = __fsub_rn(r.oy, r0.y), relz = __fsub_rn(r.oz, r0.z);
+    float og = dot3_rn(r1.x, r1.y, r1.z, relx, rely, relz);
+    float dg = dot3_rn(r1.x, r1.y, r1.z, r.dx, r.dy, r.dz);
+    float dg2 = __fmul_rn(dg, dg);
+    float den = fmaxf(1e-6f, dg2);
+    float t = __fdiv_rn(__fmul_rn(-og, dg), den);
+    if (!(dg2 >= 1e-6f)) return false;  // grazing pair: the clamped formula is no longer the geometric hit (see oracle)
+    if (!(t > T_EPS && t < IRGS_T_SCENE_MAX)) return false;
+    if (back_culling && !(-dg > 0.0f)) return false;
+    const float4 r2 = __ldg(&rec->r2), r3 = __ldg(&rec->r3);
+    float px = __fmaf_rn(t, r.dx, relx), py = __fmaf_rn(t, r.dy, rely), pz = __fmaf_rn(t, r.dz, relz);
+    float pu = dot3_rn(r2.x, r2.y, r2.z, px, py, pz);
+    float pv = dot3_rn(r2.w, r3.x, r3.y, px, py, pz);
+    float power = __fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv)));
+    float alpha = fminf(0.99f, __fmul_rn(r0.w, __expf(power)));
+    if (alpha < alpha_min) return false;
+    t_out = t; g_out = __float_as_int(r1.w); alpha_out = alpha;
+    return true;
+}
+
+__device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }
+
+// One pass: collect the <= KBUF nearest candidates strictly after (t_last, g_last), ascending, into the shared
+// k-buffer columns of this thread.  Returns the number collected.
+template <bool STATS>
+__device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, float t_last, int g_last, float *bt, int *bg,
+                                            float *ba, int *stack_n, float *stack_t, unsigned &n_nodes, unsigned &n_leaf) {
+    int cnt = 0;
+    float t_hi = IRGS_T_SCENE_MAX;
+    const float t_lo = fmaxf(t_last, 0.0f);
+    int sp = 0;
+    int cur = 0;  // root
+    const float alpha_min = p.a.alpha_min;
+    const int back_culling = p.a.back_culling;
+    for (;;) {
+        if (cur >= 0) {
+            const Node *nd = p.nodes + cur;
+            const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
+            const int4 d = __ldg(&nd->d);
+            if (STATS) ++n_nodes;
+            float tnL, tnR;
+            bool hL = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, t_lo, t_hi, tnL);
+            bool hR = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, t_lo, t_hi, tnR);
+            if (hL && hR) {
+                bool rightNear = tnR < tnL;
+                int nearC = rightNear ? d.y : d.x, farC = rightNear ? d.x : d.y;
+                float farT = rightNear ? tnL : tnR;
+                if (sp < STACK) { stack_n[sp] = farC; stack_t[sp] = farT; ++sp; }
+                cur = nearC;
+                continue;
+            } else if (hL) { cur = d.x; continue; }
+            else if (hR) { cur = d.y; continue; }
+        } else {
+            if (STATS) ++n_leaf;
+            float t, alpha; int g;
+            if (leaf_test(r, p.recs + (~cur), alpha_min, back_culling, t, g, alpha)) {
+                bool after = key_less(t_last, g_last, t, g);
+                bool fits = cnt < KBUF || key_less(t, g, bt[(KBUF - 1) * TB], bg[(KBUF - 1) * TB]);
+                if (after && fits) {
+                    int i = cnt < KBUF ? cnt++ : KBUF - 1;
+                    while (i > 0 && key_less(t, g, bt[(i - 1) * TB], bg[(i - 1) * TB])) {
+                        bt[i * TB] = bt[(i - 1) * TB]; bg[i * TB] = bg[(i - 1) * TB]; ba[i * TB] = ba[(i - 1) * TB];
+                        --i;
+                    }
+                    bt[i * TB] = t; bg[i * TB] = g; ba[i * TB] = alpha;
+                    if (cnt == KBUF) t_hi = bt[(KBUF - 1) * TB];
+                }
+            }
+        }
+        // pop, skipping entries that the shrinking range has made unreachable
+        for (;;) {
+            if (sp == 0) return cnt;
+            --sp;
+            if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <bool FEAT, bool STATS>
+__global__ void __launch_bounds__(TB) trace_forward_kernel(const KParams p) {
+    __shared__ float s_t[KBUF * TB];
+    __shared__ int s_g[KBUF * TB];
+    __shared__ float s_a[KBUF * TB];
+    float *bt = s_t + threadIdx.x; int *bg = s_g + threadIdx.x; float *ba = s_a + threadIdx.x;
+    int stack_n[STACK]; float stack_t[STACK];
+    const int lane = threadIdx.x & 31;
+    const TraceArgs &a = p.a;
+    unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)a.n_rays) break;
+        const int64_t ray = (int64_t)base + lane;
+        if (ray < a.n_rays) {
+            RayCtx r;
+            r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
+            r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
+            ray_setup(r);
+            float Y[16];
+            sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
+            float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, O = 0.f;
+            float F[FEAT ? NFMAX : 1];
+#pragma unroll
+            for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
+            float t_last = -INFINITY; int g_last = -1;
+            int total = 0;
+            for (;;) {
+                unsigned nn = 0, nl = 0;
+                const int cnt = collect_pass<STATS>(p, r, t_last, g_last, bt, bg, ba, stack_n, stack_t, nn, nl);
+                if (STATS) { st_nodes += nn; st_leaf += nl; st_pass += 1; }
+                bool term = false;
+                int i = 0;
+                for (; i < cnt; ++i) {
+                    const float t = bt[i * TB], alpha = ba[i * TB];
+                    const int g = bg[i * TB];
+                    const float nx = __ldg(a.normals + 3 * (size_t)g), ny = __ldg(a.normals + 3 * (size_t)g + 1),
+                                nz = __ldg(a.normals + 3 * (size_t)g + 2);
+                    const float dg = dot3_rn(nx, ny, nz, r.dx, r.dy, r.dz);
+                    const float m = (-dg > 0.f) ? 1.f : -1.f;
+                    float c[3];
+                    sh_color(a.shs, a.K, a.deg, g, Y, c);
+                    const float w = T * alpha;
+                    C0 += w * c[0]; C1 += w * c[1]; C2 += w * c[2];
+                    N0 += w * m * nx; N1 += w * m * ny; N2 += w * m * nz;
+                    D += w * t; O += w;
+                    if (FEAT) {
+#pragma unroll
+                        for (int j = 0; j < NFMAX; ++j)
+                            if (j < a.S) F[j] += w * __ldg(a.features + (size_t)g * a.S + j);
+                    }
+                    T *= (1.f - alpha);
+                    if (a.hits != nullptr && total + i < a.hit_cap) a.hits[ray * a.hit_cap + total + i] = g;
+                    if (T < a.T_min) { term = true; ++i; break; }
+                }
+                total += i;
+                if (term || cnt < KBUF) break;
+                t_last = bt[(KBUF - 1) * TB]; g_last = bg[(KBUF - 1) * TB];
+            }
+            a.color[3 * ray] = C0; a.color[3 * ray + 1] = C1; a.color[3 * ray + 2] = C2;
+            a.normal[3 * ray] = N0; a.normal[3 * ray + 1] = N1; a.normal[3 * ray + 2] = N2;
+            a.depth[ray] = D; a.alpha[ray] = O;
+            if (FEAT) {
+#pragma unroll
+                for (int j = 0; j < NFMAX; ++j)
+                    if (j < a.S) a.feature[ray * a.S + j] = F[j];
+            }
+            if (a.hit_count != nullptr) a.hit_count[ray] = total;
+            if (STATS) st_hits += total;
+        }
+        __syncwarp();
+    }
+    if (STATS) {
+        atomicAdd(p.stats + 0, st_nodes); atomicAdd(p.stats + 1, st_leaf);
+        atomicAdd(p.stats + 2, st_hits); atomicAdd(p.stats + 3, st_pass);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+template <bool FEAT>
+struct BwdState {
+    float T, C[3], N[3], D, O;
+    float Cf[3], Nf[3], Df, Of;
+    float gC[3], gN[3], gD, gO;
+    float go[3], gd[3];
+    float F[FEAT ? NFMAX : 1], Ff[FEAT ? NFMAX : 1], gF[FEAT ? NFMAX : 1];
+};
+
+template <bool FEAT>
+__device__ __forceinline__ void bwd_load(const TraceArgs &a, int64_t ray, BwdState<FEAT> &s) {
+    const int64_t gr = a.gout_period > 0 ? ray % a.gout_period : ray;
+    s.T = 1.f; s.D = 0.f; s.O = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        s.C[j] = 0.f; s.N[j] = 0.f; s.go[j] = 0.f; s.gd[j] = 0.f;
+        s.Cf[j] = a.color[3 * ray + j]; s.Nf[j] = a.normal[3 * ray + j];
+        s.gC[j] = __ldg(a.gC + 3 * gr + j); s.gN[j] = __ldg(a.gN + 3 * gr + j);
+    }
+    s.Df = a.depth[ray]; s.Of = a.alpha[ray];
+    s.gD = __ldg(a.gD + gr); s.gO = __ldg(a.gO + gr);
+    if (FEAT) {
+#pragma unroll
+        for (int j = 0; j < NFMAX; ++j) {
+            s.F[j] = 0.f;
+            s.Ff[j] = j < a.S ? a.feature[ray * a.S + j] : 0.f;
+            s.gF[j] = j < a.S ? __ldg(a.gF + gr * a.S + j) : 0.f;
+        }
+    }
+}
+
+// One hit of the backward replay: gaussiantrace_backward.cu:61-166 verbatim in its formulas (no derivative masks
+// for min(0.99,.) / max(.,0), no SH-direction term, division by the raw d_g), with the 13+48 scalar atomics of the
+// reference replaced by 16-byte vector reductions into the fused per-surfel gradient row.
+template <bool FEAT>
+__device__ __forceinline__ void bwd_hit(const TraceArgs &a, const RayCtx &r, const float Y[16], int g, BwdState<FEAT> &s) {
+    const float *pm = a.means + 3 * (size_t)g, *pn = a.normals + 3 * (size_t)g, *pa = a.ru + 3 * (size_t)g,
+                *pb = a.rv + 3 * (size_t)g;
+    const float mx = __ldg(pm), my = __ldg(pm + 1), mz = __ldg(pm + 2);
+    const float nx = __ldg(pn), ny = __ldg(pn + 1), nz = __ldg(pn + 2);
+    const float ax = __ldg(pa), ay = __ldg(pa + 1), az = __ldg(pa + 2);
+    const float bx = __ldg(pb), by = __ldg(pb + 1), bz = __ldg(pb + 2);
+    const float op = __ldg(a.opacity + g);
+    const float relx = __fsub_rn(r.ox, mx), rely = __fsub_rn(r.oy, my), relz = __fsub_rn(r.oz, mz);
+    const float og = dot3_rn(nx, ny, nz, relx, rely, relz);
+    const float dg = dot3_rn(nx, ny, nz, r.dx, r.dy, r.dz);
+    const float den = fmaxf(1e-6f, __fmul_rn(dg, dg));
+    const float t = __fdiv_rn(__fmul_rn(-og, dg), den);
+    const float m = (-dg > 0.f) ? 1.f : -1.f;
+    const float px = __fmaf_rn(t, r.dx, relx), py = __fmaf_rn(t, r.dy, rely), pz = __fmaf_rn(t, r.dz, relz);
+    const float pu = dot3_rn(ax, ay, az, px, py, pz), pv = dot3_rn(bx, by, bz, px, py, pz);
+    const float G = __expf(__fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv))));
+    const float alpha = fminf(0.99f, __fmul_rn(op, G));
+    float c[3];
+    sh_color(a.shs, a.K, a.deg, g, Y, c);
+    const float w = s.T * alpha;
+    const float nf[3] = {m * nx, m * ny, m * nz};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { s.C[j] += w * c[j]; s.N[j] += w * nf[j]; }
+    s.D += w * t; s.O += w;
+    float feat[FEAT ? NFMAX : 1];
+    if (FEAT) {
+#pragma unroll
+        for (int j = 0; j < NFMAX; ++j) {
+            feat[j] = j < a.S ? __ldg(a.features + (size_t)g * a.S + j) : 0.f;
+            s.F[j] += w * feat[j];
+        }
+    }
+    s.T *= (1.f - alpha);
+    const float T = s.T;
+    float dL_dalpha = s.gD * (T * t - (s.Df - s.D)) + s.gO * (1.f - s.Of);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        dL_dalpha += s.gC[j] * (T * c[j] - (s.Cf[j] - s.C[j])) + s.gN[j] * (T * nf[j] - (s.Nf[j] - s.N[j]));
+    if (FEAT) {
+#pragma unroll
+        for (int j = 0; j < NFMAX; ++j) dL_dalpha += s.gF[j] * (T * feat[j] - (s.Ff[j] - s.F[j]));
+    }
+    dL_dalpha /= (1.f - alpha);
+    const float dL_do = dL_dalpha * G;
+    const float dL_dG = dL_dalpha * op;
+    const float dpu = -dL_dG * G * pu, dpv = -dL_dG * G * pv;
+    const float dposx = dpu * ax + dpv * bx, dposy = dpu * ay + dpv * by, dposz = dpu * az + dpv * bz;
+    const float dL_dd = s.gD * w + (dposx * r.dx + dposy * r.dy + dposz * r.dz);
+    const float dL_dog = -dL_dd / dg;
+    const float dL_ddg = dL_dd * og / fmaxf(1e-6f, dg * dg);
+    s.go[0] += dposx + dL_dog * nx; s.go[1] += dposy + dL_dog * ny; s.go[2] += dposz + dL_dog * nz;
+    s.gd[0] += t * dposx + dL_ddg * nx; s.gd[1] += t * dposy + dL_ddg * ny; s.gd[2] += t * dposz + dL_ddg * nz;
+    const float dnx = m * s.gN[0] * w + dL_ddg * r.dx + dL_dog * relx;
+    const float dny = m * s.gN[1] * w + dL_ddg * r.dy + dL_dog * rely;
+    const float dnz = m * s.gN[2] * w + dL_ddg * r.dz + dL_dog * relz;
+    float4 *row = reinterpret_cast<float4 *>(a.grad_fused + (size_t)g * IRGS_GRAD_STRIDE);
+    atomicAdd(row + 0, make_float4(-dposx - dL_dog * nx, -dposy - dL_dog * ny, -dposz - dL_dog * nz, dL_do));
+    atomicAdd(row + 1, make_float4(dpu * px, dpu * py, dpu * pz, dpv * px));
+    atomicAdd(row + 2, make_float4(dpv * py, dpv * pz, dnx, dny));
+    atomicAdd(reinterpret_cast<float *>(row + 3), dnz);
+    // SH coefficients: Y_k * dL/dc, dL/dc = grad_color * w  (auxiliary.h:91-143)
+    const float gc[3] = {s.gC[0] * w, s.gC[1] * w, s.gC[2] * w};
+    const int nvec = ((a.deg + 1) * (a.deg + 1) * 3 + 3) >> 2;
+#pragma unroll
+    for (int v = 0; v < 12; ++v) {
+        if (v < nvec) {
+            float4 q;
+            q.x = Y[(4 * v) / 3] * gc[(4 * v) % 3];
+            q.y = Y[(4 * v + 1) / 3] * gc[(4 * v + 1) % 3];
+            q.z = Y[(4 * v + 2) / 3] * gc[(4 * v + 2) % 3];
+            q.w = Y[(4 * v + 3) / 3] * gc[(4 * v + 3) % 3];
+            atomicAdd(row + 4 + v, q);
+        }
+    }
+    if (FEAT) {
+#pragma unroll
+        for (int j = 0; j < NFMAX; ++j)
+            if (j < a.S) atomicAdd(a.grad_features + (size_t)g * a.S + j, s.gF[j] * w);
+    }
+}
+
+__device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
+    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
+    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
+}
+
+// Replay of the saved hit lists: one thread per ray, no traversal.
+template <bool FEAT>
+__global__ void __launch_bounds__(TB) trace_backward_replay_kernel(const KParams p) {
+    const TraceArgs &a = p.a;
+    const int64_t ray = (int64_t)blockIdx.x * TB + threadIdx.x;
+    if (ray >= a.n_rays) return;
+    const int cnt = a.hit_count[ray];
+    float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+    // gaussiantrace_backward.cu:13-14: rays whose forward alpha is exactly zero contribute nothing
+    if (cnt > 0 && cnt <= a.hit_cap && a.alpha[ray] != 0.f) {
+        RayCtx r;
+        load_ray(a, ray, r);
+        float Y[16];
+        sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
+        BwdState<FEAT> s;
+        bwd_load<FEAT>(a, ray, s);
+        const int32_t *hl = a.hits + ray * a.hit_cap;
+        for (int i = 0; i < cnt; ++i) bwd_hit<FEAT>(a, r, Y, __ldg(hl + i), s);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { go[j] = s.go[j]; gd[j] = s.gd[j]; }
+    }
+    if (cnt <= a.hit_cap) {  // rays with longer lists are written by the re-trace kernel
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { a.g_rays_o[3 * ray + j] = go[j]; a.g_rays_d[3 * ray + j] = gd[j]; }
+    }
+}
+
+// Re-trace backward (the reference's scheme): same ordered passes as the forward, gradients applied per hit.
+// With ONLY_OVERFLOW it handles just the rays whose hit list did not fit in hit_cap.
+template <bool FEAT, bool ONLY_OVERFLOW>
+__global__ void __launch_bounds__(TB) trace_backward_retrace_kernel(const KParams p) {
+    __shared__ float s_t[KBUF * TB];
+    __shared__ int s_g[KBUF * TB];
+    __shared__ float s_a[KBUF * TB];
+    float *bt = s_t + threadIdx.x; int *bg = s_g + threadIdx.x; float *ba = s_a + threadIdx.x;
+    int stack_n[STACK]; float stack_t[STACK];
+    const int lane = threadIdx.x & 31;
+    const TraceArgs &a = p.a;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)a.n_rays) break;
+        const int64_t ray = (int64_t)base + lane;
+        bool mine = ray < a.n_rays;
+        if (mine && ONLY_OVERFLOW) mine = a.hit_count[ray] > a.hit_cap;
+        if (mine) {
+            float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+            if (a.alpha[ray] != 0.f) {
+                RayCtx r;
+                load_ray(a, ray, r);
+                ray_setup(r);
+                float Y[16];
+                sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
+                BwdState<FEAT> s;
+                bwd_load<FEAT>(a, ray, s);
+                float t_last = -INFINITY; int g_last = -1;
+                for (;;) {
+                    unsigned nn = 0, nl = 0;
+                    const int cnt = collect_pass<false>(p, r, t_last, g_last, bt, bg, ba, stack_n, stack_t, nn, nl);
+                    bool term = false;
+                    for (int i = 0; i < cnt; ++i) {
+                        bwd_hit<FEAT>(a, r, Y, bg[i * TB], s);
+                        if (s.T < a.T_min) { term = true; break; }
+                    }
+                    if (term || cnt < KBUF) break;
+                    t_last = bt[(KBUF - 1) * TB]; g_last = bg[(KBUF - 1) * TB];
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { go[j] = s.go[j]; gd[j] = s.gd[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { a.g_rays_o[3 * ray + j] = go[j]; a.g_rays_d[3 * ray + j] = gd[j]; }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ misc kernels
+// gaussiantrace_intersection_test.cu:12-35: any surfel support crossed within (FLT_EPSILON, 100).
+__global__ void __launch_bounds__(TB) intersection_test_kernel(const KParams p, uint8_t *__restrict__ out) {
+    const TraceArgs &a = p.a;
+    const int64_t ray = (int64_t)blockIdx.x * TB + threadIdx.x;
+    if (ray >= a.n_rays) return;
+    RayCtx r;
+    load_ray(a, ray, r);
+    ray_setup(r);
+    int stack_n[STACK];
+    int sp = 0, cur = 0;
+    bool found = false;
+    for (;;) {
+        if (cur >= 0) {
+            const Node *nd = p.nodes + cur;
+            const float4 qa = __ldg(&nd->a), qb = __ldg(&nd->b), qc = __ldg(&nd->c);
+            const int4 d = __ldg(&nd->d);
+            float tnL, tnR;
+            bool hL = slab(r, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, 0.f, IRGS_T_SCENE_MAX, tnL);
+            bool hR = slab(r, qb.z, qb.w, qc.x, qc.y, qc.z, qc.w, 0.f, IRGS_T_SCENE_MAX, tnR);
+            if (hL && hR) { if (sp < STACK) stack_n[sp++] = d.y; cur = d.x; continue; }
+            else if (hL) { cur = d.x; continue; }
+            else if (hR) { cur = d.y; continue; }
+        } else {
+            float t, alpha; int g;
+            if (leaf_test(r, p.recs + (~cur), a.alpha_min, 0, t, g, alpha)) { found = true; break; }
+        }
+        if (sp == 0) break;
+        cur = stack_n[--sp];
+    }
+    out[ray] = found ? 1 : 0;
+}
+
+__global__ void unpack_grads_kernel(const float *__restrict__ fused, int64_t n, int K, float *__restrict__ gm,
+                                    float *__restrict__ go, float *__restrict__ gru, float *__restrict__ grv,
+                                    float *__restrict__ gn, float *__restrict__ gsh) {
+    // one thread per (surfel, float of the 64-float row): coalesced reads, near-coalesced writes
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * IRGS_GRAD_STRIDE) return;
+    const int64_t g = idx / IRGS_GRAD_STRIDE;
+    const int f = (int)(idx % IRGS_GRAD_STRIDE);
+    const float v = fused[idx];
+    if (f < 3) gm[3 * g + f] = v;
+    else if (f == 3) go[g] = v;
+    else if (f < 7) gru[3 * g + f - 4] = v;
+    else if (f < 10) grv[3 * g + f - 7] = v;
+    else if (f < 13) gn[3 * g + f - 10] = v;
+    else if (f >= 16) {
+        int k = (f - 16) / 3;
+        if (k < K) gsh[(g * K + k) * 3 + (f - 16) % 3] = v;
+    }
+}
+__global__ void zero_sh_tail_kernel(int64_t n, int K, float *__restrict__ gsh) {
+    // coefficients k >= 16 never receive gradient
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tail = (K - 16) * 3;
+    if (idx >= n * tail) return;
+    const int64_t g = idx / tail;
+    gsh[g * K * 3 + 48 + idx % tail] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static int persistent_grid(irgs_tracer *h, const void *kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TB, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return h->sm_count * per_sm;
+}
+
+static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
+    KParams p;
+    p.a = a;
+    p.nodes = h->nodes;
+    p.recs = h->recs;
+    p.counter = h->counter;
+    p.stats = h->stats;
+    return p;
+}
+
+int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+    const int n = (int)h->n;
+    pack_records_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->order, n, a.means, a.opacity, a.ru, a.rv, a.normals, h->recs);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <typename Kern>
+static int launch_persistent(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_rays, cudaStream_t s) {
+    IRGS_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), s));
+    int grid = persistent_grid(h, reinterpret_cast<const void *>(kern));
+    int64_t need = (n_rays + TB - 1) / TB;
+    if (need < grid) grid = (int)(need > 0 ? need : 1);
+    kern<<<grid, TB, 0, s>>>(p);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+    KParams p = make_params(h, a);
+    const bool feat = a.S > 0, stats = h->stats_enabled != 0;
+    if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
+    if (feat) return stats ? launch_persistent(h, trace_forward_kernel<true, true>, p, a.n_rays, s)
+                           : launch_persistent(h, trace_forward_kernel<true, false>, p, a.n_rays, s);
+    return stats ? launch_persistent(h, trace_forward_kernel<false, true>, p, a.n_rays, s)
+                 : launch_persistent(h, trace_forward_kernel<false, false>, p, a.n_rays, s);
+}
+
+int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+    KParams p = make_params(h, a);
+    const bool feat = a.S > 0;
+    if (a.hits != nullptr && a.hit_count != nullptr) {
+        const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
+        if (feat) trace_backward_replay_kernel<true><<<grid, TB, 0, s>>>(p);
+        else trace_backward_replay_kernel<false><<<grid, TB, 0, s>>>(p);
+        count_launch();
+        IRGS_CHECK(cudaGetLastError());
+        return feat ? launch_persistent(h, trace_backward_retrace_kernel<true, true>, p, a.n_rays, s)
+                    : launch_persistent(h, trace_backward_retrace_kernel<false, true>, p, a.n_rays, s);
+    }
+    return feat ? launch_persistent(h, trace_backward_retrace_kernel<true, false>, p, a.n_rays, s)
+                : launch_persistent(h, trace_backward_retrace_kernel<false, false>, p, a.n_rays, s);
+}
+
+int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s) {
+    KParams p = make_params(h, a);
+    const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
+    intersection_test_kernel<<<grid, TB, 0, s>>>(p, out);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_unpack_grads(const float *fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv, float *gn,
+                        float *gsh, cudaStream_t s) {
+    const int64_t total = n * IRGS_GRAD_STRIDE;
+    unpack_grads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(fused, n, K, gm, go, gru, grv, gn, gsh);
+    count_launch();
+    if (K > 16) {
+        const int64_t tail = n * (K - 16) * 3;
+        zero_sh_tail_kernel<<<(unsigned)((tail + 255) / 256), 256, 0, s>>>(n, K, gsh);
+        count_launch();
+    }
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace irgs

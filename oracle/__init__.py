@@ -40,6 +40,11 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def set_variant(k=16, opacity_cull=False, t_min=0.03):
+    """Traversal-design experiments on the CPU (never changes results; the canonical counters use the default)."""
+    lib().oracle_set_variant(ctypes.c_int(k), ctypes.c_int(int(opacity_cull)), ctypes.c_float(t_min))
+
+
 def num_threads():
     return int(lib().oracle_num_threads())
 

@@ -45,7 +45,18 @@
 
 #define T_SCENE_MAX 100.0f          /* auxiliary.h:11 */
 #define T_EPS 1.1920929e-07f        /* FLT_EPSILON, gaussiantrace_forward.cu:38 */
-#define ORACLE_K 16                 /* MAX_BUFFER_SIZE, auxiliary.h:10 */
+#define ORACLE_K_MAX 64
+/* k-buffer depth and termination-aware culling of the LBVH walk.  The CANONICAL structure that defines the
+ * per-ray counters V, P, H is K = 16 (MAX_BUFFER_SIZE, auxiliary.h:10) without the opacity bound;
+ * oracle_set_variant() exists to evaluate traversal designs on the CPU and never changes results. */
+static int ORACLE_K = 16;
+static int ORACLE_OPACITY_CULL = 0;
+static float ORACLE_T_MIN_CULL = 0.0f;
+void oracle_set_variant(int k, int opacity_cull, float t_min) {
+    ORACLE_K = k < 1 ? 1 : (k > ORACLE_K_MAX ? ORACLE_K_MAX : k);
+    ORACLE_OPACITY_CULL = opacity_cull;
+    ORACLE_T_MIN_CULL = t_min;
+}
 #define MAX_FEATURE_SIZE 12         /* auxiliary.h:12 */
 
 /* auxiliary.h:16-33 */
@@ -286,8 +297,8 @@ static inline int box_hit(const float *lo, const float *hi, v3 o, v3 inv, float 
 /* Collect the <=16 nearest candidates strictly after (t_last, g_last), sorted ascending. */
 static int collect_bvh(const Lbvh *b, v3 o, v3 d, float t_last, int g_last, const float *means,
                        const float *opacity, const float *ru, const float *rv, const float *normals,
-                       float alpha_min, int back_culling, Hit *buf, int64_t *cnt /* V,P */) {
-    int nbuf = 0;
+                       float alpha_min, int back_culling, Hit *buf, int64_t *cnt /* V,P */, float T_start) {
+    int nbuf = 0, term = 0;
     if (b->n == 0) return 0;
     v3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
     int stack[128]; float stack_t[128]; int sp = 0;
@@ -295,16 +306,27 @@ static int collect_bvh(const Lbvh *b, v3 o, v3 d, float t_last, int g_last, cons
     /* the slab test is padded so that it can never reject a surfel the exact arithmetic of eval_surfel accepts */
     const float pad = 1e-4f;
     for (;;) {
-        float tmax = (nbuf == ORACLE_K) ? buf[ORACLE_K - 1].t : T_SCENE_MAX;
+        float tmax = (nbuf == ORACLE_K || term) ? buf[nbuf - 1].t : T_SCENE_MAX;
         if (cur < 0) {
             int g = ~cur; Hit h; float raw;
             cnt[1]++;
             if (eval_surfel(o, d, g, means, opacity, ru, rv, normals, alpha_min, back_culling, &h, &raw)) {
                 int after = h.t > t_last || (h.t == t_last && h.g > g_last);
-                if (after && (nbuf < ORACLE_K || hit_less(&h, &buf[ORACLE_K - 1]))) {
+                int full = (nbuf == ORACLE_K || term);
+                if (after && (!full || hit_less(&h, &buf[nbuf - 1]))) {
                     int i = (nbuf < ORACLE_K) ? nbuf++ : ORACLE_K - 1;
+                    term = 0;
                     while (i > 0 && hit_less(&h, &buf[i - 1])) { buf[i] = buf[i - 1]; --i; }
                     buf[i] = h;
+                    if (ORACLE_OPACITY_CULL) {
+                        /* the buffered hits alone already drive T below T_min at entry j: nothing beyond j can ever be
+                         * composited, so the buffer (and the traversal range) ends there */
+                        float T = T_start;
+                        for (int j = 0; j < nbuf; ++j) {
+                            T *= (1.0f - buf[j].alpha);
+                            if (T < ORACLE_T_MIN_CULL) { nbuf = j + 1; term = 1; break; }
+                        }
+                    }
                 }
             }
         } else if (cur_t <= tmax + pad) {
@@ -356,7 +378,7 @@ typedef int (*visit_fn)(const Hit *h, void *ctx);
 
 static void walk_ray(const Lbvh *bvh, int n_surf, v3 o, v3 d, const float *means, const float *opacity,
                      const float *ru, const float *rv, const float *normals, float alpha_min, int back_culling,
-                     visit_fn visit, void *ctx, int64_t *cnt, float *alpha_margin) {
+                     visit_fn visit, void *ctx, int64_t *cnt, float *alpha_margin, const float *T_cur) {
     if (!bvh) {
         Hit *all = NULL; int n_all = 0, cap = 0;
         for (int g = 0; g < n_surf; ++g) {
@@ -378,8 +400,8 @@ static void walk_ray(const Lbvh *bvh, int n_surf, v3 o, v3 d, const float *means
     }
     float t_last = -INFINITY; int g_last = -1;
     for (;;) {
-        Hit buf[ORACLE_K];
-        int nb = collect_bvh(bvh, o, d, t_last, g_last, means, opacity, ru, rv, normals, alpha_min, back_culling, buf, cnt);
+        Hit buf[ORACLE_K_MAX];
+        int nb = collect_bvh(bvh, o, d, t_last, g_last, means, opacity, ru, rv, normals, alpha_min, back_culling, buf, cnt, *T_cur);
         int stop = 0;
         for (int i = 0; i < nb; ++i) if (!visit(&buf[i], ctx)) { stop = 1; break; }
         if (stop || nb < ORACLE_K) break;
@@ -430,7 +452,7 @@ int oracle_trace_forward(int64_t n_rays, int n_surf, int S, int K, int deg, int 
         c.T_margin = INFINITY; c.min_dt = INFINITY;
         int64_t cnt[2] = {0, 0}; float am = INFINITY;
         walk_ray((const Lbvh *)bvh, n_surf, o, c.d, means, opacity, ru, rv, normals, alpha_min, back_culling,
-                 fwd_visit, &c, cnt, &am);
+                 fwd_visit, &c, cnt, &am, &c.T);
         for (int j = 0; j < 3; ++j) { out_color[3 * r + j] = c.C[j]; out_normal[3 * r + j] = c.N[j]; }
         for (int j = 0; j < S; ++j) out_feature[r * S + j] = c.F[j];
         out_depth[r] = c.D; out_alpha[r] = c.O;
@@ -546,7 +568,7 @@ int oracle_trace_backward(int64_t n_rays, int n_surf, int S, int K, int deg, int
         c.G_features = G_f; c.G_shs = G_sh;
         int64_t cnt[2] = {0, 0};
         walk_ray((const Lbvh *)bvh, n_surf, c.o, c.d, means, opacity, ru, rv, normals, alpha_min, back_culling,
-                 bwd_visit, &c, cnt, NULL);
+                 bwd_visit, &c, cnt, NULL, &c.T);
         for (int j = 0; j < 3; ++j) { grad_rays_o[3 * r + j] = (float)c.g_o[j]; grad_rays_d[3 * r + j] = (float)c.g_d[j]; }
     }
     for (size_t i = 0; i < 3 * n; ++i) {

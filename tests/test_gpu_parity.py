@@ -307,7 +307,7 @@ def test_api_shapes_and_edge_cases(small_scene):
                     synth.ALPHA_MIN)
     assert all(not t.any() for t in outs) and not tr.last_hit_count.any()
     # non-contiguous inputs are accepted (raytracer.py:85-96 calls .contiguous())
-    o2 = torch.stack([o, o], -1)[..., 0].to(DEV)
+    o2 = torch.stack([o, o], -1).to(DEV)[..., 0]
     assert not o2.is_contiguous()
     tr.trace(o2, d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], None, g["shs"], synth.ALPHA_MIN)
 

@@ -108,8 +108,8 @@ int irgs_unpack_grads(const float *grad_fused, int64_t n_surfels, int K, float *
 
 /* End-to-end entry points on HOST buffers (pinned or pageable): rays are copied host->device in chunks on internal
  * streams, traced, and results copied device->host, overlapping copies with the kernels.  Surfel arrays and the
- * incoming-gradient arrays stay DEVICE pointers (they live on the GPU in IRGS); gout_* are [chunk_rays]-periodic
- * device arrays (row r uses gout[r % gout_period]).  Host outputs may be NULL to skip the copy back.
+ * incoming-gradient arrays stay DEVICE pointers (they live on the GPU in IRGS); gout_* are periodic device arrays
+ * with gout_period rows (ray r of the whole batch uses row r % gout_period).  Host outputs may be NULL to skip the copy back.
  * irgs_trace_fwd_bwd_host runs forward + backward per chunk and accumulates into grad_fused (device). */
 int irgs_trace_forward_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o_host,
                             const float *rays_d_host, const float *means3D, const float *opacity, const float *ru,

@@ -308,7 +308,7 @@ static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, i
         h->counter += si;  // each stream has its own persistent-kernel work counter
         int rc = launch_trace_forward(h, a, s);
         if (!rc && with_backward) {
-            a.gC = gC; a.gN = gN; a.gF = gF; a.gD = gD; a.gO = gO; a.gout_period = gout_period;
+            a.gC = gC; a.gN = gN; a.gF = gF; a.gD = gD; a.gO = gO; a.gout_period = gout_period; a.gout_offset = done;
             a.g_rays_o = d_go; a.g_rays_d = d_gd; a.grad_fused = grad_fused; a.grad_features = grad_features;
             rc = launch_trace_backward(h, a, s);
         }

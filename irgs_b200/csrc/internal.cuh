@@ -92,7 +92,8 @@ struct TraceArgs {
     int hit_cap;
     // backward
     const float *gC, *gN, *gF, *gD, *gO;
-    int64_t gout_period;  // 0: gout arrays have n_rays rows; >0: row r reads r % period
+    int64_t gout_period;  // 0: gout arrays have n_rays rows; >0: ray r reads row (gout_offset + r) % period
+    int64_t gout_offset;
     float *g_rays_o, *g_rays_d, *grad_fused, *grad_features;
 };
 int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);

@@ -244,7 +244,21 @@ __device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, f
     }
 }
 
+__device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
+    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
+    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
+}
+
 // ------------------------------------------------------------------------------------------------ forward
+// Persistent "dynamic fetch" kernel.  Every lane owns one ray and runs a small state machine
+//   FETCH -> TRAV (one k-buffer pass of the BVH walk) -> COMP (composite the buffer) -> TRAV (next pass) | FETCH
+// A lane that finishes its ray pulls the next one from the global counter immediately instead of waiting for the
+// slowest ray of its warp (ray costs vary by more than 10x: ~40 node visits for a miss, >500 for a ray with two
+// passes).  The warp leaves the traversal loop to composite / refill once fewer than MIN_ACTIVE lanes are still
+// walking, which keeps the SIMT utilisation of the hot loop above MIN_ACTIVE/32.
+enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2 };
+constexpr int MIN_ACTIVE = 20;
+
 template <bool FEAT, bool STATS>
 __global__ void __launch_bounds__(TB) trace_forward_kernel(const KParams p) {
     __shared__ float s_t[KBUF * TB];
@@ -252,72 +266,157 @@ __global__ void __launch_bounds__(TB) trace_forward_kernel(const KParams p) {
     __shared__ float s_a[KBUF * TB];
     float *bt = s_t + threadIdx.x; int *bg = s_g + threadIdx.x; float *ba = s_a + threadIdx.x;
     int stack_n[STACK]; float stack_t[STACK];
-    const int lane = threadIdx.x & 31;
+    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    const unsigned FULL = 0xffffffffu;
     const TraceArgs &a = p.a;
+    const float alpha_min = a.alpha_min;
+    const int back_culling = a.back_culling;
     unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
+
+    int phase = PH_FETCH;
+    bool pool_empty = false;  // warp-uniform
+    int64_t ray = 0;
+    RayCtx r;
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, O = 0.f;
+    float F[FEAT ? NFMAX : 1];
+    float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
+    int g_last = -1, total = 0, cnt = 0, sp = 0, cur = 0;
+    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = r.slack = 0.f;
+#pragma unroll
+    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
+
     for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(p.counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned long long)a.n_rays) break;
-        const int64_t ray = (int64_t)base + lane;
-        if (ray < a.n_rays) {
-            RayCtx r;
-            r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
-            r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
-            ray_setup(r);
+        // ---- refill idle lanes
+        const unsigned need = __ballot_sync(FULL, phase == PH_FETCH);
+        if (need != 0u && !pool_empty) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (phase == PH_FETCH) {
+                ray = (int64_t)base + __popc(need & lt_mask);
+                if (ray < a.n_rays) {
+                    load_ray(a, ray, r);
+                    ray_setup(r);
+                    T = 1.f; C0 = C1 = C2 = N0 = N1 = N2 = D = O = 0.f;
+#pragma unroll
+                    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
+                    t_last = -INFINITY; g_last = -1; total = 0;
+                    cnt = 0; sp = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX;
+                    phase = PH_TRAV;
+                    if (STATS) ++st_pass;
+                }
+            }
+            if (base + (unsigned long long)__popc(need) >= (unsigned long long)a.n_rays) pool_empty = true;
+        }
+        unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);
+        if (trav == 0u && __ballot_sync(FULL, phase == PH_COMP) == 0u) break;  // pool empty and every lane idle
+
+        // ---- BVH walk: one node or leaf per iteration and lane
+        const int thr = pool_empty ? 1 : MIN_ACTIVE;
+        while (__popc(trav) >= thr) {
+            if (phase == PH_TRAV) {
+                bool pop = true;
+                if (cur >= 0) {
+                    const Node *nd = p.nodes + cur;
+                    const float4 qa = __ldg(&nd->a), qb = __ldg(&nd->b), qc = __ldg(&nd->c);
+                    const int4 qd = __ldg(&nd->d);
+                    if (STATS) ++st_nodes;
+                    float tnL, tnR;
+                    const bool hL = slab(r, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, t_lo, t_hi, tnL);
+                    const bool hR = slab(r, qb.z, qb.w, qc.x, qc.y, qc.z, qc.w, t_lo, t_hi, tnR);
+                    if (hL && hR) {
+                        const bool rightNear = tnR < tnL;
+                        if (sp < STACK) { stack_n[sp] = rightNear ? qd.x : qd.y; stack_t[sp] = rightNear ? tnL : tnR; ++sp; }
+                        cur = rightNear ? qd.y : qd.x;
+                        pop = false;
+                    } else if (hL) { cur = qd.x; pop = false; }
+                    else if (hR) { cur = qd.y; pop = false; }
+                } else {
+                    if (STATS) ++st_leaf;
+                    float t, alpha; int g;
+                    if (leaf_test(r, p.recs + (~cur), alpha_min, back_culling, t, g, alpha)) {
+                        const bool after = key_less(t_last, g_last, t, g);
+                        const bool fits = cnt < KBUF || key_less(t, g, bt[(KBUF - 1) * TB], bg[(KBUF - 1) * TB]);
+                        if (after && fits) {
+                            int i = cnt < KBUF ? cnt++ : KBUF - 1;
+                            while (i > 0 && key_less(t, g, bt[(i - 1) * TB], bg[(i - 1) * TB])) {
+                                bt[i * TB] = bt[(i - 1) * TB]; bg[i * TB] = bg[(i - 1) * TB]; ba[i * TB] = ba[(i - 1) * TB];
+                                --i;
+                            }
+                            bt[i * TB] = t; bg[i * TB] = g; ba[i * TB] = alpha;
+                            // Termination-aware range: once the buffered hits alone drive the transmittance below
+                            // T_min at entry j, nothing behind entry j can ever be composited (closer hits found later
+                            // only lower T further), so the buffer and the walk end there.  Exact, see DESIGN.md.
+                            float Tc = T;
+                            for (int j = 0; j < cnt; ++j) {
+                                Tc *= (1.f - ba[j * TB]);
+                                if (Tc < a.T_min) { cnt = j + 1; t_hi = bt[j * TB]; break; }
+                            }
+                            if (cnt == KBUF) t_hi = bt[(KBUF - 1) * TB];
+                        }
+                    }
+                }
+                if (pop) {
+                    for (;;) {
+                        if (sp == 0) { phase = PH_COMP; break; }
+                        --sp;
+                        if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
+                    }
+                }
+            }
+            trav = __ballot_sync(FULL, phase == PH_TRAV);
+            if (trav == 0u) break;
+        }
+
+        // ---- composite the buffer of lanes whose pass is complete
+        if (phase == PH_COMP) {
             float Y[16];
             sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
-            float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, O = 0.f;
-            float F[FEAT ? NFMAX : 1];
+            bool term = false;
+            int i = 0;
+            for (; i < cnt; ++i) {
+                const float t = bt[i * TB], alpha = ba[i * TB];
+                const int g = bg[i * TB];
+                const float nx = __ldg(a.normals + 3 * (size_t)g), ny = __ldg(a.normals + 3 * (size_t)g + 1),
+                            nz = __ldg(a.normals + 3 * (size_t)g + 2);
+                const float dg = dot3_rn(nx, ny, nz, r.dx, r.dy, r.dz);
+                const float m = (-dg > 0.f) ? 1.f : -1.f;
+                float c[3];
+                sh_color(a.shs, a.K, a.deg, g, Y, c);
+                const float w = T * alpha;
+                C0 += w * c[0]; C1 += w * c[1]; C2 += w * c[2];
+                N0 += w * m * nx; N1 += w * m * ny; N2 += w * m * nz;
+                D += w * t; O += w;
+                if (FEAT) {
 #pragma unroll
-            for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
-            float t_last = -INFINITY; int g_last = -1;
-            int total = 0;
-            for (;;) {
-                unsigned nn = 0, nl = 0;
-                const int cnt = collect_pass<STATS>(p, r, t_last, g_last, bt, bg, ba, stack_n, stack_t, nn, nl);
-                if (STATS) { st_nodes += nn; st_leaf += nl; st_pass += 1; }
-                bool term = false;
-                int i = 0;
-                for (; i < cnt; ++i) {
-                    const float t = bt[i * TB], alpha = ba[i * TB];
-                    const int g = bg[i * TB];
-                    const float nx = __ldg(a.normals + 3 * (size_t)g), ny = __ldg(a.normals + 3 * (size_t)g + 1),
-                                nz = __ldg(a.normals + 3 * (size_t)g + 2);
-                    const float dg = dot3_rn(nx, ny, nz, r.dx, r.dy, r.dz);
-                    const float m = (-dg > 0.f) ? 1.f : -1.f;
-                    float c[3];
-                    sh_color(a.shs, a.K, a.deg, g, Y, c);
-                    const float w = T * alpha;
-                    C0 += w * c[0]; C1 += w * c[1]; C2 += w * c[2];
-                    N0 += w * m * nx; N1 += w * m * ny; N2 += w * m * nz;
-                    D += w * t; O += w;
-                    if (FEAT) {
-#pragma unroll
-                        for (int j = 0; j < NFMAX; ++j)
-                            if (j < a.S) F[j] += w * __ldg(a.features + (size_t)g * a.S + j);
-                    }
-                    T *= (1.f - alpha);
-                    if (a.hits != nullptr && total + i < a.hit_cap) a.hits[ray * a.hit_cap + total + i] = g;
-                    if (T < a.T_min) { term = true; ++i; break; }
+                    for (int j = 0; j < NFMAX; ++j)
+                        if (j < a.S) F[j] += w * __ldg(a.features + (size_t)g * a.S + j);
                 }
-                total += i;
-                if (term || cnt < KBUF) break;
+                T *= (1.f - alpha);
+                if (a.hits != nullptr && total + i < a.hit_cap) a.hits[ray * a.hit_cap + total + i] = g;
+                if (T < a.T_min) { term = true; ++i; break; }
+            }
+            total += i;
+            if (!term && cnt == KBUF) {  // buffer exhausted without terminating: next pass, strictly after the last hit
                 t_last = bt[(KBUF - 1) * TB]; g_last = bg[(KBUF - 1) * TB];
-            }
-            a.color[3 * ray] = C0; a.color[3 * ray + 1] = C1; a.color[3 * ray + 2] = C2;
-            a.normal[3 * ray] = N0; a.normal[3 * ray + 1] = N1; a.normal[3 * ray + 2] = N2;
-            a.depth[ray] = D; a.alpha[ray] = O;
-            if (FEAT) {
+                cnt = 0; sp = 0; cur = 0; t_lo = fmaxf(t_last, 0.f); t_hi = IRGS_T_SCENE_MAX;
+                phase = PH_TRAV;
+                if (STATS) ++st_pass;
+            } else {
+                a.color[3 * ray] = C0; a.color[3 * ray + 1] = C1; a.color[3 * ray + 2] = C2;
+                a.normal[3 * ray] = N0; a.normal[3 * ray + 1] = N1; a.normal[3 * ray + 2] = N2;
+                a.depth[ray] = D; a.alpha[ray] = O;
+                if (FEAT) {
 #pragma unroll
-                for (int j = 0; j < NFMAX; ++j)
-                    if (j < a.S) a.feature[ray * a.S + j] = F[j];
+                    for (int j = 0; j < NFMAX; ++j)
+                        if (j < a.S) a.feature[ray * a.S + j] = F[j];
+                }
+                if (a.hit_count != nullptr) a.hit_count[ray] = total;
+                if (STATS) st_hits += total;
+                phase = PH_FETCH;
             }
-            if (a.hit_count != nullptr) a.hit_count[ray] = total;
-            if (STATS) st_hits += total;
         }
-        __syncwarp();
     }
     if (STATS) {
         atomicAdd(p.stats + 0, st_nodes); atomicAdd(p.stats + 1, st_leaf);
@@ -337,7 +436,7 @@ struct BwdState {
 
 template <bool FEAT>
 __device__ __forceinline__ void bwd_load(const TraceArgs &a, int64_t ray, BwdState<FEAT> &s) {
-    const int64_t gr = a.gout_period > 0 ? ray % a.gout_period : ray;
+    const int64_t gr = a.gout_period > 0 ? (a.gout_offset + ray) % a.gout_period : ray;
     s.T = 1.f; s.D = 0.f; s.O = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -441,11 +540,6 @@ __device__ __forceinline__ void bwd_hit(const TraceArgs &a, const RayCtx &r, con
         for (int j = 0; j < NFMAX; ++j)
             if (j < a.S) atomicAdd(a.grad_features + (size_t)g * a.S + j, s.gF[j] * w);
     }
-}
-
-__device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
-    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
-    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
 }
 
 // Replay of the saved hit lists: one thread per ray, no traversal.

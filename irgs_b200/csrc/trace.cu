@@ -18,98 +18,9 @@
 //     (no second traversal) and adds per-surfel gradients with 16-byte vector atomics into one fused buffer.
 //   * the depth of a hit is computed with the same explicit sequence of IEEE operations as oracle/surfel_oracle.c,
 //     so the hit order is bit-identical to the oracle's.
-#include <cfloat>
-#include <climits>
-
-#include "internal.cuh"
+#include "trace_common.cuh"
 
 namespace irgs {
-
-constexpr int TB = 128;     // threads per block
-constexpr int KBUF = 16;    // k-buffer depth (MAX_BUFFER_SIZE, auxiliary.h:10)
-constexpr int STACK = 64;   // traversal stack entries (LBVH depth <= 30 code bits + 32 index bits)
-constexpr float T_EPS = 1.1920929e-07f;  // FLT_EPSILON tmin, gaussiantrace_forward.cu:38
-constexpr int NFMAX = IRGS_MAX_FEATURES;
-
-// auxiliary.h:16-33
-__device__ constexpr float SH_C0 = 0.28209479177387814f;
-__device__ constexpr float SH_C1 = 0.4886025119029199f;
-__device__ constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
-                           SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
-__device__ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
-                           SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
-                           SH_C3_6 = -0.5900435899266435f;
-
-struct KParams {
-    TraceArgs a;
-    const Node *nodes;
-    const SurfelRec *recs;
-    unsigned long long *counter;
-    unsigned long long *stats;
-};
-
-// fixed-order dot product, bit-identical to dot3() of oracle/surfel_oracle.c
-__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
-    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
-}
-
-// SH basis Y_k(d), zero beyond (deg+1)^2  (auxiliary.h:52-89)
-__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float Y[16]) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) Y[k] = 0.f;
-    Y[0] = SH_C0;
-    if (deg > 0) {
-        Y[1] = -SH_C1 * y; Y[2] = SH_C1 * z; Y[3] = -SH_C1 * x;
-        if (deg > 1) {
-            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            Y[4] = SH_C2_0 * xy; Y[5] = SH_C2_1 * yz; Y[6] = SH_C2_2 * (2.0f * zz - xx - yy);
-            Y[7] = SH_C2_3 * xz; Y[8] = SH_C2_4 * (xx - yy);
-            if (deg > 2) {
-                Y[9] = SH_C3_0 * y * (3.0f * xx - yy);
-                Y[10] = SH_C3_1 * xy * z;
-                Y[11] = SH_C3_2 * y * (4.0f * zz - xx - yy);
-                Y[12] = SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                Y[13] = SH_C3_4 * x * (4.0f * zz - xx - yy);
-                Y[14] = SH_C3_5 * z * (xx - yy);
-                Y[15] = SH_C3_6 * x * (xx - 3.0f * yy);
-            }
-        }
-    }
-}
-
-// colour = max(0, 0.5 + sum_k Y_k sh[g,k])   (auxiliary.h:52-89).  K == 16: twelve 16-byte loads at most.
-__device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, int deg, int g, const float Y[16],
-                                         float c[3]) {
-    const int nb = (deg + 1) * (deg + 1);
-    float acc[3] = {0.f, 0.f, 0.f};
-    if (K == 16) {
-        const float4 *p = reinterpret_cast<const float4 *>(shs + (size_t)g * 48);
-        const int nvec = (nb * 3 + 3) >> 2;
-#pragma unroll
-        for (int v = 0; v < 12; ++v) {
-            if (v < nvec) {
-                float4 q = __ldg(p + v);
-                acc[(4 * v) % 3] += Y[(4 * v) / 3] * q.x;
-                acc[(4 * v + 1) % 3] += Y[(4 * v + 1) / 3] * q.y;
-                acc[(4 * v + 2) % 3] += Y[(4 * v + 2) / 3] * q.z;
-                acc[(4 * v + 3) % 3] += Y[(4 * v + 3) / 3] * q.w;
-            }
-        }
-    } else {
-        const float *p = shs + (size_t)g * K * 3;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            if (k < nb) {
-                acc[0] += Y[k] * __ldg(p + 3 * k);
-                acc[1] += Y[k] * __ldg(p + 3 * k + 1);
-                acc[2] += Y[k] * __ldg(p + 3 * k + 2);
-            }
-        }
-    }
-    c[0] = fmaxf(acc[0] + 0.5f, 0.f);
-    c[1] = fmaxf(acc[1] + 0.5f, 0.f);
-    c[2] = fmaxf(acc[2] + 0.5f, 0.f);
-}
 
 // ------------------------------------------------------------------------------------------------ pack
 // Gather the caller's five per-surfel arrays into 64-byte records in leaf (Morton) order, once per trace call,
@@ -129,64 +40,6 @@ __global__ void pack_records_kernel(const int *__restrict__ order, int n, const 
     r.r3 = make_float4(b[1], b[2], 0.f, 0.f);
     recs[i] = r;
 }
-
-// ------------------------------------------------------------------------------------------------ traversal
-struct RayCtx {
-    float ox, oy, oz, dx, dy, dz;
-    float idx, idy, idz, oodx, oody, oodz;
-    float slack;
-};
-
-__device__ __forceinline__ void ray_setup(RayCtx &r) {
-    // a zero direction component would give inf * 0 = NaN in the slab test: nudge it (the slack term below then
-    // disables culling along that axis instead of producing garbage)
-    const float tiny = 1e-30f;
-    float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
-    float sy = fabsf(r.dy) > tiny ? r.dy : copysignf(tiny, r.dy);
-    float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
-    r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
-    r.oodx = r.ox * r.idx; r.oody = r.oy * r.idy; r.oodz = r.oz * r.idz;
-    // fma(lo, id, -ood) carries an absolute error of ~ulp(ood): widen the interval test by 4 ulp of the largest
-    float m = fmaxf(fmaxf(fabsf(r.oodx), fabsf(r.oody)), fmaxf(fabsf(r.oodz), 1.0f));
-    r.slack = m * 4.8e-7f;
-}
-
-__device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
-                                     float t_lo, float t_hi, float &tn) {
-    float x0 = __fmaf_rn(lox, r.idx, -r.oodx), x1 = __fmaf_rn(hix, r.idx, -r.oodx);
-    float y0 = __fmaf_rn(loy, r.idy, -r.oody), y1 = __fmaf_rn(hiy, r.idy, -r.oody);
-    float z0 = __fmaf_rn(loz, r.idz, -r.oodz), z1 = __fmaf_rn(hiz, r.idz, -r.oodz);
-    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
-    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
-    return tn <= tf + r.slack;
-}
-
-// Plane hit of a packed record.  Arithmetic order == eval_surfel() of oracle/surfel_oracle.c
-// (gaussiantrace_forward.cu:61-81).  Returns true for a compositing candidate.
-__device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
-                                          int back_culling, float &t_out, int &g_out, float &alpha_out) {
-    const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1);
-    float relx = __fsub_rn(r.ox, r0.x), rely = __fsub_rn(r.oy, r0.y), relz = __fsub_rn(r.oz, r0.z);
-    float og = dot3_rn(r1.x, r1.y, r1.z, relx, rely, relz);
-    float dg = dot3_rn(r1.x, r1.y, r1.z, r.dx, r.dy, r.dz);
-    float dg2 = __fmul_rn(dg, dg);
-    float den = fmaxf(1e-6f, dg2);
-    float t = __fdiv_rn(__fmul_rn(-og, dg), den);
-    if (!(dg2 >= 1e-6f)) return false;  // grazing pair: the clamped formula is no longer the geometric hit (see oracle)
-    if (!(t > T_EPS && t < IRGS_T_SCENE_MAX)) return false;
-    if (back_culling && !(-dg > 0.0f)) return false;
-    const float4 r2 = __ldg(&rec->r2), r3 = __ldg(&rec->r3);
-    float px = __fmaf_rn(t, r.dx, relx), py = __fmaf_rn(t, r.dy, rely), pz = __fmaf_rn(t, r.dz, relz);
-    float pu = dot3_rn(r2.x, r2.y, r2.z, px, py, pz);
-    float pv = dot3_rn(r2.w, r3.x, r3.y, px, py, pz);
-    float power = __fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv)));
-    float alpha = fminf(0.99f, __fmul_rn(r0.w, __expf(power)));
-    if (alpha < alpha_min) return false;
-    t_out = t; g_out = __float_as_int(r1.w); alpha_out = alpha;
-    return true;
-}
-
-__device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }
 
 // One pass: collect the <= KBUF nearest candidates strictly after (t_last, g_last), ascending, into the shared
 // k-buffer columns of this thread.  Returns the number collected.
@@ -241,186 +94,6 @@ __device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, f
             --sp;
             if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
         }
-    }
-}
-
-__device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
-    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
-    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
-}
-
-// ------------------------------------------------------------------------------------------------ forward
-// Persistent "dynamic fetch" kernel.  Every lane owns one ray and runs a small state machine
-//   FETCH -> TRAV (one k-buffer pass of the BVH walk) -> COMP (composite the buffer) -> TRAV (next pass) | FETCH
-// A lane that finishes its ray pulls the next one from the global counter immediately instead of waiting for the
-// slowest ray of its warp (ray costs vary by more than 10x: ~40 node visits for a miss, >500 for a ray with two
-// passes).  The warp leaves the traversal loop to composite / refill once fewer than MIN_ACTIVE lanes are still
-// walking, which keeps the SIMT utilisation of the hot loop above MIN_ACTIVE/32.
-enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2 };
-constexpr int MIN_ACTIVE = 20;
-
-template <bool FEAT, bool STATS>
-__global__ void __launch_bounds__(TB) trace_forward_kernel(const KParams p) {
-    __shared__ float s_t[KBUF * TB];
-    __shared__ int s_g[KBUF * TB];
-    __shared__ float s_a[KBUF * TB];
-    float *bt = s_t + threadIdx.x; int *bg = s_g + threadIdx.x; float *ba = s_a + threadIdx.x;
-    int stack_n[STACK]; float stack_t[STACK];
-    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
-    const unsigned FULL = 0xffffffffu;
-    const TraceArgs &a = p.a;
-    const float alpha_min = a.alpha_min;
-    const int back_culling = a.back_culling;
-    unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
-
-    int phase = PH_FETCH;
-    bool pool_empty = false;  // warp-uniform
-    int64_t ray = 0;
-    RayCtx r;
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, O = 0.f;
-    float F[FEAT ? NFMAX : 1];
-    float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
-    int g_last = -1, total = 0, cnt = 0, sp = 0, cur = 0;
-    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = r.slack = 0.f;
-#pragma unroll
-    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
-
-    for (;;) {
-        // ---- refill idle lanes
-        const unsigned need = __ballot_sync(FULL, phase == PH_FETCH);
-        if (need != 0u && !pool_empty) {
-            const int leader = __ffs(need) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (phase == PH_FETCH) {
-                ray = (int64_t)base + __popc(need & lt_mask);
-                if (ray < a.n_rays) {
-                    load_ray(a, ray, r);
-                    ray_setup(r);
-                    T = 1.f; C0 = C1 = C2 = N0 = N1 = N2 = D = O = 0.f;
-#pragma unroll
-                    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
-                    t_last = -INFINITY; g_last = -1; total = 0;
-                    cnt = 0; sp = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX;
-                    phase = PH_TRAV;
-                    if (STATS) ++st_pass;
-                }
-            }
-            if (base + (unsigned long long)__popc(need) >= (unsigned long long)a.n_rays) pool_empty = true;
-        }
-        unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);
-        if (trav == 0u && __ballot_sync(FULL, phase == PH_COMP) == 0u) break;  // pool empty and every lane idle
-
-        // ---- BVH walk: one node or leaf per iteration and lane
-        const int thr = pool_empty ? 1 : MIN_ACTIVE;
-        while (__popc(trav) >= thr) {
-            if (phase == PH_TRAV) {
-                bool pop = true;
-                if (cur >= 0) {
-                    const Node *nd = p.nodes + cur;
-                    const float4 qa = __ldg(&nd->a), qb = __ldg(&nd->b), qc = __ldg(&nd->c);
-                    const int4 qd = __ldg(&nd->d);
-                    if (STATS) ++st_nodes;
-                    float tnL, tnR;
-                    const bool hL = slab(r, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, t_lo, t_hi, tnL);
-                    const bool hR = slab(r, qb.z, qb.w, qc.x, qc.y, qc.z, qc.w, t_lo, t_hi, tnR);
-                    if (hL && hR) {
-                        const bool rightNear = tnR < tnL;
-                        if (sp < STACK) { stack_n[sp] = rightNear ? qd.x : qd.y; stack_t[sp] = rightNear ? tnL : tnR; ++sp; }
-                        cur = rightNear ? qd.y : qd.x;
-                        pop = false;
-                    } else if (hL) { cur = qd.x; pop = false; }
-                    else if (hR) { cur = qd.y; pop = false; }
-                } else {
-                    if (STATS) ++st_leaf;
-                    float t, alpha; int g;
-                    if (leaf_test(r, p.recs + (~cur), alpha_min, back_culling, t, g, alpha)) {
-                        const bool after = key_less(t_last, g_last, t, g);
-                        const bool fits = cnt < KBUF || key_less(t, g, bt[(KBUF - 1) * TB], bg[(KBUF - 1) * TB]);
-                        if (after && fits) {
-                            int i = cnt < KBUF ? cnt++ : KBUF - 1;
-                            while (i > 0 && key_less(t, g, bt[(i - 1) * TB], bg[(i - 1) * TB])) {
-                                bt[i * TB] = bt[(i - 1) * TB]; bg[i * TB] = bg[(i - 1) * TB]; ba[i * TB] = ba[(i - 1) * TB];
-                                --i;
-                            }
-                            bt[i * TB] = t; bg[i * TB] = g; ba[i * TB] = alpha;
-                            // Termination-aware range: once the buffered hits alone drive the transmittance below
-                            // T_min at entry j, nothing behind entry j can ever be composited (closer hits found later
-                            // only lower T further), so the buffer and the walk end there.  Exact, see DESIGN.md.
-                            float Tc = T;
-                            for (int j = 0; j < cnt; ++j) {
-                                Tc *= (1.f - ba[j * TB]);
-                                if (Tc < a.T_min) { cnt = j + 1; t_hi = bt[j * TB]; break; }
-                            }
-                            if (cnt == KBUF) t_hi = bt[(KBUF - 1) * TB];
-                        }
-                    }
-                }
-                if (pop) {
-                    for (;;) {
-                        if (sp == 0) { phase = PH_COMP; break; }
-                        --sp;
-                        if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
-                    }
-                }
-            }
-            trav = __ballot_sync(FULL, phase == PH_TRAV);
-            if (trav == 0u) break;
-        }
-
-        // ---- composite the buffer of lanes whose pass is complete
-        if (phase == PH_COMP) {
-            float Y[16];
-            sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
-            bool term = false;
-            int i = 0;
-            for (; i < cnt; ++i) {
-                const float t = bt[i * TB], alpha = ba[i * TB];
-                const int g = bg[i * TB];
-                const float nx = __ldg(a.normals + 3 * (size_t)g), ny = __ldg(a.normals + 3 * (size_t)g + 1),
-                            nz = __ldg(a.normals + 3 * (size_t)g + 2);
-                const float dg = dot3_rn(nx, ny, nz, r.dx, r.dy, r.dz);
-                const float m = (-dg > 0.f) ? 1.f : -1.f;
-                float c[3];
-                sh_color(a.shs, a.K, a.deg, g, Y, c);
-                const float w = T * alpha;
-                C0 += w * c[0]; C1 += w * c[1]; C2 += w * c[2];
-                N0 += w * m * nx; N1 += w * m * ny; N2 += w * m * nz;
-                D += w * t; O += w;
-                if (FEAT) {
-#pragma unroll
-                    for (int j = 0; j < NFMAX; ++j)
-                        if (j < a.S) F[j] += w * __ldg(a.features + (size_t)g * a.S + j);
-                }
-                T *= (1.f - alpha);
-                if (a.hits != nullptr && total + i < a.hit_cap) a.hits[ray * a.hit_cap + total + i] = g;
-                if (T < a.T_min) { term = true; ++i; break; }
-            }
-            total += i;
-            if (!term && cnt == KBUF) {  // buffer exhausted without terminating: next pass, strictly after the last hit
-                t_last = bt[(KBUF - 1) * TB]; g_last = bg[(KBUF - 1) * TB];
-                cnt = 0; sp = 0; cur = 0; t_lo = fmaxf(t_last, 0.f); t_hi = IRGS_T_SCENE_MAX;
-                phase = PH_TRAV;
-                if (STATS) ++st_pass;
-            } else {
-                a.color[3 * ray] = C0; a.color[3 * ray + 1] = C1; a.color[3 * ray + 2] = C2;
-                a.normal[3 * ray] = N0; a.normal[3 * ray + 1] = N1; a.normal[3 * ray + 2] = N2;
-                a.depth[ray] = D; a.alpha[ray] = O;
-                if (FEAT) {
-#pragma unroll
-                    for (int j = 0; j < NFMAX; ++j)
-                        if (j < a.S) a.feature[ray * a.S + j] = F[j];
-                }
-                if (a.hit_count != nullptr) a.hit_count[ray] = total;
-                if (STATS) st_hits += total;
-                phase = PH_FETCH;
-            }
-        }
-    }
-    if (STATS) {
-        atomicAdd(p.stats + 0, st_nodes); atomicAdd(p.stats + 1, st_leaf);
-        atomicAdd(p.stats + 2, st_hits); atomicAdd(p.stats + 3, st_pass);
     }
 }
 
@@ -716,16 +389,6 @@ static int launch_persistent(irgs_tracer *h, Kern kern, const KParams &p, int64_
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;
-}
-
-int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
-    KParams p = make_params(h, a);
-    const bool feat = a.S > 0, stats = h->stats_enabled != 0;
-    if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
-    if (feat) return stats ? launch_persistent(h, trace_forward_kernel<true, true>, p, a.n_rays, s)
-                           : launch_persistent(h, trace_forward_kernel<true, false>, p, a.n_rays, s);
-    return stats ? launch_persistent(h, trace_forward_kernel<false, true>, p, a.n_rays, s)
-                 : launch_persistent(h, trace_forward_kernel<false, false>, p, a.n_rays, s);
 }
 
 int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {

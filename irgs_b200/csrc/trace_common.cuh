@@ -1,0 +1,159 @@
+// Device helpers shared by the tracing kernels (sm_100a).  See trace.cu / trace_fwd.cu for the kernels.
+#pragma once
+#include <cfloat>
+#include <climits>
+
+#include "internal.cuh"
+
+namespace irgs {
+
+constexpr int TB = 128;     // threads per block
+constexpr int KBUF = 16;    // k-buffer depth (MAX_BUFFER_SIZE, auxiliary.h:10)
+constexpr int STACK = 64;   // traversal stack entries (LBVH depth <= 30 code bits + 32 index bits)
+constexpr float T_EPS = 1.1920929e-07f;  // FLT_EPSILON tmin, gaussiantrace_forward.cu:38
+constexpr int NFMAX = IRGS_MAX_FEATURES;
+
+// auxiliary.h:16-33
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
+                           SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
+__device__ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
+                           SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
+                           SH_C3_6 = -0.5900435899266435f;
+
+struct KParams {
+    TraceArgs a;
+    const Node *nodes;
+    const SurfelRec *recs;
+    unsigned long long *counter;
+    unsigned long long *stats;
+};
+
+// fixed-order dot product, bit-identical to dot3() of oracle/surfel_oracle.c
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+}
+
+// SH basis Y_k(d), zero beyond (deg+1)^2  (auxiliary.h:52-89)
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float Y[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) Y[k] = 0.f;
+    Y[0] = SH_C0;
+    if (deg > 0) {
+        Y[1] = -SH_C1 * y; Y[2] = SH_C1 * z; Y[3] = -SH_C1 * x;
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            Y[4] = SH_C2_0 * xy; Y[5] = SH_C2_1 * yz; Y[6] = SH_C2_2 * (2.0f * zz - xx - yy);
+            Y[7] = SH_C2_3 * xz; Y[8] = SH_C2_4 * (xx - yy);
+            if (deg > 2) {
+                Y[9] = SH_C3_0 * y * (3.0f * xx - yy);
+                Y[10] = SH_C3_1 * xy * z;
+                Y[11] = SH_C3_2 * y * (4.0f * zz - xx - yy);
+                Y[12] = SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                Y[13] = SH_C3_4 * x * (4.0f * zz - xx - yy);
+                Y[14] = SH_C3_5 * z * (xx - yy);
+                Y[15] = SH_C3_6 * x * (xx - 3.0f * yy);
+            }
+        }
+    }
+}
+
+// colour = max(0, 0.5 + sum_k Y_k sh[g,k])   (auxiliary.h:52-89).  K == 16: twelve 16-byte loads at most.
+__device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, int deg, int g, const float Y[16],
+                                         float c[3]) {
+    const int nb = (deg + 1) * (deg + 1);
+    float acc[3] = {0.f, 0.f, 0.f};
+    if (K == 16) {
+        const float4 *p = reinterpret_cast<const float4 *>(shs + (size_t)g * 48);
+        const int nvec = (nb * 3 + 3) >> 2;
+#pragma unroll
+        for (int v = 0; v < 12; ++v) {
+            if (v < nvec) {
+                float4 q = __ldg(p + v);
+                acc[(4 * v) % 3] += Y[(4 * v) / 3] * q.x;
+                acc[(4 * v + 1) % 3] += Y[(4 * v + 1) / 3] * q.y;
+                acc[(4 * v + 2) % 3] += Y[(4 * v + 2) / 3] * q.z;
+                acc[(4 * v + 3) % 3] += Y[(4 * v + 3) / 3] * q.w;
+            }
+        }
+    } else {
+        const float *p = shs + (size_t)g * K * 3;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k < nb) {
+                acc[0] += Y[k] * __ldg(p + 3 * k);
+                acc[1] += Y[k] * __ldg(p + 3 * k + 1);
+                acc[2] += Y[k] * __ldg(p + 3 * k + 2);
+            }
+        }
+    }
+    c[0] = fmaxf(acc[0] + 0.5f, 0.f);
+    c[1] = fmaxf(acc[1] + 0.5f, 0.f);
+    c[2] = fmaxf(acc[2] + 0.5f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ traversal
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz;
+    float idx, idy, idz, oodx, oody, oodz;
+    float slack;
+};
+
+__device__ __forceinline__ void ray_setup(RayCtx &r) {
+    // a zero direction component would give inf * 0 = NaN in the slab test: nudge it (the slack term below then
+    // disables culling along that axis instead of producing garbage)
+    const float tiny = 1e-30f;
+    float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
+    float sy = fabsf(r.dy) > tiny ? r.dy : copysignf(tiny, r.dy);
+    float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
+    r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
+    r.oodx = r.ox * r.idx; r.oody = r.oy * r.idy; r.oodz = r.oz * r.idz;
+    // fma(lo, id, -ood) carries an absolute error of ~ulp(ood): widen the interval test by 4 ulp of the largest
+    float m = fmaxf(fmaxf(fabsf(r.oodx), fabsf(r.oody)), fmaxf(fabsf(r.oodz), 1.0f));
+    r.slack = m * 4.8e-7f;
+}
+
+__device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                     float t_lo, float t_hi, float &tn) {
+    float x0 = __fmaf_rn(lox, r.idx, -r.oodx), x1 = __fmaf_rn(hix, r.idx, -r.oodx);
+    float y0 = __fmaf_rn(loy, r.idy, -r.oody), y1 = __fmaf_rn(hiy, r.idy, -r.oody);
+    float z0 = __fmaf_rn(loz, r.idz, -r.oodz), z1 = __fmaf_rn(hiz, r.idz, -r.oodz);
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+    return tn <= tf + r.slack;
+}
+
+// Plane hit of a packed record.  Arithmetic order == eval_surfel() of oracle/surfel_oracle.c
+// (gaussiantrace_forward.cu:61-81).  Returns true for a compositing candidate.
+__device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
+                                          int back_culling, float &t_out, int &g_out, float &alpha_out) {
+    const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1);
+    float relx = __fsub_rn(r.ox, r0.x), rely = __fsub_rn(r.oy, r0.y), relz = __fsub_rn(r.oz, r0.z);
+    float og = dot3_rn(r1.x, r1.y, r1.z, relx, rely, relz);
+    float dg = dot3_rn(r1.x, r1.y, r1.z, r.dx, r.dy, r.dz);
+    float dg2 = __fmul_rn(dg, dg);
+    float den = fmaxf(1e-6f, dg2);
+    float t = __fdiv_rn(__fmul_rn(-og, dg), den);
+    if (!(dg2 >= 1e-6f)) return false;  // grazing pair: the clamped formula is no longer the geometric hit (see oracle)
+    if (!(t > T_EPS && t < IRGS_T_SCENE_MAX)) return false;
+    if (back_culling && !(-dg > 0.0f)) return false;
+    const float4 r2 = __ldg(&rec->r2), r3 = __ldg(&rec->r3);
+    float px = __fmaf_rn(t, r.dx, relx), py = __fmaf_rn(t, r.dy, rely), pz = __fmaf_rn(t, r.dz, relz);
+    float pu = dot3_rn(r2.x, r2.y, r2.z, px, py, pz);
+    float pv = dot3_rn(r2.w, r3.x, r3.y, px, py, pz);
+    float power = __fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv)));
+    float alpha = fminf(0.99f, __fmul_rn(r0.w, __expf(power)));
+    if (alpha < alpha_min) return false;
+    t_out = t; g_out = __float_as_int(r1.w); alpha_out = alpha;
+    return true;
+}
+
+__device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }
+
+__device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
+    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
+    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
+}
+
+}  // namespace irgs

@@ -305,15 +305,16 @@ __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restr
                              const int *__restrict__ scene_i, Node *nodes, int *flags, float *root_bound) {
     int leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
-    // absolute pad: a few float ulps of the scene scale, so that the slab test can never reject a surfel whose
-    // plane-hit arithmetic (trace.cu eval_surfel) accepts it; relative pad covers the proxy's 0.999993 in-radius
+    // absolute pad: a few float ulps of the scene scale, so that neither the rounding of the fma slab test nor that
+    // of the plane-hit arithmetic (trace_common.cuh leaf_test) can make the walk reject a surfel the hit test accepts;
+    // relative pad covers the proxy's 0.999993 in-radius
     float scale = 1e-3f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float clo = ord2f(scene_i[k]), chi = ord2f(scene_i[3 + k]);
         if (clo <= chi) scale = fmaxf(scale, fmaxf(chi - clo, fmaxf(fabsf(clo), fabsf(chi))));
     }
-    const float pad_abs = 4e-6f * scale;
+    const float pad_abs = 8e-6f * scale;
     const float *bx = boxes + 6 * (size_t)order[leaf];
     float lo[3], hi[3];
 #pragma unroll

@@ -92,7 +92,7 @@ __device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, f
         for (;;) {
             if (sp == 0) return cnt;
             --sp;
-            if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
+            if (stack_t[sp] <= t_hi) { cur = stack_n[sp]; break; }
         }
     }
 }

@@ -97,21 +97,20 @@ __device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, i
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz;
     float idx, idy, idz, oodx, oody, oodz;
-    float slack;
 };
 
+// Slab-test constants.  fma(plane, 1/d, -o/d) carries an absolute error of about (|o| + |plane - o|) * 2^-23 in SPACE
+// (the error in t scales with 1/d exactly like the t-extent of a spatial pad does), independent of how small a
+// direction component is.  The leaf bounds are therefore padded in space at refit time (lbvh.cu: 8e-6 x scene
+// scale + 1e-4 x extent) and the interval test itself needs no slack; ray origins are assumed to lie within ~16
+// scene diameters (beyond that the reference's own float32 plane arithmetic is equally fuzzy).
 __device__ __forceinline__ void ray_setup(RayCtx &r) {
-    // a zero direction component would give inf * 0 = NaN in the slab test: nudge it (the slack term below then
-    // disables culling along that axis instead of producing garbage)
-    const float tiny = 1e-30f;
+    const float tiny = 1e-30f;  // a zero component would give 0 * inf = NaN
     float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
     float sy = fabsf(r.dy) > tiny ? r.dy : copysignf(tiny, r.dy);
     float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
     r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
     r.oodx = r.ox * r.idx; r.oody = r.oy * r.idy; r.oodz = r.oz * r.idz;
-    // fma(lo, id, -ood) carries an absolute error of ~ulp(ood): widen the interval test by 4 ulp of the largest
-    float m = fmaxf(fmaxf(fabsf(r.oodx), fabsf(r.oody)), fmaxf(fabsf(r.oodz), 1.0f));
-    r.slack = m * 4.8e-7f;
 }
 
 __device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
@@ -121,7 +120,7 @@ __device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, floa
     float z0 = __fmaf_rn(loz, r.idz, -r.oodz), z1 = __fmaf_rn(hiz, r.idz, -r.oodz);
     tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
     float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
-    return tn <= tf + r.slack;
+    return tn <= tf;
 }
 
 // Plane hit of a packed record.  Arithmetic order == eval_surfel() of oracle/surfel_oracle.c

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
     float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
     int g_last = -1, g_hi = INT_MAX, total = 0, cnt = 0, sp = 0, cur = 0;
     bool saturated = false;   // the buffer is full and sorted; t_hi is the capacity bound (another pass may follow)
-    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = r.slack = 0.f;
+    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = 0.f;
 #pragma unroll
     for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
 
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
                     for (;;) {
                         if (sp == 0) { phase = PH_COMP; break; }
                         --sp;
-                        if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
+                        if (stack_t[sp] <= t_hi) { cur = stack_n[sp]; break; }
                     }
                 }
             }
@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
                 const float th = __shfl_sync(FULL, my_t, n_comp - 1);
                 const int gh = __shfl_sync(FULL, my_g, n_comp - 1);
                 if ((int)lane == L) {
-                    cnt = n_comp; t_hi = th; g_hi = gh; saturated = !term;
+                    cnt = n_comp; t_hi = th; g_hi = gh; saturated = (n_comp == KB);  // full and sorted: insertion mode
                     phase = PH_TRAV;
                     // resume the walk: `cur` is the leaf that filled the buffer, pop the next reachable node
                     for (;;) {
                         if (sp == 0) { phase = PH_COMP; break; }
                         --sp;
-                        if (stack_t[sp] <= t_hi + r.slack) { cur = stack_n[sp]; break; }
+                        if (stack_t[sp] <= t_hi) { cur = stack_n[sp]; break; }
                     }
                 }
                 if (__shfl_sync(FULL, phase, L) == PH_COMP) work |= (1u << L);  // stack ran empty: composite right away
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
                 }
                 T = Tc;
                 total += n_comp;
-                if (!term && saturated) {
+                if (!term && cnt == KB) {
                     // the nearest KB candidates were all composited without terminating: another pass, strictly
                     // after the last one
                     t_last = t_end; g_last = g_end;

@@ -110,6 +110,44 @@ def test_forward_matches_oracle(small_scene, kind, deg, back_culling, mode):
     assert np.abs(out["alpha"] - ref["alpha"]).max() < 5e-2
 
 
+def test_axis_aligned_and_nearly_axis_aligned_rays(small_scene):
+    """Direction components that are exactly zero or tiny must neither break the slab test nor disable culling."""
+    sc, inp = small_scene
+    gen = torch.Generator().manual_seed(4)
+    n = 600
+    o = torch.zeros(n, 3)
+    o[:, 0] = (torch.rand(n, generator=gen) * 2 - 1) * 0.9
+    o[:, 2] = (torch.rand(n, generator=gen) * 2 - 1) * 0.9
+    o[:, 1] = -3.0
+    d = torch.zeros(n, 3)
+    d[:, 1] = 1.0
+    d[200:400, 0] = 1e-9
+    d[300:400, 2] = -3e-12
+    d[400:, 0] = (torch.rand(200, generator=gen) - 0.5) * 2e-5
+    d[400:, 2] = (torch.rand(200, generator=gen) - 0.5) * 2e-6
+    d = d / d.norm(dim=-1, keepdim=True)
+    perm = [1, 2, 0]
+    o = torch.cat([o, o[:, perm]]).contiguous()
+    d = torch.cat([d, d[:, perm]]).contiguous()
+    ref = oracle.trace_forward(_oracle_scene(inp), o, d, hit_cap=96)
+    g = _gpu(inp)
+    tr = _tracer(g, hit_cap=96)
+    tr.set_stats(True)
+    out = tr.trace_with_hits(o.to(DEV), d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"],
+                             g["features"], g["shs"], synth.ALPHA_MIN)
+    nodes = tr.get_stats()[0]
+    tr.set_stats(False)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    safe = _safe(ref)
+    assert (ref["hit_count"] > 0).mean() > 0.2
+    assert np.array_equal(out["hit_count"][safe], ref["hit_count"][safe])
+    cols = np.arange(96)[None] < ref["hit_count"][:, None]
+    assert np.array_equal(np.where(cols, out["hits"], -1)[safe], np.where(cols, ref["hits"], -1)[safe])
+    for k in ("color", "normal", "feature", "depth", "alpha"):
+        assert np.abs(out[k] - ref[k])[safe].max() <= 1e-4, k
+    assert nodes / o.shape[0] < 2000, "culling must stay effective for axis-aligned rays"
+
+
 def test_forward_matches_oracle_at_300k_on_a_ray_sample():
     sc = synth.make_scene(300000)
     inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)

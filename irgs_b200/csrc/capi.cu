@@ -92,7 +92,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     cudaDeviceSynchronize();
     cudaFree(h->nodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
-    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats);
+    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
@@ -305,14 +305,14 @@ static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, i
         a.n_rays = c; a.rays_o = d_o; a.rays_d = d_d;
         a.color = d_col; a.normal = d_nrm; a.feature = d_feat; a.depth = d_dep; a.alpha = d_alp;
         if (with_backward) { a.hit_count = d_cnt; a.hits = d_hits; a.hit_cap = hit_cap; }
-        h->counter += si;  // each stream has its own persistent-kernel work counter
+        h->slot = si;  // each stream has its own persistent-kernel work counter and scratch
         int rc = launch_trace_forward(h, a, s);
         if (!rc && with_backward) {
             a.gC = gC; a.gN = gN; a.gF = gF; a.gD = gD; a.gO = gO; a.gout_period = gout_period; a.gout_offset = done;
             a.g_rays_o = d_go; a.g_rays_d = d_gd; a.grad_fused = grad_fused; a.grad_features = grad_features;
             rc = launch_trace_backward(h, a, s);
         }
-        h->counter -= si;
+        h->slot = 0;
         if (rc) return 1;
         if (out_color_host) IRGS_CHECK(cudaMemcpyAsync(out_color_host + 3 * done, d_col, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
         if (out_normal_host) IRGS_CHECK(cudaMemcpyAsync(out_normal_host + 3 * done, d_nrm, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));

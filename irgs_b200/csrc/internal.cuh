@@ -50,7 +50,10 @@ struct irgs_tracer {
     int64_t radix_tiles_cap = 0;
     float *scene = nullptr;             // [16]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats), 12 pad
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
-    unsigned long long *counter = nullptr;  // persistent-kernel work counter [4]
+    unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
+    int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)
+    uint2 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t bits, leaf)
+    int64_t cand_threads = 0;               // threads one slot has room for
     unsigned long long *stats = nullptr;    // [4]
     int stats_enabled = 0;
     bool built = false;

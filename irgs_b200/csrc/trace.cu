@@ -366,7 +366,7 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
     p.a = a;
     p.nodes = h->nodes;
     p.recs = h->recs;
-    p.counter = h->counter;
+    p.counter = h->counter + h->slot;
     p.stats = h->stats;
     return p;
 }
@@ -381,7 +381,7 @@ int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
 
 template <typename Kern>
 static int launch_persistent(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_rays, cudaStream_t s) {
-    IRGS_CHECK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), s));
+    IRGS_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
     int grid = persistent_grid(h, reinterpret_cast<const void *>(kern));
     int64_t need = (n_rays + TB - 1) / TB;
     if (need < grid) grid = (int)(need > 0 ? need : 1);

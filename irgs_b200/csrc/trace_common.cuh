@@ -123,29 +123,34 @@ __device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, floa
     return tn <= tf;
 }
 
-// Plane hit of a packed record.  Arithmetic order == eval_surfel() of oracle/surfel_oracle.c
-// (gaussiantrace_forward.cu:61-81).  Returns true for a compositing candidate.
-__device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
-                                          int back_culling, float &t_out, int &g_out, float &alpha_out) {
-    const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1);
+// Plane hit of a packed record (already in registers).  Arithmetic order == eval_surfel() of
+// oracle/surfel_oracle.c (gaussiantrace_forward.cu:61-81).  Returns true for a compositing candidate.
+__device__ __forceinline__ bool leaf_eval(const RayCtx &r, const float4 r0, const float4 r1, const float4 r2,
+                                          const float4 r3, float alpha_min, int back_culling, float &t_out, int &g_out,
+                                          float &alpha_out) {
     float relx = __fsub_rn(r.ox, r0.x), rely = __fsub_rn(r.oy, r0.y), relz = __fsub_rn(r.oz, r0.z);
     float og = dot3_rn(r1.x, r1.y, r1.z, relx, rely, relz);
     float dg = dot3_rn(r1.x, r1.y, r1.z, r.dx, r.dy, r.dz);
     float dg2 = __fmul_rn(dg, dg);
     float den = fmaxf(1e-6f, dg2);
     float t = __fdiv_rn(__fmul_rn(-og, dg), den);
+    t_out = t; g_out = __float_as_int(r1.w); alpha_out = 0.f;
     if (!(dg2 >= 1e-6f)) return false;  // grazing pair: the clamped formula is no longer the geometric hit (see oracle)
     if (!(t > T_EPS && t < IRGS_T_SCENE_MAX)) return false;
     if (back_culling && !(-dg > 0.0f)) return false;
-    const float4 r2 = __ldg(&rec->r2), r3 = __ldg(&rec->r3);
     float px = __fmaf_rn(t, r.dx, relx), py = __fmaf_rn(t, r.dy, rely), pz = __fmaf_rn(t, r.dz, relz);
     float pu = dot3_rn(r2.x, r2.y, r2.z, px, py, pz);
     float pv = dot3_rn(r2.w, r3.x, r3.y, px, py, pz);
     float power = __fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv)));
     float alpha = fminf(0.99f, __fmul_rn(r0.w, __expf(power)));
-    if (alpha < alpha_min) return false;
-    t_out = t; g_out = __float_as_int(r1.w); alpha_out = alpha;
-    return true;
+    alpha_out = alpha;
+    return alpha >= alpha_min;
+}
+
+__device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
+                                          int back_culling, float &t_out, int &g_out, float &alpha_out) {
+    return leaf_eval(r, __ldg(&rec->r0), __ldg(&rec->r1), __ldg(&rec->r2), __ldg(&rec->r3), alpha_min, back_culling, t_out,
+                     g_out, alpha_out);
 }
 
 __device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }

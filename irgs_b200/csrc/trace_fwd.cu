@@ -1,30 +1,35 @@
-// Forward tracing kernel (sm_100a): persistent, dynamic ray fetch, warp-cooperative sort + compositing.
+// Forward tracing kernel (sm_100a): persistent, dynamic ray fetch, co-operative 64-byte fetches staged through shared
+// memory, warp-cooperative sort + compositing.
 //
 // Replaces gaussiantrace_forward.cu:12-141 of the reference (raygen with 16-hit chunks + any-hit sorted insertion).
 //
 // Every lane owns one ray and runs a small state machine
 //     FETCH -> TRAV -> COMP -> (TRAV for another pass | FETCH)          TRAV -> FULL -> TRAV
-//   TRAV  near-first stack walk of the LBVH, one node or one leaf per iteration.  A surfel that passes the plane /
-//         alpha test is APPENDED (O(1), unsorted) to the lane's candidate buffer in shared memory.
-//   FULL  the buffer holds KB candidates: the warp sorts it co-operatively and trims it at the entry where the
-//         buffered hits alone already push the transmittance below T_min (nothing behind it can ever be composited);
-//         the walk then continues with the range clipped to that depth.
-//   COMP  the pass's walk is finished: the warp sorts the buffer co-operatively (rank sort through shuffles),
-//         the transmittance chain is evaluated in the sequential order of the reference, every lane shades ONE hit
-//         (SH colour: twelve 16-byte loads, all hits in flight at once) and the weighted sums are warp-reduced.
-//         The ordered surfel ids are written with one coalesced store (saved hit list for the backward replay).
+//   TRAV  near-first stack walk of the LBVH, one node or one leaf per iteration.  The 64-byte node / surfel record a
+//         lane needs is fetched by FOUR lanes (16 bytes each) so that one load instruction touches 8 cache lines
+//         instead of 32, staged through a swizzled shared-memory tile and read back by the owning lane: ncu showed the
+//         one-thread-per-record version bound by L1TEX wavefronts (one per distinct line per instruction), not by HBM
+//         or L2.  The traversal stack lives in shared memory ([entry][lane]: conflict free for any mix of depths).
+//         A surfel that passes the plane / alpha test is APPENDED (8 bytes, unsorted) to the lane's candidate row in
+//         a global scratch buffer (L2 resident).
+//   FULL  the row holds KB candidates: the warp sorts it co-operatively and trims it at the entry where the buffered
+//         hits alone already push the transmittance below T_min (nothing behind it can ever be composited); the walk
+//         continues with the range clipped to that depth.
+//   COMP  the pass's walk is finished: every lane re-evaluates ONE candidate (alpha, normal, SH colour: twelve
+//         16-byte loads, all hits in flight at once), ranks are computed through shuffles, the transmittance chain is
+//         evaluated in the sequential order of the reference, the weighted sums are warp-reduced and added to the
+//         (pre-zeroed) outputs.  The ordered surfel ids are written with one store (hit list for the backward).
 // A lane that finishes its ray pulls the next one from a global counter at once; the warp leaves the walk to serve
-// FULL / COMP lanes as soon as fewer than MIN_ACTIVE lanes are still walking, which bounds the divergence of the hot
-// loop.  (First version: one thread per ray kept a sorted k-buffer by insertion and composited alone; ncu showed 4 of
-// 32 lanes active on average -- profiles/r01_ncu_forward_v1.md.)
+// FULL / COMP lanes as soon as fewer than MIN_ACTIVE lanes are still walking.
 #include "trace_common.cuh"
 
 namespace irgs {
 
-constexpr int KB = 32;             // candidate buffer depth per ray
-constexpr int KROW = KB + 1;       // padded row: co-operative reads of one row are bank-conflict free
+constexpr int KB = 32;             // candidates per row == warp width (one candidate per lane in the COMP phase)
+constexpr int SSTK = 32;           // traversal stack entries kept in shared memory; deeper entries spill to local
 constexpr int MIN_ACTIVE = 20;
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
+constexpr int CUR_NONE = INT_MIN;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -32,35 +37,41 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+struct WarpSmem {
+    float4 stage[4 * 32];     // [ray lane][quad ^ swizzle]
+    int stack[SSTK * 32];     // [entry][lane]
+};
+
 template <bool FEAT, bool STATS>
-__global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *s_t = reinterpret_cast<float *>(smem_raw);          // [TB][KROW]
-    int *s_g = reinterpret_cast<int *>(s_t + TB * KROW);        // [TB][KROW]
-    float *s_a = reinterpret_cast<float *>(s_g + TB * KROW);    // [TB][KROW]
+__global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, uint2 *__restrict__ cand_base) {
+    __shared__ WarpSmem smem[TB / 32];
     const int tid = threadIdx.x;
-    const int warp_row0 = (tid & ~31) * KROW;                   // first row of this warp
-    float *bt = s_t + tid * KROW; int *bg = s_g + tid * KROW; float *ba = s_a + tid * KROW;
-    int stack_n[STACK]; float stack_t[STACK];
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
+    WarpSmem &ws = smem[tid >> 5];
+    int *stk = ws.stack + lane;
+    int stack_spill[STACK - SSTK];
     const unsigned FULL = 0xffffffffu;
     const TraceArgs &a = p.a;
     const float alpha_min = a.alpha_min, T_min = a.T_min;
     const int back_culling = a.back_culling;
+    uint2 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
+    uint2 *my_cand = warp_cand + (size_t)lane * KB;
     unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
 
     int phase = PH_FETCH;
     bool pool_empty = false;  // warp-uniform
     int64_t ray = 0;
     RayCtx r;
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, O = 0.f;
-    float F[FEAT ? NFMAX : 1];
+    float T = 1.f;
     float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
     int g_last = -1, g_hi = INT_MAX, total = 0, cnt = 0, sp = 0, cur = 0;
-    bool saturated = false;   // the buffer is full and sorted; t_hi is the capacity bound (another pass may follow)
+    bool saturated = false;   // the row is full and sorted; t_hi is the capacity bound (another pass may follow)
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = 0.f;
-#pragma unroll
-    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
+
+    // swizzled staging: the 4 quads of ray-lane q live at float4 index 4*q + (k ^ ((q >> 1) & 3)); both the
+    // co-operative 16-byte stores and the per-lane 16-byte loads are then bank-conflict free
+    const int my_quad = lane & 3;
+    const int rd_sw = (lane >> 1) & 3;
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
@@ -75,9 +86,7 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
                 if (ray < a.n_rays) {
                     load_ray(a, ray, r);
                     ray_setup(r);
-                    T = 1.f; C0 = C1 = C2 = N0 = N1 = N2 = D = O = 0.f;
-#pragma unroll
-                    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) F[j] = 0.f;
+                    T = 1.f;
                     t_last = -INFINITY; g_last = -1; total = 0;
                     cnt = 0; sp = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; saturated = false;
                     phase = PH_TRAV;
@@ -92,50 +101,71 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
         // ------------------------------------------------------------------ BVH walk
         const int thr = pool_empty ? 1 : MIN_ACTIVE;
         while (__popc(trav) >= thr) {
+            // co-operative fetch of the 64 bytes each walking lane needs next (node or surfel record)
+            const int want = (phase == PH_TRAV) ? cur : CUR_NONE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int q = 8 * k + (lane >> 2);                   // ray lane served by this group of four
+                const int c = __shfl_sync(FULL, want, q);
+                if (c != CUR_NONE) {
+                    const float4 *src = c >= 0 ? reinterpret_cast<const float4 *>(p.nodes + c)
+                                               : reinterpret_cast<const float4 *>(p.recs + (~c));
+                    ws.stage[4 * q + (my_quad ^ ((q >> 1) & 3))] = __ldg(src + my_quad);
+                }
+            }
+            __syncwarp();
+            const float4 q0 = ws.stage[4 * lane + (0 ^ rd_sw)], q1 = ws.stage[4 * lane + (1 ^ rd_sw)],
+                         q2 = ws.stage[4 * lane + (2 ^ rd_sw)], q3 = ws.stage[4 * lane + (3 ^ rd_sw)];
+            __syncwarp();
             if (phase == PH_TRAV) {
                 bool pop = true;
                 if (cur >= 0) {
-                    const Node *nd = p.nodes + cur;
-                    const float4 qa = __ldg(&nd->a), qb = __ldg(&nd->b), qc = __ldg(&nd->c);
-                    const int4 qd = __ldg(&nd->d);
                     if (STATS) ++st_nodes;
                     float tnL, tnR;
-                    const bool hL = slab(r, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, t_lo, t_hi, tnL);
-                    const bool hR = slab(r, qb.z, qb.w, qc.x, qc.y, qc.z, qc.w, t_lo, t_hi, tnR);
+                    const bool hL = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_lo, t_hi, tnL);
+                    const bool hR = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_lo, t_hi, tnR);
+                    const int cl = __float_as_int(q3.x), cr = __float_as_int(q3.y);
                     if (hL && hR) {
                         const bool rightNear = tnR < tnL;
-                        if (sp < STACK) { stack_n[sp] = rightNear ? qd.x : qd.y; stack_t[sp] = rightNear ? tnL : tnR; ++sp; }
-                        cur = rightNear ? qd.y : qd.x;
+                        const int far_c = rightNear ? cl : cr;
+                        if (sp < SSTK) stk[sp * 32] = far_c;
+                        else if (sp < STACK) stack_spill[sp - SSTK] = far_c;
+                        if (sp < STACK) ++sp;
+                        cur = rightNear ? cr : cl;
                         pop = false;
-                    } else if (hL) { cur = qd.x; pop = false; }
-                    else if (hR) { cur = qd.y; pop = false; }
+                    } else if (hL) { cur = cl; pop = false; }
+                    else if (hR) { cur = cr; pop = false; }
                 } else {
                     if (STATS) ++st_leaf;
                     float t, alpha; int g;
-                    if (leaf_test(r, p.recs + (~cur), alpha_min, back_culling, t, g, alpha) &&
+                    if (leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
                         key_less(t_last, g_last, t, g) && key_less(t, g, t_hi, g_hi)) {
                         if (!saturated) {
-                            bt[cnt] = t; bg[cnt] = g; ba[cnt] = alpha;
+                            my_cand[cnt] = make_uint2(__float_as_uint(t), (unsigned)(~cur));
                             if (++cnt == KB) phase = PH_FULL;
                         } else {
                             // rare: more than KB candidates and no termination among the nearest KB -- keep the KB
-                            // nearest by sorted insertion (the buffer is sorted in this mode), dropping the farthest
+                            // nearest by sorted insertion (the row is sorted in this mode), dropping the farthest
                             int i = KB - 1;
-                            while (i > 0 && key_less(t, g, bt[i - 1], bg[i - 1])) {
-                                bt[i] = bt[i - 1]; bg[i] = bg[i - 1]; ba[i] = ba[i - 1];
+                            while (i > 0) {
+                                const uint2 e = __ldcg(&my_cand[i - 1]);
+                                const float te = __uint_as_float(e.x);
+                                bool less = t < te;
+                                if (t == te) less = g < __float_as_int(__ldg(&p.recs[e.y].r1.w));
+                                if (!less) break;
+                                my_cand[i] = e;
                                 --i;
                             }
-                            bt[i] = t; bg[i] = g; ba[i] = alpha;
-                            t_hi = bt[KB - 1]; g_hi = bg[KB - 1];
+                            my_cand[i] = make_uint2(__float_as_uint(t), (unsigned)(~cur));
+                            const uint2 e = __ldcg(&my_cand[KB - 1]);
+                            t_hi = __uint_as_float(e.x);
+                            g_hi = __float_as_int(__ldg(&p.recs[e.y].r1.w));
                         }
                     }
                 }
                 if (pop && phase == PH_TRAV) {
-                    for (;;) {
-                        if (sp == 0) { phase = PH_COMP; break; }
-                        --sp;
-                        if (stack_t[sp] <= t_hi) { cur = stack_n[sp]; break; }
-                    }
+                    if (sp == 0) phase = PH_COMP;
+                    else { --sp; cur = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; }
                 }
             }
             trav = __ballot_sync(FULL, phase == PH_TRAV);
@@ -144,15 +174,8 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
 
         // ------------------------------------------------------------------ lanes whose pass found nothing
         if (phase == PH_COMP && cnt == 0) {
-            a.color[3 * ray] = C0; a.color[3 * ray + 1] = C1; a.color[3 * ray + 2] = C2;
-            a.normal[3 * ray] = N0; a.normal[3 * ray + 1] = N1; a.normal[3 * ray + 2] = N2;
-            a.depth[ray] = D; a.alpha[ray] = O;
-            if (FEAT) {
-#pragma unroll
-                for (int j = 0; j < NFMAX; ++j)
-                    if (j < a.S) a.feature[ray * a.S + j] = F[j];
-            }
-            if (a.hit_count != nullptr) a.hit_count[ray] = total;
+            // outputs are pre-zeroed; a multi-pass ray already added its earlier passes
+            if (total > 0 && a.hit_count != nullptr) a.hit_count[ray] = total;
             if (STATS) st_hits += total;
             phase = PH_FETCH;
         }
@@ -162,62 +185,77 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
         while (work != 0u) {
             const int L = __ffs(work) - 1;
             work &= work - 1u;
+            __syncwarp();  // lane L's appended candidates are visible to the whole warp
             const int n = __shfl_sync(FULL, cnt, L);
             const bool is_full = __shfl_sync(FULL, phase, L) == PH_FULL;
-            const int row = warp_row0 + L * KROW;
-            // rank sort of the n candidates by (t, surfel id): entry `lane` counts how many precede it
-            float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX;
-            if ((int)lane < n) { my_t = s_t[row + lane]; my_g = s_g[row + lane]; my_a = s_a[row + lane]; }
+            // the ray of lane L, broadcast
+            RayCtx rl;
+            rl.ox = __shfl_sync(FULL, r.ox, L); rl.oy = __shfl_sync(FULL, r.oy, L); rl.oz = __shfl_sync(FULL, r.oz, L);
+            rl.dx = __shfl_sync(FULL, r.dx, L); rl.dy = __shfl_sync(FULL, r.dy, L); rl.dz = __shfl_sync(FULL, r.dz, L);
+            // lane i re-evaluates candidate i (same arithmetic as during the walk: identical t and alpha)
+            float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX; unsigned my_leaf = 0;
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if ((int)lane < n) {
+                const uint2 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
+                my_leaf = e.y;
+                const SurfelRec *rec = p.recs + my_leaf;
+                const float4 r1 = __ldg(&rec->r1);
+                leaf_eval(rl, __ldg(&rec->r0), r1, __ldg(&rec->r2), __ldg(&rec->r3), alpha_min, 0, my_t, my_g, my_a);
+                my_t = __uint_as_float(e.x);
+                nx = r1.x; ny = r1.y; nz = r1.z;
+            }
+            // rank by (t, surfel id)
             int rank = 0;
             for (int j = 0; j < n; ++j) {
                 const float tj = __shfl_sync(FULL, my_t, j);
                 const int gj = __shfl_sync(FULL, my_g, j);
                 rank += key_less(tj, gj, my_t, my_g) ? 1 : 0;
             }
+            // alphas in sorted order through shared memory, then the transmittance chain in sequential order
+            float *s_alpha = reinterpret_cast<float *>(ws.stage);
             __syncwarp();
-            if ((int)lane < n) { s_t[row + rank] = my_t; s_g[row + rank] = my_g; s_a[row + rank] = my_a; }
+            if ((int)lane < n) s_alpha[rank] = my_a;
             __syncwarp();
-            if ((int)lane < n) { my_t = s_t[row + lane]; my_g = s_g[row + lane]; my_a = s_a[row + lane]; }
-            // transmittance chain in the reference's sequential order (bit-identical termination decisions)
             float Tc = __shfl_sync(FULL, T, L);
             float my_w = 0.f;
             int n_comp = n;
             bool term = false;
             for (int i = 0; i < n; ++i) {
-                const float ai = __shfl_sync(FULL, my_a, i);
-                if ((int)lane == i) my_w = Tc * ai;
+                const float ai = s_alpha[i];
+                if (rank == i) my_w = Tc * ai;
                 Tc *= (1.f - ai);
                 if (Tc < T_min) { n_comp = i + 1; term = true; break; }
             }
+            __syncwarp();
+            // the entry that ends the composited prefix / the row
+            const unsigned last_mask = __ballot_sync(FULL, (int)lane < n && rank == n_comp - 1);
+            const int last_lane = __ffs(last_mask) - 1;
+            const float t_end = __shfl_sync(FULL, my_t, last_lane);
+            const int g_end = __shfl_sync(FULL, my_g, last_lane);
             if (is_full) {
-                // trim: nothing behind the terminating entry can be composited; otherwise the capacity bound applies
-                const float th = __shfl_sync(FULL, my_t, n_comp - 1);
-                const int gh = __shfl_sync(FULL, my_g, n_comp - 1);
+                // trim: keep the composited prefix, in sorted order, and clip the walk to its last entry
+                __syncwarp();
+                if ((int)lane < n && rank < n_comp) warp_cand[(size_t)L * KB + rank] = make_uint2(__float_as_uint(my_t), my_leaf);
+                __syncwarp();
                 if ((int)lane == L) {
-                    cnt = n_comp; t_hi = th; g_hi = gh; saturated = (n_comp == KB);  // full and sorted: insertion mode
-                    phase = PH_TRAV;
-                    // resume the walk: `cur` is the leaf that filled the buffer, pop the next reachable node
-                    for (;;) {
-                        if (sp == 0) { phase = PH_COMP; break; }
-                        --sp;
-                        if (stack_t[sp] <= t_hi) { cur = stack_n[sp]; break; }
-                    }
+                    cnt = n_comp; t_hi = t_end; g_hi = g_end; saturated = (n_comp == KB);
+                    // resume the walk: `cur` is the leaf that filled the row, pop the next node
+                    if (sp == 0) phase = PH_COMP;
+                    else { --sp; cur = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; phase = PH_TRAV; }
                 }
                 if (__shfl_sync(FULL, phase, L) == PH_COMP) work |= (1u << L);  // stack ran empty: composite right away
                 continue;
             }
             // shade one hit per lane
-            const float dx = __shfl_sync(FULL, r.dx, L), dy = __shfl_sync(FULL, r.dy, L), dz = __shfl_sync(FULL, r.dz, L);
             float c0 = 0.f, c1 = 0.f, c2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dd = 0.f, oo = 0.f;
             float f[FEAT ? NFMAX : 1];
 #pragma unroll
             for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) f[j] = 0.f;
-            if ((int)lane < n_comp) {
+            const bool mine = (int)lane < n && rank < n_comp;
+            if (mine) {
                 float Y[16];
-                sh_basis(a.deg, dx, dy, dz, Y);
-                const float nx = __ldg(a.normals + 3 * (size_t)my_g), ny = __ldg(a.normals + 3 * (size_t)my_g + 1),
-                            nz = __ldg(a.normals + 3 * (size_t)my_g + 2);
-                const float dg = dot3_rn(nx, ny, nz, dx, dy, dz);
+                sh_basis(a.deg, rl.dx, rl.dy, rl.dz, Y);
+                const float dg = dot3_rn(nx, ny, nz, rl.dx, rl.dy, rl.dz);
                 const float m = (-dg > 0.f) ? 1.f : -1.f;
                 float c[3];
                 sh_color(a.shs, a.K, a.deg, my_g, Y, c);
@@ -232,8 +270,7 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
             }
             const int64_t ray_L = __shfl_sync(FULL, ray, L);
             const int total_L = __shfl_sync(FULL, total, L);
-            if (a.hits != nullptr && (int)lane < n_comp && total_L + (int)lane < a.hit_cap)
-                a.hits[ray_L * a.hit_cap + total_L + lane] = my_g;
+            if (a.hits != nullptr && mine && total_L + rank < a.hit_cap) a.hits[ray_L * a.hit_cap + total_L + rank] = my_g;
             c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
             n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2);
             dd = warp_sum(dd); oo = warp_sum(oo);
@@ -242,13 +279,15 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
                 for (int j = 0; j < NFMAX; ++j)
                     if (j < a.S) f[j] = warp_sum(f[j]);
             }
-            const float t_end = __shfl_sync(FULL, my_t, n - 1);
-            const int g_end = __shfl_sync(FULL, my_g, n - 1);
             if ((int)lane == L) {
-                C0 += c0; C1 += c1; C2 += c2; N0 += n0; N1 += n1; N2 += n2; D += dd; O += oo;
+                // outputs are pre-zeroed by the launcher: every pass adds its share
+                a.color[3 * ray] += c0; a.color[3 * ray + 1] += c1; a.color[3 * ray + 2] += c2;
+                a.normal[3 * ray] += n0; a.normal[3 * ray + 1] += n1; a.normal[3 * ray + 2] += n2;
+                a.depth[ray] += dd; a.alpha[ray] += oo;
                 if (FEAT) {
 #pragma unroll
-                    for (int j = 0; j < NFMAX; ++j) F[j] += f[j];
+                    for (int j = 0; j < NFMAX; ++j)
+                        if (j < a.S) a.feature[ray * a.S + j] += f[j];
                 }
                 T = Tc;
                 total += n_comp;
@@ -261,14 +300,6 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
                     phase = PH_TRAV;
                     if (STATS) ++st_pass;
                 } else {
-                    a.color[3 * ray] = C0; a.color[3 * ray + 1] = C1; a.color[3 * ray + 2] = C2;
-                    a.normal[3 * ray] = N0; a.normal[3 * ray + 1] = N1; a.normal[3 * ray + 2] = N2;
-                    a.depth[ray] = D; a.alpha[ray] = O;
-                    if (FEAT) {
-#pragma unroll
-                        for (int j = 0; j < NFMAX; ++j)
-                            if (j < a.S) a.feature[ray * a.S + j] = F[j];
-                    }
                     if (a.hit_count != nullptr) a.hit_count[ray] = total;
                     if (STATS) st_hits += total;
                     phase = PH_FETCH;
@@ -284,15 +315,22 @@ __global__ void __launch_bounds__(TB, 4) trace_forward_kernel(const KParams p) {
 
 template <typename Kern>
 static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_rays, cudaStream_t s) {
-    const size_t smem = (size_t)TB * KROW * 12;
-    IRGS_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IRGS_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem) != cudaSuccess || per_sm < 1) per_sm = 2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     int grid = h->sm_count * per_sm;
+    // candidate scratch: one 32-entry row per resident thread and stream slot (L2-resident: 256 B x ~100k threads)
+    const int64_t threads = (int64_t)grid * TB;
+    if (threads > h->cand_threads) {
+        IRGS_CHECK(cudaDeviceSynchronize());
+        if (h->cand) cudaFree(h->cand);
+        h->cand = nullptr;
+        IRGS_CHECK(cudaMalloc(&h->cand, sizeof(uint2) * KB * (size_t)threads * 2));
+        h->cand_threads = threads;
+    }
     const int64_t need = (n_rays + TB - 1) / TB;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
-    kern<<<grid, TB, smem, s>>>(p);
+    IRGS_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
+    kern<<<grid, TB, 0, s>>>(p, h->cand + (size_t)h->slot * KB * (size_t)h->cand_threads);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;
@@ -300,9 +338,17 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p;
-    p.a = a; p.nodes = h->nodes; p.recs = h->recs; p.counter = h->counter; p.stats = h->stats;
+    p.a = a; p.nodes = h->nodes; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
+    // rays that hit nothing are never written by the kernel
+    const size_t R = (size_t)a.n_rays;
+    IRGS_CHECK(cudaMemsetAsync(a.color, 0, sizeof(float) * 3 * R, s));
+    IRGS_CHECK(cudaMemsetAsync(a.normal, 0, sizeof(float) * 3 * R, s));
+    IRGS_CHECK(cudaMemsetAsync(a.depth, 0, sizeof(float) * R, s));
+    IRGS_CHECK(cudaMemsetAsync(a.alpha, 0, sizeof(float) * R, s));
+    if (a.S > 0) IRGS_CHECK(cudaMemsetAsync(a.feature, 0, sizeof(float) * (size_t)a.S * R, s));
+    if (a.hit_count) IRGS_CHECK(cudaMemsetAsync(a.hit_count, 0, sizeof(int32_t) * R, s));
     if (feat) return stats ? launch_fwd(h, trace_forward_kernel<true, true>, p, a.n_rays, s)
                            : launch_fwd(h, trace_forward_kernel<true, false>, p, a.n_rays, s);
     return stats ? launch_fwd(h, trace_forward_kernel<false, true>, p, a.n_rays, s)

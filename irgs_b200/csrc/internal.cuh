@@ -52,7 +52,7 @@ struct irgs_tracer {
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
     unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
     int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)
-    uint2 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t bits, leaf)
+    uint4 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t, id, alpha, -)
     int64_t cand_threads = 0;               // threads one slot has room for
     unsigned long long *stats = nullptr;    // [4]
     int stats_enabled = 0;

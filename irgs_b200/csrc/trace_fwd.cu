@@ -10,15 +10,18 @@
 //         instead of 32, staged through a swizzled shared-memory tile and read back by the owning lane: ncu showed the
 //         one-thread-per-record version bound by L1TEX wavefronts (one per distinct line per instruction), not by HBM
 //         or L2.  The traversal stack lives in shared memory ([entry][lane]: conflict free for any mix of depths).
-//         A surfel that passes the plane / alpha test is APPENDED (8 bytes, unsorted) to the lane's candidate row in
-//         a global scratch buffer (L2 resident).
-//   FULL  the row holds KB candidates: the warp sorts it co-operatively and trims it at the entry where the buffered
-//         hits alone already push the transmittance below T_min (nothing behind it can ever be composited); the walk
-//         continues with the range clipped to that depth.
-//   COMP  the pass's walk is finished: every lane re-evaluates ONE candidate (alpha, normal, SH colour: twelve
-//         16-byte loads, all hits in flight at once), ranks are computed through shuffles, the transmittance chain is
-//         evaluated in the sequential order of the reference, the weighted sums are warp-reduced and added to the
-//         (pre-zeroed) outputs.  The ordered surfel ids are written with one store (hit list for the backward).
+//         A surfel that passes the plane / alpha test is APPENDED (one 16-byte store: t, surfel id, alpha; unsorted)
+//         to the lane's candidate row in a global scratch buffer (L2 resident).
+//   FULL  the row holds KB candidates: the warp sorts it co-operatively.  If the buffered hits alone already push the
+//         transmittance below T_min at some entry, nothing behind that entry can ever be composited: the row is
+//         trimmed there and the walk continues with its range clipped to that depth.  Otherwise the pass's depth range
+//         is SPLIT: the nearest KB/2 candidates are kept, the range is clipped to the last of them and the rest of the
+//         ray is left to a following pass (no per-candidate eviction ever happens).
+//   COMP  the pass's walk is finished: the warp ranks the candidates through shuffles and permutes them into depth
+//         order (one per lane), evaluates the transmittance chain in the sequential order of the reference, shades
+//         one hit per lane (SH colour: twelve 16-byte loads, all hits in flight at once), warp-reduces the weighted
+//         sums in depth order and adds them to the (pre-zeroed) outputs.  The ordered surfel ids are written with one
+//         coalesced store (hit list for the backward replay).
 // A lane that finishes its ray pulls the next one from a global counter at once; the warp leaves the walk to serve
 // FULL / COMP lanes as soon as fewer than MIN_ACTIVE lanes are still walking.
 #include "trace_common.cuh"
@@ -43,7 +46,7 @@ struct WarpSmem {
 };
 
 template <bool FEAT, bool STATS>
-__global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, uint2 *__restrict__ cand_base) {
+__global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, uint4 *__restrict__ cand_base) {
     __shared__ WarpSmem smem[TB / 32];
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
@@ -54,8 +57,8 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
     const TraceArgs &a = p.a;
     const float alpha_min = a.alpha_min, T_min = a.T_min;
     const int back_culling = a.back_culling;
-    uint2 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
-    uint2 *my_cand = warp_cand + (size_t)lane * KB;
+    uint4 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
+    uint4 *my_cand = warp_cand + (size_t)lane * KB;
     unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
 
     int phase = PH_FETCH;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
     float T = 1.f;
     float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
     int g_last = -1, g_hi = INT_MAX, total = 0, cnt = 0, sp = 0, cur = 0;
-    bool saturated = false;   // the row is full and sorted; t_hi is the capacity bound (another pass may follow)
+    bool more = false;        // this pass's depth range was split: another pass follows unless the ray terminates
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = 0.f;
 
     // swizzled staging: the 4 quads of ray-lane q live at float4 index 4*q + (k ^ ((q >> 1) & 3)); both the
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
                     ray_setup(r);
                     T = 1.f;
                     t_last = -INFINITY; g_last = -1; total = 0;
-                    cnt = 0; sp = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; saturated = false;
+                    cnt = 0; sp = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; more = false;
                     phase = PH_TRAV;
                     if (STATS) ++st_pass;
                 }
@@ -140,27 +143,8 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
                     float t, alpha; int g;
                     if (leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
                         key_less(t_last, g_last, t, g) && key_less(t, g, t_hi, g_hi)) {
-                        if (!saturated) {
-                            my_cand[cnt] = make_uint2(__float_as_uint(t), (unsigned)(~cur));
-                            if (++cnt == KB) phase = PH_FULL;
-                        } else {
-                            // rare: more than KB candidates and no termination among the nearest KB -- keep the KB
-                            // nearest by sorted insertion (the row is sorted in this mode), dropping the farthest
-                            int i = KB - 1;
-                            while (i > 0) {
-                                const uint2 e = __ldcg(&my_cand[i - 1]);
-                                const float te = __uint_as_float(e.x);
-                                bool less = t < te;
-                                if (t == te) less = g < __float_as_int(__ldg(&p.recs[e.y].r1.w));
-                                if (!less) break;
-                                my_cand[i] = e;
-                                --i;
-                            }
-                            my_cand[i] = make_uint2(__float_as_uint(t), (unsigned)(~cur));
-                            const uint2 e = __ldcg(&my_cand[KB - 1]);
-                            t_hi = __uint_as_float(e.x);
-                            g_hi = __float_as_int(__ldg(&p.recs[e.y].r1.w));
-                        }
+                        my_cand[cnt] = make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), 0u);
+                        if (++cnt == KB) phase = PH_FULL;
                     }
                 }
                 if (pop && phase == PH_TRAV) {
@@ -188,57 +172,47 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
             __syncwarp();  // lane L's appended candidates are visible to the whole warp
             const int n = __shfl_sync(FULL, cnt, L);
             const bool is_full = __shfl_sync(FULL, phase, L) == PH_FULL;
-            // the ray of lane L, broadcast
-            RayCtx rl;
-            rl.ox = __shfl_sync(FULL, r.ox, L); rl.oy = __shfl_sync(FULL, r.oy, L); rl.oz = __shfl_sync(FULL, r.oz, L);
-            rl.dx = __shfl_sync(FULL, r.dx, L); rl.dy = __shfl_sync(FULL, r.dy, L); rl.dz = __shfl_sync(FULL, r.dz, L);
-            // lane i re-evaluates candidate i (same arithmetic as during the walk: identical t and alpha)
-            float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX; unsigned my_leaf = 0;
-            float nx = 0.f, ny = 0.f, nz = 0.f;
+            // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
+            float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX;
             if ((int)lane < n) {
-                const uint2 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
-                my_leaf = e.y;
-                const SurfelRec *rec = p.recs + my_leaf;
-                const float4 r1 = __ldg(&rec->r1);
-                leaf_eval(rl, __ldg(&rec->r0), r1, __ldg(&rec->r2), __ldg(&rec->r3), alpha_min, 0, my_t, my_g, my_a);
-                my_t = __uint_as_float(e.x);
-                nx = r1.x; ny = r1.y; nz = r1.z;
+                const uint4 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
+                my_t = __uint_as_float(e.x); my_g = (int)e.y; my_a = __uint_as_float(e.z);
             }
-            // rank by (t, surfel id)
             int rank = 0;
             for (int j = 0; j < n; ++j) {
                 const float tj = __shfl_sync(FULL, my_t, j);
                 const int gj = __shfl_sync(FULL, my_g, j);
                 rank += key_less(tj, gj, my_t, my_g) ? 1 : 0;
             }
-            // alphas in sorted order through shared memory, then the transmittance chain in sequential order
-            float *s_alpha = reinterpret_cast<float *>(ws.stage);
-            __syncwarp();
-            if ((int)lane < n) s_alpha[rank] = my_a;
-            __syncwarp();
+            {
+                float *s_f = reinterpret_cast<float *>(ws.stage);
+                int *s_i = reinterpret_cast<int *>(ws.stage);
+                if ((int)lane < n) { s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a; }
+                __syncwarp();
+                if ((int)lane < n) { my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; }
+                __syncwarp();
+            }
+            // transmittance chain in the reference's sequential order (bit-identical termination decisions)
             float Tc = __shfl_sync(FULL, T, L);
             float my_w = 0.f;
             int n_comp = n;
             bool term = false;
             for (int i = 0; i < n; ++i) {
-                const float ai = s_alpha[i];
-                if (rank == i) my_w = Tc * ai;
+                const float ai = __shfl_sync(FULL, my_a, i);
+                if ((int)lane == i) my_w = Tc * ai;
                 Tc *= (1.f - ai);
                 if (Tc < T_min) { n_comp = i + 1; term = true; break; }
             }
-            __syncwarp();
-            // the entry that ends the composited prefix / the row
-            const unsigned last_mask = __ballot_sync(FULL, (int)lane < n && rank == n_comp - 1);
-            const int last_lane = __ffs(last_mask) - 1;
-            const float t_end = __shfl_sync(FULL, my_t, last_lane);
-            const int g_end = __shfl_sync(FULL, my_g, last_lane);
             if (is_full) {
-                // trim: keep the composited prefix, in sorted order, and clip the walk to its last entry
-                __syncwarp();
-                if ((int)lane < n && rank < n_comp) warp_cand[(size_t)L * KB + rank] = make_uint2(__float_as_uint(my_t), my_leaf);
-                __syncwarp();
+                // terminated: keep the composited prefix; otherwise split the depth range at the KB/2-th candidate
+                const int keep = term ? n_comp : KB / 2;
+                const float t_end = __shfl_sync(FULL, my_t, keep - 1);
+                const int g_end = __shfl_sync(FULL, my_g, keep - 1);
+                if ((int)lane < keep)
+                    warp_cand[(size_t)L * KB + lane] = make_uint4(__float_as_uint(my_t), (unsigned)my_g, __float_as_uint(my_a), 0u);
                 if ((int)lane == L) {
-                    cnt = n_comp; t_hi = t_end; g_hi = g_end; saturated = (n_comp == KB);
+                    cnt = keep; t_hi = t_end; g_hi = g_end;
+                    if (!term) more = true;
                     // resume the walk: `cur` is the leaf that filled the row, pop the next node
                     if (sp == 0) phase = PH_COMP;
                     else { --sp; cur = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; phase = PH_TRAV; }
@@ -246,16 +220,19 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
                 if (__shfl_sync(FULL, phase, L) == PH_COMP) work |= (1u << L);  // stack ran empty: composite right away
                 continue;
             }
+            const float dxl = __shfl_sync(FULL, r.dx, L), dyl = __shfl_sync(FULL, r.dy, L), dzl = __shfl_sync(FULL, r.dz, L);
             // shade one hit per lane
             float c0 = 0.f, c1 = 0.f, c2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dd = 0.f, oo = 0.f;
             float f[FEAT ? NFMAX : 1];
 #pragma unroll
             for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) f[j] = 0.f;
-            const bool mine = (int)lane < n && rank < n_comp;
+            const bool mine = (int)lane < n_comp;
             if (mine) {
                 float Y[16];
-                sh_basis(a.deg, rl.dx, rl.dy, rl.dz, Y);
-                const float dg = dot3_rn(nx, ny, nz, rl.dx, rl.dy, rl.dz);
+                sh_basis(a.deg, dxl, dyl, dzl, Y);
+                const float nx = __ldg(a.normals + 3 * (size_t)my_g), ny = __ldg(a.normals + 3 * (size_t)my_g + 1),
+                            nz = __ldg(a.normals + 3 * (size_t)my_g + 2);
+                const float dg = dot3_rn(nx, ny, nz, dxl, dyl, dzl);
                 const float m = (-dg > 0.f) ? 1.f : -1.f;
                 float c[3];
                 sh_color(a.shs, a.K, a.deg, my_g, Y, c);
@@ -270,7 +247,7 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
             }
             const int64_t ray_L = __shfl_sync(FULL, ray, L);
             const int total_L = __shfl_sync(FULL, total, L);
-            if (a.hits != nullptr && mine && total_L + rank < a.hit_cap) a.hits[ray_L * a.hit_cap + total_L + rank] = my_g;
+            if (a.hits != nullptr && mine && total_L + (int)lane < a.hit_cap) a.hits[ray_L * a.hit_cap + total_L + lane] = my_g;
             c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
             n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2);
             dd = warp_sum(dd); oo = warp_sum(oo);
@@ -291,12 +268,12 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
                 }
                 T = Tc;
                 total += n_comp;
-                if (!term && cnt == KB) {
-                    // the nearest KB candidates were all composited without terminating: another pass, strictly
-                    // after the last one
-                    t_last = t_end; g_last = g_end;
+                if (!term && more) {
+                    // this pass covered the depth range up to (t_hi, g_hi) completely without terminating: the next
+                    // pass continues strictly after it
+                    t_last = t_hi; g_last = g_hi;
                     cnt = 0; sp = 0; cur = 0; t_lo = fmaxf(t_last, 0.f); t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX;
-                    saturated = false;
+                    more = false;
                     phase = PH_TRAV;
                     if (STATS) ++st_pass;
                 } else {
@@ -318,13 +295,13 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     int grid = h->sm_count * per_sm;
-    // candidate scratch: one 32-entry row per resident thread and stream slot (L2-resident: 256 B x ~100k threads)
+    // candidate scratch: one 32-entry row (512 B) per resident thread and stream slot; only rows in use are live in L2
     const int64_t threads = (int64_t)grid * TB;
     if (threads > h->cand_threads) {
         IRGS_CHECK(cudaDeviceSynchronize());
         if (h->cand) cudaFree(h->cand);
         h->cand = nullptr;
-        IRGS_CHECK(cudaMalloc(&h->cand, sizeof(uint2) * KB * (size_t)threads * 2));
+        IRGS_CHECK(cudaMalloc(&h->cand, sizeof(uint4) * KB * (size_t)threads * 2));
         h->cand_threads = threads;
     }
     const int64_t need = (n_rays + TB - 1) / TB;

@@ -205,14 +205,16 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
             }
             if (is_full) {
                 // terminated: keep the composited prefix; otherwise split the depth range at the KB/2-th candidate
-                const int keep = term ? n_comp : KB / 2;
+                // (a row that terminates only at its very last entry cannot be trimmed: it is split like any other)
+                const bool split = !(term && n_comp < KB);
+                const int keep = split ? KB / 2 : n_comp;
                 const float t_end = __shfl_sync(FULL, my_t, keep - 1);
                 const int g_end = __shfl_sync(FULL, my_g, keep - 1);
                 if ((int)lane < keep)
                     warp_cand[(size_t)L * KB + lane] = make_uint4(__float_as_uint(my_t), (unsigned)my_g, __float_as_uint(my_a), 0u);
                 if ((int)lane == L) {
                     cnt = keep; t_hi = t_end; g_hi = g_end;
-                    if (!term) more = true;
+                    if (split) more = true;
                     // resume the walk: `cur` is the leaf that filled the row, pop the next node
                     if (sp == 0) phase = PH_COMP;
                     else { --sp; cur = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; phase = PH_TRAV; }

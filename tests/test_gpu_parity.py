@@ -256,8 +256,15 @@ def test_proxy_build_and_surfel_build_give_identical_results(small_scene):
         tr = _tracer(g, mode, sc)
         outs.append(tr.trace_with_hits(o.to(DEV), d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"],
                                        g["features"], g["shs"], synth.ALPHA_MIN))
-    for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k
+    _assert_same_trace(outs[0], outs[1])
+
+
+def _assert_same_trace(a, b):
+    """Two acceleration structures over the same surfels: identical hit lists; composited sums agree to float
+    rounding (the warp-level reductions group the depth-ordered terms by traversal pass)."""
+    assert torch.equal(a["hit_count"], b["hit_count"]) and torch.equal(a["hits"], b["hits"])
+    for k in ("color", "normal", "feature", "depth", "alpha"):
+        assert float((a[k] - b[k]).abs().max()) <= 2e-6 * max(1.0, float(a[k].abs().max())), k
 
 
 def test_refit_equals_rebuild(small_scene):
@@ -275,8 +282,7 @@ def test_refit_equals_rebuild(small_scene):
     tr2 = _tracer(moved)
     b = tr2.trace_with_hits(o.to(DEV), d.to(DEV), moved["means3D"], moved["opacity"], moved["ru"], moved["rv"],
                             moved["normals"], moved["features"], moved["shs"], synth.ALPHA_MIN)
-    for k in a:
-        assert torch.equal(a[k], b[k]), k
+    _assert_same_trace(a, b)
     with pytest.raises(RuntimeError):
         tr.update_from_surfels(moved["means3D"][:-1], moved["opacity"][:-1], moved["ru"][:-1], moved["rv"][:-1],
                                moved["normals"][:-1], synth.ALPHA_MIN)
@@ -316,8 +322,7 @@ def test_general_proxy_mesh_layout(small_scene):
                            g["shs"], synth.ALPHA_MIN)
     b = _tracer(g).trace_with_hits(o.to(DEV), d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"],
                                    g["features"], g["shs"], synth.ALPHA_MIN)
-    for k in a:
-        assert torch.equal(a[k], b[k]), k
+    _assert_same_trace(a, b)
 
 
 # ---------------------------------------------------------------------------------------------- API behaviour

@@ -131,6 +131,10 @@ int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int 
 int64_t irgs_launch_count(void);
 void irgs_reset_launch_count(void);
 
+/* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
+ * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  Returns non-zero for unknown names. */
+int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
+
 /* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with
  * irgs_set_stats(h, 1): sums over rays of node visits, surfel tests, composited hits, traversal passes. */
 int irgs_set_stats(irgs_tracer_t *h, int enable);

@@ -33,6 +33,7 @@ PROTOTYPES = {
                                 + [_vp] * 2 + [_f32, _f32, _i32, _i64]),
     "irgs_launch_count": (_i64, []),
     "irgs_reset_launch_count": (None, []),
+    "irgs_set_option": (_i32, [_vp, ctypes.c_char_p, _i64]),
     "irgs_set_stats": (_i32, [_vp, _i32]),
     "irgs_get_stats": (_i32, [_vp, ctypes.POINTER(_i64)]),
 }

@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("IRGS_NVCC_DEFS", "").split()  # tuning experiments only, e.g. "-DIRGS_MIN_ACTIVE=16"
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

@@ -1,6 +1,7 @@
 // C ABI of libirgs_b200.so (see include/irgs_b200.h for the contract and the reference interface each entry replaces).
 #include <atomic>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 
@@ -93,6 +94,10 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     cudaFree(h->nodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
     cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
+    for (int i = 0; i < 2; ++i) {
+        for (int k = 0; k < 2; ++k) { cudaFree(h->rsort_keys[i][k]); cudaFree(h->rsort_vals[i][k]); }
+        cudaFree(h->rsort_hist[i]);
+    }
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
@@ -356,6 +361,15 @@ int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int 
 
 int64_t irgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void irgs_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
+    if (!h || !name) return fail("null argument");
+    if (strcmp(name, "sort_rays_min") == 0) {
+        h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
+        return 0;
+    }
+    return fail("unknown option");
+}
 
 int irgs_set_stats(irgs_tracer_t *h, int enable) {
     if (!h) return fail("null tracer handle");

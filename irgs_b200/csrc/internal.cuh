@@ -54,6 +54,13 @@ struct irgs_tracer {
     int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)
     uint4 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t, id, alpha, -)
     int64_t cand_threads = 0;               // threads one slot has room for
+    // ray-coherence sort scratch, per stream slot
+    uint32_t *rsort_keys[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int *rsort_vals[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int *rsort_hist[2] = {nullptr, nullptr};
+    int64_t rsort_cap[2] = {0, 0};
+    int sort_rays_min = 0;                  // forward calls with at least this many rays are coherence-sorted (0: never;
+                                            // measured on B200: the sort costs more than it saves, profiles/r01_notes.md)
     unsigned long long *stats = nullptr;    // [4]
     int stats_enabled = 0;
     bool built = false;
@@ -78,6 +85,8 @@ void count_launch(int n = 1);
 // lbvh.cu
 int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s);  // boxes[] already filled
 int lbvh_reserve(irgs_tracer *h, int64_t n);
+int launch_ray_order(irgs_tracer *h, const float *rays_o, const float *rays_d, int64_t n_rays, int **order_out,
+                     cudaStream_t s);
 int launch_bounds_from_proxy(irgs_tracer *h, const float *verts, int vps, cudaStream_t s);
 int launch_bounds_from_surfels(irgs_tracer *h, const float *means, const float *opacity, const float *ru,
                                const float *rv, const float *normals, float alpha_min, cudaStream_t s);
@@ -93,6 +102,7 @@ struct TraceArgs {
     float *color, *normal, *feature, *depth, *alpha;
     int32_t *hit_count, *hits;
     int hit_cap;
+    const int *ray_order;  // forward: optional processing order (coherence sort); results are still written per ray id
     // backward
     const float *gC, *gN, *gF, *gD, *gO;
     int64_t gout_period;  // 0: gout arrays have n_rays rows; >0: ray r reads row (gout_offset + r) % period

@@ -237,6 +237,83 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
     }
 }
 
+// Stable LSD sort of (key, value) pairs on the low 8*n_passes key bits; the sorted data ends up in keys/vals
+// (pointers are swapped as needed).  hist must hold 256 * ceil(n / RS_TILE) ints.
+int radix_sort_pairs(uint32_t *&keys, uint32_t *&keys_alt, int *&vals, int *&vals_alt, int n, int n_passes, int *hist,
+                     cudaStream_t s) {
+    const int n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    for (int pass = 0; pass < n_passes; ++pass) {
+        const int shift = 8 * pass;
+        radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(keys, n, shift, n_tiles, hist);
+        radix_scan_kernel<<<1, 1024, 0, s>>>(hist, 256 * n_tiles);
+        radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(keys, vals, n, shift, n_tiles, hist, keys_alt, vals_alt);
+        count_launch(3);
+        uint32_t *tk = keys; keys = keys_alt; keys_alt = tk;
+        int *tv = vals; vals = vals_alt; vals_alt = tv;
+    }
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+int radix_hist_ints(int n) { return 256 * ((n + RS_TILE - 1) / RS_TILE); }
+
+// Coherence key of a ray: 15-bit Morton code of the origin cell (32^3 grid over the root bound) followed by an
+// 8-bit octahedral direction bin.  Rays that start close together and point the same way become neighbours in a
+// warp of the forward kernel, so they walk the same nodes and reach their leaves together.
+__global__ void ray_key_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int n,
+                               const float *__restrict__ root, uint32_t *__restrict__ keys, int *__restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float lo = root[k], hi = root[3 + k];
+        const float ext = hi - lo;
+        float u = ext > 0.f ? (rays_o[3 * (size_t)i + k] - lo) / ext : 0.f;
+        u = fminf(fmaxf(u, 0.f), 1.f);
+        q[k] = (uint32_t)min((int)(u * 32.0f), 31);
+    }
+    const uint32_t cell = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    float dx = rays_d[3 * (size_t)i], dy = rays_d[3 * (size_t)i + 1], dz = rays_d[3 * (size_t)i + 2];
+    const float inv = 1.0f / fmaxf(fabsf(dx) + fabsf(dy) + fabsf(dz), 1e-30f);
+    float px = dx * inv, py = dy * inv;
+    if (dz < 0.f) {
+        const float ax = (1.0f - fabsf(py)) * (px >= 0.f ? 1.f : -1.f);
+        const float ay = (1.0f - fabsf(px)) * (py >= 0.f ? 1.f : -1.f);
+        px = ax; py = ay;
+    }
+    const uint32_t du = (uint32_t)min(max((int)((px * 0.5f + 0.5f) * 16.0f), 0), 15);
+    const uint32_t dv = (uint32_t)min(max((int)((py * 0.5f + 0.5f) * 16.0f), 0), 15);
+    keys[i] = (cell << 8) | (du << 4) | dv;
+    vals[i] = i;
+}
+
+int launch_ray_order(irgs_tracer *h, const float *rays_o, const float *rays_d, int64_t n_rays, int **order_out,
+                     cudaStream_t s) {
+    const int n = (int)n_rays;
+    const int slot = h->slot;
+    if (n_rays > h->rsort_cap[slot]) {
+        IRGS_CHECK(cudaDeviceSynchronize());
+        for (int k = 0; k < 2; ++k) {
+            if (h->rsort_keys[slot][k]) cudaFree(h->rsort_keys[slot][k]);
+            if (h->rsort_vals[slot][k]) cudaFree(h->rsort_vals[slot][k]);
+            h->rsort_keys[slot][k] = nullptr; h->rsort_vals[slot][k] = nullptr;
+            IRGS_CHECK(cudaMalloc(&h->rsort_keys[slot][k], sizeof(uint32_t) * (size_t)n_rays));
+            IRGS_CHECK(cudaMalloc(&h->rsort_vals[slot][k], sizeof(int) * (size_t)n_rays));
+        }
+        if (h->rsort_hist[slot]) cudaFree(h->rsort_hist[slot]);
+        h->rsort_hist[slot] = nullptr;
+        IRGS_CHECK(cudaMalloc(&h->rsort_hist[slot], sizeof(int) * (size_t)radix_hist_ints(n)));
+        h->rsort_cap[slot] = n_rays;
+    }
+    uint32_t *k0 = h->rsort_keys[slot][0], *k1 = h->rsort_keys[slot][1];
+    int *v0 = h->rsort_vals[slot][0], *v1 = h->rsort_vals[slot][1];
+    ray_key_kernel<<<(n + 255) / 256, 256, 0, s>>>(rays_o, rays_d, n, h->scene + 6, k0, v0);
+    count_launch();
+    if (radix_sort_pairs(k0, k1, v0, v1, n, 3, h->rsort_hist[slot], s)) return 1;
+    *order_out = v0;
+    return 0;
+}
+
 // Step 4: Karras 2012.  Keys are made unique by appending the sorted position.
 __device__ __forceinline__ int lcp(const uint32_t *__restrict__ codes, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
@@ -404,17 +481,7 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
     if (!refit_only) {
         morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, scene_i, n, h->codes, h->order);
         count_launch();
-        int n_tiles = (n + RS_TILE - 1) / RS_TILE;
-        for (int pass = 0; pass < 4; ++pass) {
-            int shift = 8 * pass;
-            radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(h->codes, n, shift, n_tiles, h->radix_hist);
-            radix_scan_kernel<<<1, 1024, 0, s>>>(h->radix_hist, 256 * n_tiles);
-            radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(h->codes, h->order, n, shift, n_tiles, h->radix_hist,
-                                                               h->codes_alt, h->order_alt);
-            count_launch(3);
-            uint32_t *tc = h->codes; h->codes = h->codes_alt; h->codes_alt = tc;
-            int *to = h->order; h->order = h->order_alt; h->order_alt = to;
-        }
+        if (radix_sort_pairs(h->codes, h->codes_alt, h->order, h->order_alt, n, 4, h->radix_hist, s)) return 1;
         int n_int = n > 1 ? n - 1 : 1;
         hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
         count_launch();

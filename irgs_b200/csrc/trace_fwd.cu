@@ -5,11 +5,12 @@
 //
 // Every lane owns one ray and runs a small state machine
 //     FETCH -> TRAV -> COMP -> (TRAV for another pass | FETCH)          TRAV -> FULL -> TRAV
-//   TRAV  near-first stack walk of the LBVH, one node or one leaf per iteration.  The 64-byte node / surfel record a
-//         lane needs is fetched by FOUR lanes (16 bytes each) so that one load instruction touches 8 cache lines
-//         instead of 32, staged through a swizzled shared-memory tile and read back by the owning lane: ncu showed the
-//         one-thread-per-record version bound by L1TEX wavefronts (one per distinct line per instruction), not by HBM
-//         or L2.  The traversal stack lives in shared memory ([entry][lane]: conflict free for any mix of depths).
+//   TRAV  near-first stack walk of the LBVH, one node or one leaf per iteration: four 16-byte loads fetch the 64-byte
+//         node (both children's bounds) or surfel record.  (A variant in which four lanes fetch 16 bytes each of one
+//         ray's record and stage it through a swizzled shared-memory tile -- 8 cache lines per load instruction instead
+//         of 32 -- is kept behind IRGS_COOP_FETCH; on B200 it measured 25 % SLOWER, the extra shuffles / stores /
+//         barriers cost more issue slots than the saved L1 wavefronts, see profiles/.)  The traversal stack lives in
+//         shared memory ([entry][lane]: conflict free for any mix of depths).
 //         A surfel that passes the plane / alpha test is APPENDED (one 16-byte store: t, surfel id, alpha; unsorted)
 //         to the lane's candidate row in a global scratch buffer (L2 resident).
 //   FULL  the row holds KB candidates: the warp sorts it co-operatively.  If the buffered hits alone already push the
@@ -30,7 +31,16 @@ namespace irgs {
 
 constexpr int KB = 32;             // candidates per row == warp width (one candidate per lane in the COMP phase)
 constexpr int SSTK = 32;           // traversal stack entries kept in shared memory; deeper entries spill to local
-constexpr int MIN_ACTIVE = 20;
+#ifndef IRGS_MIN_ACTIVE
+#define IRGS_MIN_ACTIVE 24
+#endif
+#ifndef IRGS_COOP_FETCH
+#define IRGS_COOP_FETCH 0
+#endif
+#ifndef IRGS_FWD_BLOCKS
+#define IRGS_FWD_BLOCKS 6
+#endif
+constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -46,7 +56,7 @@ struct WarpSmem {
 };
 
 template <bool FEAT, bool STATS>
-__global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, uint4 *__restrict__ cand_base) {
+__global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(const KParams p, uint4 *__restrict__ cand_base) {
     __shared__ WarpSmem smem[TB / 32];
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
@@ -87,6 +97,7 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
             if (phase == PH_FETCH) {
                 ray = (int64_t)base + __popc(need & lt_mask);
                 if (ray < a.n_rays) {
+                    if (a.ray_order != nullptr) ray = __ldg(a.ray_order + ray);
                     load_ray(a, ray, r);
                     ray_setup(r);
                     T = 1.f;
@@ -104,7 +115,10 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
         // ------------------------------------------------------------------ BVH walk
         const int thr = pool_empty ? 1 : MIN_ACTIVE;
         while (__popc(trav) >= thr) {
-            // co-operative fetch of the 64 bytes each walking lane needs next (node or surfel record)
+            // fetch the 64 bytes each walking lane needs next (node or surfel record)
+#if IRGS_COOP_FETCH
+            // co-operatively: four lanes fetch 16 bytes each of one ray's record, so that one load instruction touches
+            // 8 cache lines instead of 32; staged through the swizzled shared-memory tile
             const int want = (phase == PH_TRAV) ? cur : CUR_NONE;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -120,6 +134,14 @@ __global__ void __launch_bounds__(TB, 5) trace_forward_kernel(const KParams p, u
             const float4 q0 = ws.stage[4 * lane + (0 ^ rd_sw)], q1 = ws.stage[4 * lane + (1 ^ rd_sw)],
                          q2 = ws.stage[4 * lane + (2 ^ rd_sw)], q3 = ws.stage[4 * lane + (3 ^ rd_sw)];
             __syncwarp();
+#else
+            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+            if (phase == PH_TRAV) {
+                const float4 *src = cur >= 0 ? reinterpret_cast<const float4 *>(p.nodes + cur)
+                                             : reinterpret_cast<const float4 *>(p.recs + (~cur));
+                q0 = __ldg(src); q1 = __ldg(src + 1); q2 = __ldg(src + 2); q3 = __ldg(src + 3);
+            }
+#endif
             if (phase == PH_TRAV) {
                 bool pop = true;
                 if (cur >= 0) {
@@ -320,6 +342,11 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     p.a = a; p.nodes = h->nodes; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
+    if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31)) {
+        int *order = nullptr;
+        if (launch_ray_order(h, a.rays_o, a.rays_d, a.n_rays, &order, s)) return 1;
+        p.a.ray_order = order;
+    }
     // rays that hit nothing are never written by the kernel
     const size_t R = (size_t)a.n_rays;
     IRGS_CHECK(cudaMemsetAsync(a.color, 0, sizeof(float) * 3 * R, s));

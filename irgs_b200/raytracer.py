@@ -271,6 +271,10 @@ class GaussianTracer:
                 self.transmittance_min, int(back_culling), _stream(dev)))
         return out
 
+    def set_option(self, name, value):
+        """Tuning knobs of the native tracer (never change results), e.g. set_option("sort_rays_min", 0)."""
+        _lib.check(self.impl.lib.irgs_set_option(self.impl.h, name.encode(), int(value)))
+
     def set_stats(self, enable):
         _lib.check(self.impl.lib.irgs_set_stats(self.impl.h, int(enable)))
 

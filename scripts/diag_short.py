@@ -1,0 +1,23 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from irgs_b200 import synth
+from irgs_b200.raytracer import GaussianTracer
+import bench
+dev = torch.device("cuda:0")
+class A: surfels=300000; img=int(os.environ.get("IMG", 320)); spp=256
+def factory(sc, inp):
+    tr = GaussianTracer(transmittance_min=synth.T_MIN, device=dev)
+    tr.build_from_surfels(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], synth.ALPHA_MIN)
+    return tr
+sc, inp, tr, ro, rd = bench.build_workload(A, dev, 0, 1, factory)
+args = (inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"], synth.ALPHA_MIN)
+for srt in (0, 1 << 17):
+  tr.set_option("sort_rays_min", srt)
+  for n in (1 << 22, 1 << 24):
+    n = min(n, ro.shape[0]); best = 1e9
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = tr.trace_with_hits(ro[:n], rd[:n], *args, hit_cap=48); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(f"sort_min={srt} n={n} fwd(with hit lists) {best:.3f} ms {n/best/1e3:.1f} Mrays/s")

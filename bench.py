@@ -418,3 +418,5 @@ if __name__ == "__main__":
         run_reference(a)
     else:
         run_ours(a)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()

@@ -215,94 +215,32 @@ __device__ __forceinline__ void bwd_hit(const TraceArgs &a, const RayCtx &r, con
     }
 }
 
-// Replay of the saved hit lists, no traversal.  Persistent warps scan hit_count in tiles, queue the rays that have a
-// (complete) list in shared memory, and every lane replays one ray at a time, pulling the next from the queue as soon
-// as it is done: ~70 % of the secondary rays hit nothing and list lengths vary from 1 to hit_cap, so a fixed
-// thread-per-ray mapping ran at 8 of 32 lanes (ncu).  Ray gradients are pre-zeroed by the launcher.
-constexpr int RQ_CAP = 224;      // queue entries per warp
-constexpr int RQ_TILE = 4096;    // rays per tile grabbed from the global counter
-constexpr int RQ_MIN_ACTIVE = 24;
-
+// Replay of the saved hit lists: one thread per ray, no traversal.  (A persistent variant that compacts the ~30 % of
+// rays that have hits into a shared-memory queue and refills lanes individually ran at full warps but was not faster
+// -- 8.1 vs 7.2 ms per 6.5 M rays: the kernel is bound by the 16 vector reductions per hit, not by lane occupancy.)
 template <bool FEAT>
 __global__ void __launch_bounds__(TB) trace_backward_replay_kernel(const KParams p) {
-    __shared__ long long s_queue[TB / 32][RQ_CAP];
     const TraceArgs &a = p.a;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
-    long long *queue = s_queue[threadIdx.x >> 5];
-    int qn = 0;                       // warp-uniform
-    long long tile_base = 0; int tile_pos = RQ_TILE;   // warp-uniform scan cursor
-    bool scan_done = false;           // warp-uniform
-    bool active = false;
-    int64_t ray = 0; int i = 0, cnt = 0;
-    RayCtx r; float Y[16]; BwdState<FEAT> s;
-    const int32_t *hl = nullptr;
-    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = 0.f;
+    const int64_t ray = (int64_t)blockIdx.x * TB + threadIdx.x;
+    if (ray >= a.n_rays) return;
+    const int cnt = a.hit_count[ray];
+    float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+    // gaussiantrace_backward.cu:13-14: rays whose forward alpha is exactly zero contribute nothing
+    if (cnt > 0 && cnt <= a.hit_cap && a.alpha[ray] != 0.f) {
+        RayCtx r;
+        load_ray(a, ray, r);
+        float Y[16];
+        sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
+        BwdState<FEAT> s;
+        bwd_load<FEAT>(a, ray, s);
+        const int32_t *hl = a.hits + ray * a.hit_cap;
+        for (int i = 0; i < cnt; ++i) bwd_hit<FEAT>(a, r, Y, __ldg(hl + i), s);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) Y[k] = 0.f;
-    for (;;) {
-        // ---- keep the queue stocked
-        while (!scan_done && qn <= RQ_CAP - 128) {
-            if (tile_pos >= RQ_TILE) {
-                unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)RQ_TILE);
-                b = __shfl_sync(FULL, b, 0);
-                if (b >= (unsigned long long)a.n_rays) { scan_done = true; break; }
-                tile_base = (long long)b; tile_pos = 0;
-            }
-            const long long idx0 = tile_base + tile_pos + 4 * (long long)lane;
-            int hc[4];
+        for (int j = 0; j < 3; ++j) { go[j] = s.go[j]; gd[j] = s.gd[j]; }
+    }
+    if (cnt <= a.hit_cap) {  // rays with longer lists are written by the re-trace kernel
 #pragma unroll
-            for (int c = 0; c < 4; ++c) hc[c] = (idx0 + c < a.n_rays) ? __ldg(a.hit_count + idx0 + c) : 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool ok = hc[c] > 0 && hc[c] <= a.hit_cap;
-                const unsigned m = __ballot_sync(FULL, ok);
-                if (ok) queue[qn + __popc(m & lt_mask)] = idx0 + c;
-                qn += __popc(m);
-            }
-            tile_pos += 128;
-        }
-        __syncwarp();
-        // ---- hand queued rays to idle lanes
-        const unsigned idle = __ballot_sync(FULL, !active);
-        const int take = min(__popc(idle), qn);
-        if (!active) {
-            const int j = __popc(idle & lt_mask);
-            if (j < take) {
-                ray = queue[qn - 1 - j];
-                // gaussiantrace_backward.cu:13-14: rays whose forward alpha is exactly zero contribute nothing
-                if (a.alpha[ray] != 0.f) {
-                    load_ray(a, ray, r);
-                    sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
-                    bwd_load<FEAT>(a, ray, s);
-                    cnt = __ldg(a.hit_count + ray);
-                    hl = a.hits + ray * a.hit_cap;
-                    i = 0;
-                    active = true;
-                }
-            }
-        }
-        qn -= take;
-        __syncwarp();
-        unsigned act = __ballot_sync(FULL, active);
-        if (act == 0u) {
-            if (scan_done && qn == 0) break;
-            continue;
-        }
-        // ---- replay one hit per lane and iteration while enough lanes are busy
-        const int thr = (scan_done && qn == 0) ? 1 : RQ_MIN_ACTIVE;
-        do {
-            if (active) {
-                bwd_hit<FEAT>(a, r, Y, __ldg(hl + i), s);
-                if (++i == cnt) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) { a.g_rays_o[3 * ray + j] = s.go[j]; a.g_rays_d[3 * ray + j] = s.gd[j]; }
-                    active = false;
-                }
-            }
-            act = __ballot_sync(FULL, active);
-        } while (__popc(act) >= thr && act != 0u);
+        for (int j = 0; j < 3; ++j) { a.g_rays_o[3 * ray + j] = go[j]; a.g_rays_d[3 * ray + j] = gd[j]; }
     }
 }
 
@@ -504,12 +442,11 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p = make_params(h, a);
     const bool feat = a.S > 0;
     if (a.hits != nullptr && a.hit_count != nullptr) {
-        // rays without hits are never touched by the replay kernel
-        IRGS_CHECK(cudaMemsetAsync(a.g_rays_o, 0, sizeof(float) * 3 * (size_t)a.n_rays, s));
-        IRGS_CHECK(cudaMemsetAsync(a.g_rays_d, 0, sizeof(float) * 3 * (size_t)a.n_rays, s));
-        if (feat ? launch_persistent(h, trace_backward_replay_kernel<true>, p, a.n_rays, s)
-                 : launch_persistent(h, trace_backward_replay_kernel<false>, p, a.n_rays, s))
-            return 1;
+        const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
+        if (feat) trace_backward_replay_kernel<true><<<grid, TB, 0, s>>>(p);
+        else trace_backward_replay_kernel<false><<<grid, TB, 0, s>>>(p);
+        count_launch();
+        IRGS_CHECK(cudaGetLastError());
         return feat ? launch_persistent(h, trace_backward_retrace_kernel<true, true>, p, a.n_rays, s)
                     : launch_persistent(h, trace_backward_retrace_kernel<false, true>, p, a.n_rays, s);
     }

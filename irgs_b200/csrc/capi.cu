@@ -275,7 +275,7 @@ static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, i
                            float *out_normal_host, float *out_feature_host, float *out_depth_host,
                            float *out_alpha_host, float *g_rays_o_host, float *g_rays_d_host, float *grad_fused,
                            float *grad_features, float alpha_min, float T_min, int back_culling, int64_t chunk) {
-    const int hit_cap = with_backward ? 64 : 0;
+    const int hit_cap = with_backward ? 96 : 0;
     if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
     if (n_rays == 0) return 0;
     if (chunk <= 0) chunk = (int64_t)1 << 21;

@@ -5,12 +5,15 @@
 //
 // Every lane owns one ray and runs a small state machine
 //     FETCH -> TRAV -> COMP -> (TRAV for another pass | FETCH)          TRAV -> FULL -> TRAV
-//   TRAV  near-first stack walk of the LBVH, one node or one leaf per iteration: four 16-byte loads fetch the 64-byte
-//         node (both children's bounds) or surfel record.  (A variant in which four lanes fetch 16 bytes each of one
-//         ray's record and stage it through a swizzled shared-memory tile -- 8 cache lines per load instruction instead
-//         of 32 -- is kept behind IRGS_COOP_FETCH; on B200 it measured 25 % SLOWER, the extra shuffles / stores /
-//         barriers cost more issue slots than the saved L1 wavefronts, see profiles/.)  The traversal stack lives in
-//         shared memory ([entry][lane]: conflict free for any mix of depths).
+//   TRAV  near-first stack walk of the LBVH in two alternating sub-phases.  NODE: four 16-byte loads fetch a 64-byte
+//         node (both children's bounds), two slab tests; children that are leaves are not tested on the spot but
+//         pushed on a small per-lane queue of pending leaves (shared memory), internal children are walked / stacked.
+//         LEAF: all lanes that have pending leaves fetch one 64-byte surfel record each and run the plane / alpha test
+//         together.  Postponing the leaves is what keeps both sub-phases wide: with node and leaf work interleaved per
+//         iteration, ncu showed the leaf code (27 % of all issued instructions) running at 3.4 of 32 lanes.
+//         The traversal stack lives in shared memory ([entry][lane]: conflict free for any mix of depths).
+//         (A variant that fetched each 64-byte record with four lanes and staged it through a swizzled shared-memory
+//         tile measured 25 % slower than direct loads and was removed; profiles/r01_notes.md.)
 //         A surfel that passes the plane / alpha test is APPENDED (one 16-byte store: t, surfel id, alpha; unsorted)
 //         to the lane's candidate row in a global scratch buffer (L2 resident).
 //   FULL  the row holds KB candidates: the warp sorts it co-operatively.  If the buffered hits alone already push the
@@ -34,13 +37,14 @@ constexpr int SSTK = 32;           // traversal stack entries kept in shared mem
 #ifndef IRGS_MIN_ACTIVE
 #define IRGS_MIN_ACTIVE 24
 #endif
-#ifndef IRGS_COOP_FETCH
-#define IRGS_COOP_FETCH 0
-#endif
 #ifndef IRGS_FWD_BLOCKS
 #define IRGS_FWD_BLOCKS 6
 #endif
 constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
+#ifndef IRGS_PQ
+#define IRGS_PQ 6
+#endif
+constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -51,8 +55,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 struct WarpSmem {
-    float4 stage[4 * 32];     // [ray lane][quad ^ swizzle]
-    int stack[SSTK * 32];     // [entry][lane]
+    float scratch[3 * 32];    // co-operative sort scratch
+    int pend[PQ * 32];        // pending leaves [entry][lane]
+    int stack[SSTK * 32];     // traversal stack [entry][lane]
 };
 
 template <bool FEAT, bool STATS>
@@ -62,6 +67,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
     WarpSmem &ws = smem[tid >> 5];
     int *stk = ws.stack + lane;
+    int *pend = ws.pend + lane;
     int stack_spill[STACK - SSTK];
     const unsigned FULL = 0xffffffffu;
     const TraceArgs &a = p.a;
@@ -77,14 +83,9 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     RayCtx r;
     float T = 1.f;
     float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
-    int g_last = -1, g_hi = INT_MAX, total = 0, cnt = 0, sp = 0, cur = 0;
+    int g_last = -1, g_hi = INT_MAX, total = 0, cnt = 0, sp = 0, cur = CUR_NONE, pn = 0;
     bool more = false;        // this pass's depth range was split: another pass follows unless the ray terminates
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = 0.f;
-
-    // swizzled staging: the 4 quads of ray-lane q live at float4 index 4*q + (k ^ ((q >> 1) & 3)); both the
-    // co-operative 16-byte stores and the per-lane 16-byte loads are then bank-conflict free
-    const int my_quad = lane & 3;
-    const int rd_sw = (lane >> 1) & 3;
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
@@ -102,81 +103,69 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     ray_setup(r);
                     T = 1.f;
                     t_last = -INFINITY; g_last = -1; total = 0;
-                    cnt = 0; sp = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; more = false;
+                    cnt = 0; sp = 0; pn = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; more = false;
                     phase = PH_TRAV;
                     if (STATS) ++st_pass;
                 }
             }
             if (base + (unsigned long long)__popc(need) >= (unsigned long long)a.n_rays) pool_empty = true;
         }
-        unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);
-        if (trav == 0u && __ballot_sync(FULL, phase >= PH_COMP) == 0u) break;  // pool empty and every lane idle
+        if (__ballot_sync(FULL, phase != PH_FETCH) == 0u) break;  // pool empty and every lane idle
 
-        // ------------------------------------------------------------------ BVH walk
+        // ------------------------------------------------------------------ BVH walk, NODE sub-phase
         const int thr = pool_empty ? 1 : MIN_ACTIVE;
-        while (__popc(trav) >= thr) {
-            // fetch the 64 bytes each walking lane needs next (node or surfel record)
-#if IRGS_COOP_FETCH
-            // co-operatively: four lanes fetch 16 bytes each of one ray's record, so that one load instruction touches
-            // 8 cache lines instead of 32; staged through the swizzled shared-memory tile
-            const int want = (phase == PH_TRAV) ? cur : CUR_NONE;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int q = 8 * k + (lane >> 2);                   // ray lane served by this group of four
-                const int c = __shfl_sync(FULL, want, q);
-                if (c != CUR_NONE) {
-                    const float4 *src = c >= 0 ? reinterpret_cast<const float4 *>(p.nodes + c)
-                                               : reinterpret_cast<const float4 *>(p.recs + (~c));
-                    ws.stage[4 * q + (my_quad ^ ((q >> 1) & 3))] = __ldg(src + my_quad);
+        unsigned walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
+        // (a node visit can queue two leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
+        while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 2)) {
+            if (phase == PH_TRAV && cur != CUR_NONE) {
+                const float4 *src = reinterpret_cast<const float4 *>(p.nodes + cur);
+                const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+                if (STATS) ++st_nodes;
+                float tnL, tnR;
+                const bool hL = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_lo, t_hi, tnL);
+                const bool hR = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_lo, t_hi, tnR);
+                const int cl = __float_as_int(q3.x), cr = __float_as_int(q3.y);
+                const bool rightNear = hR && (!hL || tnR < tnL);
+                const int c_near = rightNear ? cr : cl, c_far = rightNear ? cl : cr;
+                const bool h_near = rightNear ? hR : hL, h_far = rightNear ? hL : hR;
+                int next = CUR_NONE;
+                if (h_near) {
+                    if (c_near < 0) { pend[pn * 32] = c_near; ++pn; }
+                    else next = c_near;
                 }
-            }
-            __syncwarp();
-            const float4 q0 = ws.stage[4 * lane + (0 ^ rd_sw)], q1 = ws.stage[4 * lane + (1 ^ rd_sw)],
-                         q2 = ws.stage[4 * lane + (2 ^ rd_sw)], q3 = ws.stage[4 * lane + (3 ^ rd_sw)];
-            __syncwarp();
-#else
-            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
-            if (phase == PH_TRAV) {
-                const float4 *src = cur >= 0 ? reinterpret_cast<const float4 *>(p.nodes + cur)
-                                             : reinterpret_cast<const float4 *>(p.recs + (~cur));
-                q0 = __ldg(src); q1 = __ldg(src + 1); q2 = __ldg(src + 2); q3 = __ldg(src + 3);
-            }
-#endif
-            if (phase == PH_TRAV) {
-                bool pop = true;
-                if (cur >= 0) {
-                    if (STATS) ++st_nodes;
-                    float tnL, tnR;
-                    const bool hL = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_lo, t_hi, tnL);
-                    const bool hR = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_lo, t_hi, tnR);
-                    const int cl = __float_as_int(q3.x), cr = __float_as_int(q3.y);
-                    if (hL && hR) {
-                        const bool rightNear = tnR < tnL;
-                        const int far_c = rightNear ? cl : cr;
-                        if (sp < SSTK) stk[sp * 32] = far_c;
-                        else if (sp < STACK) stack_spill[sp - SSTK] = far_c;
+                if (h_far) {
+                    if (c_far < 0) { pend[pn * 32] = c_far; ++pn; }
+                    else if (next == CUR_NONE) next = c_far;
+                    else {
+                        if (sp < SSTK) stk[sp * 32] = c_far;
+                        else if (sp < STACK) stack_spill[sp - SSTK] = c_far;
                         if (sp < STACK) ++sp;
-                        cur = rightNear ? cr : cl;
-                        pop = false;
-                    } else if (hL) { cur = cl; pop = false; }
-                    else if (hR) { cur = cr; pop = false; }
-                } else {
-                    if (STATS) ++st_leaf;
-                    float t, alpha; int g;
-                    if (leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
-                        key_less(t_last, g_last, t, g) && key_less(t, g, t_hi, g_hi)) {
-                        my_cand[cnt] = make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), 0u);
-                        if (++cnt == KB) phase = PH_FULL;
                     }
                 }
-                if (pop && phase == PH_TRAV) {
-                    if (sp == 0) phase = PH_COMP;
-                    else { --sp; cur = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; }
+                if (next == CUR_NONE && sp > 0) { --sp; next = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; }
+                cur = next;
+            }
+            walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
+        }
+
+        // ------------------------------------------------------------------ BVH walk, LEAF sub-phase
+        while (__any_sync(FULL, phase == PH_TRAV && pn > 0)) {
+            if (phase == PH_TRAV && pn > 0) {
+                --pn;
+                const int leaf = ~pend[pn * 32];
+                const float4 *src = reinterpret_cast<const float4 *>(p.recs + leaf);
+                const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+                if (STATS) ++st_leaf;
+                float t, alpha; int g;
+                if (leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
+                    key_less(t_last, g_last, t, g) && key_less(t, g, t_hi, g_hi)) {
+                    my_cand[cnt] = make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), 0u);
+                    if (++cnt == KB) phase = PH_FULL;   // pending leaves stay queued until the row has been trimmed
                 }
             }
-            trav = __ballot_sync(FULL, phase == PH_TRAV);
-            if (trav == 0u) break;
         }
+        // the walk of this pass is complete once the stack, the current node and the leaf queue are all empty
+        if (phase == PH_TRAV && cur == CUR_NONE && pn == 0) phase = PH_COMP;
 
         // ------------------------------------------------------------------ lanes whose pass found nothing
         if (phase == PH_COMP && cnt == 0) {
@@ -207,8 +196,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 rank += key_less(tj, gj, my_t, my_g) ? 1 : 0;
             }
             {
-                float *s_f = reinterpret_cast<float *>(ws.stage);
-                int *s_i = reinterpret_cast<int *>(ws.stage);
+                float *s_f = ws.scratch;
+                int *s_i = reinterpret_cast<int *>(ws.scratch);
                 if ((int)lane < n) { s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a; }
                 __syncwarp();
                 if ((int)lane < n) { my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; }
@@ -237,11 +226,10 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 if ((int)lane == L) {
                     cnt = keep; t_hi = t_end; g_hi = g_end;
                     if (split) more = true;
-                    // resume the walk: `cur` is the leaf that filled the row, pop the next node
-                    if (sp == 0) phase = PH_COMP;
-                    else { --sp; cur = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; phase = PH_TRAV; }
+                    // resume the walk; if nothing is left to walk the row is composited right away
+                    phase = (cur == CUR_NONE && pn == 0) ? PH_COMP : PH_TRAV;
                 }
-                if (__shfl_sync(FULL, phase, L) == PH_COMP) work |= (1u << L);  // stack ran empty: composite right away
+                if (__shfl_sync(FULL, phase, L) == PH_COMP) work |= (1u << L);
                 continue;
             }
             const float dxl = __shfl_sync(FULL, r.dx, L), dyl = __shfl_sync(FULL, r.dy, L), dzl = __shfl_sync(FULL, r.dz, L);
@@ -296,7 +284,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     // this pass covered the depth range up to (t_hi, g_hi) completely without terminating: the next
                     // pass continues strictly after it
                     t_last = t_hi; g_last = g_hi;
-                    cnt = 0; sp = 0; cur = 0; t_lo = fmaxf(t_last, 0.f); t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX;
+                    cnt = 0; sp = 0; pn = 0; cur = 0; t_lo = fmaxf(t_last, 0.f); t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX;
                     more = false;
                     phase = PH_TRAV;
                     if (STATS) ++st_pass;

@@ -76,7 +76,7 @@ int irgs_tracer_create(irgs_tracer_t **out, int device) {
         return fail("libirgs_b200 is built for sm_100a (B200) only");
     }
     h->sm_count = prop.multiProcessorCount;
-    if (!check(cudaMalloc(&h->scene, 16 * sizeof(float)), "cudaMalloc") ||
+    if (!check(cudaMalloc(&h->scene, 24 * sizeof(float)), "cudaMalloc") ||
         !check(cudaMalloc(&h->counter, 4 * sizeof(unsigned long long)), "cudaMalloc") ||
         !check(cudaMalloc(&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc")) {
         irgs_tracer_destroy(h);
@@ -91,7 +91,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->nodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
+    cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
     cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
     for (int i = 0; i < 2; ++i) {

@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libirgs_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <string>
 
@@ -32,6 +33,19 @@ static_assert(sizeof(SurfelRec) == 64, "record must be 64 bytes");
 
 #define IRGS_EMPTY_FAR 1.0e30f
 
+// Traversal copy of a node: 32 bytes, i.e. TWO 16-byte loads per visit instead of four (ncu: the walk is bound by the
+// L1TEX tag stage -- one lookup per 16-byte request -- not by DRAM or L2 bandwidth).  Child bounds are quantised
+// conservatively (lo rounded down, hi up) to 16 bits per coordinate on a grid spanning the padded root bound:
+//   per child: w0 = lo.x | lo.y << 16,  w1 = lo.z | hi.x << 16,  w2 = hi.y | hi.z << 16,  w3 = child reference
+// child reference: >= 0 internal node, < 0 leaf ~pos, IRGS_CHILD_NONE = no child (empty bound).
+// Coordinate q decodes to frame_lo + q/65536 * frame_ext; the ray walk folds the decode into one fma per plane by
+// building the float 1 + q/65536 directly in the mantissa.
+struct __align__(16) QNode {
+    uint4 l, r;
+};
+static_assert(sizeof(QNode) == 32, "quantised node must be 32 bytes");
+#define IRGS_CHILD_NONE INT_MIN
+
 }  // namespace irgs
 
 struct irgs_tracer {
@@ -39,7 +53,8 @@ struct irgs_tracer {
     int sm_count = 148;
     int64_t n = 0;         // surfels in the structure
     int64_t cap = 0;       // allocated capacity (surfels)
-    irgs::Node *nodes = nullptr;        // [max(n-1,1)]
+    irgs::Node *nodes = nullptr;        // [max(n-1,1)] float bounds (refit works on these)
+    irgs::QNode *qnodes = nullptr;      // [max(n-1,1)] quantised copy the ray walk reads
     float *boxes = nullptr;             // [n,6] unpadded per-surfel bounds, surfel order
     uint32_t *codes = nullptr, *codes_alt = nullptr;  // [n]
     int *order = nullptr, *order_alt = nullptr;       // [n] leaf position -> surfel id
@@ -48,7 +63,8 @@ struct irgs_tracer {
     int *flags = nullptr;               // [n]   bottom-up arrival counters
     int *radix_hist = nullptr;          // [256 * n_tiles]
     int64_t radix_tiles_cap = 0;
-    float *scene = nullptr;             // [16]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats), 12 pad
+    float *scene = nullptr;             // [24]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats),
+                                        //       12-14 quantisation frame lo, 15-17 frame extent
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
     unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
     int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)

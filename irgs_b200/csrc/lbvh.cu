@@ -432,6 +432,59 @@ __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restr
     }
 }
 
+// Step 6: quantised traversal copy of the nodes (see QNode in internal.cuh).
+__global__ void quant_frame_kernel(float *scene) {
+    // frame: lo = root lo; extent slightly larger than the root's so that code 65535 decodes beyond the root hi
+    const int k = threadIdx.x;
+    if (k < 3) {
+        const float lo = scene[6 + k], hi = scene[9 + k];
+        float ext = (hi >= lo) ? (hi - lo) : 0.f;
+        ext = ext * (65536.0f / 65535.0f) * (1.0f + 8e-6f) + 1e-30f;
+        scene[12 + k] = lo;
+        scene[15 + k] = ext;
+    }
+}
+__device__ __forceinline__ float qdecode(unsigned q, float lo, float ext) {
+    return fmaf(__uint_as_float(0x3F800000u | (q << 7)), ext, lo - ext);
+}
+__device__ __forceinline__ unsigned quant_lo(float x, float lo, float ext) {
+    int q = (int)floorf((x - lo) / ext * 65536.0f);
+    q = min(max(q, 0), 65535);
+    while (q > 0 && qdecode((unsigned)q, lo, ext) > x) --q;
+    return (unsigned)q;
+}
+__device__ __forceinline__ unsigned quant_hi(float x, float lo, float ext) {
+    int q = (int)ceilf((x - lo) / ext * 65536.0f);
+    q = min(max(q, 0), 65535);
+    while (q < 65535 && qdecode((unsigned)q, lo, ext) < x) ++q;
+    return (unsigned)q;
+}
+__global__ void quantize_nodes_kernel(const Node *__restrict__ nodes, int n_int, const float *__restrict__ scene,
+                                      QNode *__restrict__ qnodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_int) return;
+    const float *f = reinterpret_cast<const float *>(nodes + i);
+    const int4 d = nodes[i].d;
+    uint4 out[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float *b = f + 6 * c;
+        unsigned q[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        int ref = c == 0 ? d.x : d.y;
+        if (b[0] >= IRGS_EMPTY_FAR) ref = IRGS_CHILD_NONE;
+        else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                q[k] = quant_lo(b[k], scene[12 + k], scene[15 + k]);
+                q[3 + k] = quant_hi(b[3 + k], scene[12 + k], scene[15 + k]);
+            }
+        }
+        out[c] = make_uint4(q[0] | (q[1] << 16), q[2] | (q[3] << 16), q[4] | (q[5] << 16), (unsigned)ref);
+    }
+    qnodes[i].l = out[0];
+    qnodes[i].r = out[1];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 template <typename T>
 static bool realloc_dev(T *&p, size_t count) {
@@ -443,7 +496,7 @@ static bool realloc_dev(T *&p, size_t count) {
 int lbvh_reserve(irgs_tracer *h, int64_t n) {
     if (n <= h->cap) return 0;
     int64_t c = n;
-    if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
+    if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->qnodes, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
         !realloc_dev(h->codes_alt, (size_t)c) || !realloc_dev(h->order, (size_t)c) || !realloc_dev(h->order_alt, (size_t)c) ||
         !realloc_dev(h->leaf_parent, (size_t)c) || !realloc_dev(h->node_parent, (size_t)c) ||
         !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c))
@@ -489,7 +542,10 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
     IRGS_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(int) * (size_t)n, s));
     refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, scene_i, h->nodes,
                                                  h->flags, h->scene + 6);
-    count_launch();
+    const int n_internal = n > 1 ? n - 1 : 1;
+    quant_frame_kernel<<<1, 32, 0, s>>>(h->scene);
+    quantize_nodes_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, n_internal, h->scene, h->qnodes);
+    count_launch(3);
     IRGS_CHECK(cudaGetLastError());
     h->built = true;
     return 0;

@@ -55,13 +55,12 @@ __device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, f
     const int back_culling = p.a.back_culling;
     for (;;) {
         if (cur >= 0) {
-            const Node *nd = p.nodes + cur;
-            const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
-            const int4 d = __ldg(&nd->d);
+            const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
+            const int2 d = make_int2((int)wl.w, (int)wr.w);
             if (STATS) ++n_nodes;
             float tnL, tnR;
-            bool hL = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, t_lo, t_hi, tnL);
-            bool hR = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, t_lo, t_hi, tnR);
+            bool hL = slab(r, wl, t_lo, t_hi, tnL);
+            bool hR = slab(r, wr, t_lo, t_hi, tnR);
             if (hL && hR) {
                 bool rightNear = tnR < tnL;
                 int nearC = rightNear ? d.y : d.x, farC = rightNear ? d.x : d.y;
@@ -254,7 +253,7 @@ __device__ __forceinline__ void retrace_ray(const KParams &p, int64_t ray, float
     if (a.alpha[ray] != 0.f) {
         RayCtx r;
         load_ray(a, ray, r);
-        ray_setup(r);
+        ray_setup(r, p.qframe);
         float Y[16];
         sh_basis(a.deg, r.dx, r.dy, r.dz, Y);
         BwdState<FEAT> s;
@@ -348,18 +347,17 @@ __global__ void __launch_bounds__(TB) intersection_test_kernel(const KParams p, 
     if (ray >= a.n_rays) return;
     RayCtx r;
     load_ray(a, ray, r);
-    ray_setup(r);
+    ray_setup(r, p.qframe);
     int stack_n[STACK];
     int sp = 0, cur = 0;
     bool found = false;
     for (;;) {
         if (cur >= 0) {
-            const Node *nd = p.nodes + cur;
-            const float4 qa = __ldg(&nd->a), qb = __ldg(&nd->b), qc = __ldg(&nd->c);
-            const int4 d = __ldg(&nd->d);
+            const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
+            const int2 d = make_int2((int)wl.w, (int)wr.w);
             float tnL, tnR;
-            bool hL = slab(r, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, 0.f, IRGS_T_SCENE_MAX, tnL);
-            bool hR = slab(r, qb.z, qb.w, qc.x, qc.y, qc.z, qc.w, 0.f, IRGS_T_SCENE_MAX, tnR);
+            bool hL = slab(r, wl, 0.f, IRGS_T_SCENE_MAX, tnL);
+            bool hR = slab(r, wr, 0.f, IRGS_T_SCENE_MAX, tnR);
             if (hL && hR) { if (sp < STACK) stack_n[sp++] = d.y; cur = d.x; continue; }
             else if (hL) { cur = d.x; continue; }
             else if (hR) { cur = d.y; continue; }
@@ -411,7 +409,8 @@ static int persistent_grid(irgs_tracer *h, const void *kernel) {
 static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
     KParams p;
     p.a = a;
-    p.nodes = h->nodes;
+    p.nodes = h->qnodes;
+    p.qframe = h->scene + 12;
     p.recs = h->recs;
     p.counter = h->counter + h->slot;
     p.stats = h->stats;

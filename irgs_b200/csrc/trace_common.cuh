@@ -24,7 +24,8 @@ __device__ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442
 
 struct KParams {
     TraceArgs a;
-    const Node *nodes;
+    const QNode *nodes;
+    const float *qframe;   // [6] quantisation frame: lo xyz, extent xyz
     const SurfelRec *recs;
     unsigned long long *counter;
     unsigned long long *stats;
@@ -96,31 +97,41 @@ __device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, i
 // ------------------------------------------------------------------------------------------------ traversal
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz;
-    float idx, idy, idz, oodx, oody, oodz;
+    // slab-test constants for quantised planes: t = fma(1 + q/65536, a, b)
+    float ax, ay, az, bx, by, bz;
 };
 
-// Slab-test constants.  fma(plane, 1/d, -o/d) carries an absolute error of about (|o| + |plane - o|) * 2^-23 in SPACE
-// (the error in t scales with 1/d exactly like the t-extent of a spatial pad does), independent of how small a
-// direction component is.  The leaf bounds are therefore padded in space at refit time (lbvh.cu: 8e-6 x scene
-// scale + 1e-4 x extent) and the interval test itself needs no slack; ray origins are assumed to lie within ~16
-// scene diameters (beyond that the reference's own float32 plane arithmetic is equally fuzzy).
-__device__ __forceinline__ void ray_setup(RayCtx &r) {
+// The slab test evaluates t = (plane - o) / d as ONE fma per plane.  For a plane stored as the 16-bit code q on the
+// frame (lo, ext): plane = lo + q/65536 * ext = (lo - ext) + v * ext with v = 1 + q/65536 built directly in a float's
+// mantissa, so t = v * (ext/d) + (lo - ext - o)/d.  The fma carries an absolute error of about
+// (|o| + |plane - o|) * 2^-23 in SPACE (the error in t scales with 1/d exactly like the t-extent of a spatial pad
+// does), independent of how small a direction component is; the leaf bounds are padded in space at refit time
+// (lbvh.cu: 8e-6 x scene scale + 1e-4 x extent) and quantised conservatively, so the interval test needs no slack.
+// Ray origins are assumed to lie within ~16 scene diameters (beyond that the reference's own float32 plane arithmetic
+// is equally fuzzy).
+__device__ __forceinline__ void ray_setup(RayCtx &r, const float *__restrict__ qframe) {
     const float tiny = 1e-30f;  // a zero component would give 0 * inf = NaN
-    float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
-    float sy = fabsf(r.dy) > tiny ? r.dy : copysignf(tiny, r.dy);
-    float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
-    r.idx = 1.0f / sx; r.idy = 1.0f / sy; r.idz = 1.0f / sz;
-    r.oodx = r.ox * r.idx; r.oody = r.oy * r.idy; r.oodz = r.oz * r.idz;
+    const float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
+    const float sy = fabsf(r.dy) > tiny ? r.dy : copysignf(tiny, r.dy);
+    const float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
+    const float ix = 1.0f / sx, iy = 1.0f / sy, iz = 1.0f / sz;
+    const float lx = __ldg(qframe), ly = __ldg(qframe + 1), lz = __ldg(qframe + 2);
+    const float ex = __ldg(qframe + 3), ey = __ldg(qframe + 4), ez = __ldg(qframe + 5);
+    r.ax = ex * ix; r.ay = ey * iy; r.az = ez * iz;
+    r.bx = (lx - ex - r.ox) * ix; r.by = (ly - ey - r.oy) * iy; r.bz = (lz - ez - r.oz) * iz;
 }
 
-__device__ __forceinline__ bool slab(const RayCtx &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
-                                     float t_lo, float t_hi, float &tn) {
-    float x0 = __fmaf_rn(lox, r.idx, -r.oodx), x1 = __fmaf_rn(hix, r.idx, -r.oodx);
-    float y0 = __fmaf_rn(loy, r.idy, -r.oody), y1 = __fmaf_rn(hiy, r.idy, -r.oody);
-    float z0 = __fmaf_rn(loz, r.idz, -r.oodz), z1 = __fmaf_rn(hiz, r.idz, -r.oodz);
+__device__ __forceinline__ float qlo16(unsigned w) { return __uint_as_float(((w << 7) & 0x007FFF80u) | 0x3F800000u); }
+__device__ __forceinline__ float qhi16(unsigned w) { return __uint_as_float(((w >> 9) & 0x007FFF80u) | 0x3F800000u); }
+
+// one child of a quantised node: w = (lo.x|lo.y<<16, lo.z|hi.x<<16, hi.y|hi.z<<16, ref)
+__device__ __forceinline__ bool slab(const RayCtx &r, const uint4 w, float t_lo, float t_hi, float &tn) {
+    const float x0 = __fmaf_rn(qlo16(w.x), r.ax, r.bx), x1 = __fmaf_rn(qhi16(w.y), r.ax, r.bx);
+    const float y0 = __fmaf_rn(qhi16(w.x), r.ay, r.by), y1 = __fmaf_rn(qlo16(w.z), r.ay, r.by);
+    const float z0 = __fmaf_rn(qlo16(w.y), r.az, r.bz), z1 = __fmaf_rn(qhi16(w.z), r.az, r.bz);
     tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
-    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
-    return tn <= tf;
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+    return (int)w.w != IRGS_CHILD_NONE && tn <= tf;
 }
 
 // Plane hit of a packed record (already in registers).  Arithmetic order == eval_surfel() of

@@ -5,8 +5,8 @@
 //
 // Every lane owns one ray and runs a small state machine
 //     FETCH -> TRAV -> COMP -> (TRAV for another pass | FETCH)          TRAV -> FULL -> TRAV
-//   TRAV  near-first stack walk of the LBVH in two alternating sub-phases.  NODE: four 16-byte loads fetch a 64-byte
-//         node (both children's bounds), two slab tests; children that are leaves are not tested on the spot but
+//   TRAV  near-first stack walk of the LBVH in two alternating sub-phases.  NODE: two 16-byte loads fetch a 32-byte
+//         quantised node (both children's bounds, 16 bits per coordinate, conservative), two slab tests; children that are leaves are not tested on the spot but
 //         pushed on a small per-lane queue of pending leaves (shared memory), internal children are walked / stacked.
 //         LEAF: all lanes that have pending leaves fetch one 64-byte surfel record each and run the plane / alpha test
 //         together.  Postponing the leaves is what keeps both sub-phases wide: with node and leaf work interleaved per
@@ -55,7 +55,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 struct WarpSmem {
-    float scratch[3 * 32];    // co-operative sort scratch
+    float scratch[(8 + NFMAX) * 32];   // co-operative sort / accumulation scratch
     int pend[PQ * 32];        // pending leaves [entry][lane]
     int stack[SSTK * 32];     // traversal stack [entry][lane]
 };
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     float t_last = -INFINITY, t_lo = 0.f, t_hi = IRGS_T_SCENE_MAX;
     int g_last = -1, g_hi = INT_MAX, total = 0, cnt = 0, sp = 0, cur = CUR_NONE, pn = 0;
     bool more = false;        // this pass's depth range was split: another pass follows unless the ray terminates
-    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.idx = r.idy = r.idz = r.oodx = r.oody = r.oodz = 0.f;
+    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f; r.ax = r.ay = r.az = r.bx = r.by = r.bz = 0.f;
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 if (ray < a.n_rays) {
                     if (a.ray_order != nullptr) ray = __ldg(a.ray_order + ray);
                     load_ray(a, ray, r);
-                    ray_setup(r);
+                    ray_setup(r, p.qframe);
                     T = 1.f;
                     t_last = -INFINITY; g_last = -1; total = 0;
                     cnt = 0; sp = 0; pn = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; more = false;
@@ -118,13 +118,12 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         // (a node visit can queue two leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
         while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 2)) {
             if (phase == PH_TRAV && cur != CUR_NONE) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.nodes + cur);
-                const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+                const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
                 if (STATS) ++st_nodes;
                 float tnL, tnR;
-                const bool hL = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_lo, t_hi, tnL);
-                const bool hR = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_lo, t_hi, tnR);
-                const int cl = __float_as_int(q3.x), cr = __float_as_int(q3.y);
+                const bool hL = slab(r, wl, t_lo, t_hi, tnL);
+                const bool hR = slab(r, wr, t_lo, t_hi, tnR);
+                const int cl = (int)wl.w, cr = (int)wr.w;
                 const bool rightNear = hR && (!hL || tnR < tnL);
                 const int c_near = rightNear ? cr : cl, c_far = rightNear ? cl : cr;
                 const bool h_near = rightNear ? hR : hL, h_far = rightNear ? hL : hR;
@@ -260,24 +259,37 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const int64_t ray_L = __shfl_sync(FULL, ray, L);
             const int total_L = __shfl_sync(FULL, total, L);
             if (a.hits != nullptr && mine && total_L + (int)lane < a.hit_cap) a.hits[ray_L * a.hit_cap + total_L + lane] = my_g;
-            c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
-            n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2);
-            dd = warp_sum(dd); oo = warp_sum(oo);
-            if (FEAT) {
-#pragma unroll
-                for (int j = 0; j < NFMAX; ++j)
-                    if (j < a.S) f[j] = warp_sum(f[j]);
-            }
-            if ((int)lane == L) {
-                // outputs are pre-zeroed by the launcher: every pass adds its share
-                a.color[3 * ray] += c0; a.color[3 * ray + 1] += c1; a.color[3 * ray + 2] += c2;
-                a.normal[3 * ray] += n0; a.normal[3 * ray + 1] += n1; a.normal[3 * ray + 2] += n2;
-                a.depth[ray] += dd; a.alpha[ray] += oo;
+            // Sequential accumulation in depth order, exactly like the reference's loop (and the oracle's): channel k of
+            // the ray's outputs is owned by lane k, which adds the n_comp terms one after the other to the running value
+            // in global memory (pre-zeroed by the launcher).  The result is therefore independent of how the hits were
+            // grouped into passes and of the acceleration structure's topology.
+            {
+                float *s_c = ws.scratch;   // [channel][hit]
+                __syncwarp();
+                s_c[0 * 32 + lane] = c0; s_c[1 * 32 + lane] = c1; s_c[2 * 32 + lane] = c2;
+                s_c[3 * 32 + lane] = n0; s_c[4 * 32 + lane] = n1; s_c[5 * 32 + lane] = n2;
+                s_c[6 * 32 + lane] = dd; s_c[7 * 32 + lane] = oo;
                 if (FEAT) {
 #pragma unroll
                     for (int j = 0; j < NFMAX; ++j)
-                        if (j < a.S) a.feature[ray * a.S + j] += f[j];
+                        if (j < a.S) s_c[(8 + j) * 32 + lane] = f[j];
                 }
+                __syncwarp();
+                const int n_ch = 8 + (FEAT ? a.S : 0);
+                if ((int)lane < n_ch) {
+                    float *dst;
+                    if (lane < 3) dst = a.color + 3 * ray_L + lane;
+                    else if (lane < 6) dst = a.normal + 3 * ray_L + (lane - 3);
+                    else if (lane == 6) dst = a.depth + ray_L;
+                    else if (lane == 7) dst = a.alpha + ray_L;
+                    else dst = a.feature + ray_L * a.S + (lane - 8);
+                    float acc = *dst;
+                    for (int i = 0; i < n_comp; ++i) acc += s_c[lane * 32 + i];
+                    *dst = acc;
+                }
+                __syncwarp();
+            }
+            if ((int)lane == L) {
                 T = Tc;
                 total += n_comp;
                 if (!term && more) {
@@ -327,7 +339,7 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p;
-    p.a = a; p.nodes = h->nodes; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
+    p.a = a; p.nodes = h->qnodes; p.qframe = h->scene + 12; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
     if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31)) {

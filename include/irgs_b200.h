@@ -132,8 +132,7 @@ int64_t irgs_launch_count(void);
 void irgs_reset_launch_count(void);
 
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
- * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "leaf_size": surfels per BVH leaf
- * (1..8) used by the next build.  Returns non-zero for unknown names. */
+ * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 
 /* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with

@@ -368,11 +368,6 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
         return 0;
     }
-    if (strcmp(name, "leaf_size") == 0) {   // takes effect at the next build_bvh
-        if (value < 1 || value > 8) return fail("leaf_size must be in [1, 8]");
-        h->leaf_size = (int)value;
-        return 0;
-    }
     return fail("unknown option");
 }
 

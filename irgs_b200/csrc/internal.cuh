@@ -79,8 +79,6 @@ struct irgs_tracer {
                                             // measured on B200: the sort costs more than it saves, profiles/r01_notes.md)
     unsigned long long *stats = nullptr;    // [4]
     int stats_enabled = 0;
-    int leaf_size = 4;                      // surfels per leaf for the NEXT build (1..8)
-    int built_leaf_size = 1;                // surfels per leaf of the current structure
     bool built = false;
     // host-streaming resources
     cudaStream_t hs[2] = {nullptr, nullptr};

@@ -315,14 +315,12 @@ int launch_ray_order(irgs_tracer *h, const float *rays_o, const float *rays_d, i
 }
 
 // Step 4: Karras 2012.  Keys are made unique by appending the sorted position.
-// A leaf is a cluster of `ls` consecutive surfels in Morton order (key = code of its first surfel); n = #clusters.
-__device__ __forceinline__ int lcp_s(const uint32_t *__restrict__ codes, int ls, int n, int i, int j) {
+__device__ __forceinline__ int lcp(const uint32_t *__restrict__ codes, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
-    uint32_t a = codes[(size_t)i * ls], b = codes[(size_t)j * ls];
+    uint32_t a = codes[i], b = codes[j];
     return a == b ? 32 + __clz(i ^ j) : __clz(a ^ b);
 }
-#define lcp(codes, n, i, j) lcp_s(codes, ls, n, i, j)
-__global__ void hierarchy_kernel(const uint32_t *__restrict__ codes, int ls, int n, Node *__restrict__ nodes,
+__global__ void hierarchy_kernel(const uint32_t *__restrict__ codes, int n, Node *__restrict__ nodes,
                                  int *__restrict__ leaf_parent, int *__restrict__ node_parent) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 1) {
@@ -379,12 +377,10 @@ __device__ __forceinline__ void load_slot(const Node *nd, int side, float lo[3],
     }
 }
 
-#undef lcp
 __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restrict__ order,
-                             const int *__restrict__ leaf_parent, const int *__restrict__ node_parent, int n_surf,
-                             int ls, int n, const int *__restrict__ scene_i, Node *nodes, int *flags,
-                             float *root_bound) {
-    int leaf = blockIdx.x * blockDim.x + threadIdx.x;   // cluster index
+                             const int *__restrict__ leaf_parent, const int *__restrict__ node_parent, int n,
+                             const int *__restrict__ scene_i, Node *nodes, int *flags, float *root_bound) {
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
     // absolute pad: a few float ulps of the scene scale, so that neither the rounding of the fma slab test nor that
     // of the plane-hit arithmetic (trace_common.cuh leaf_test) can make the walk reject a surfel the hit test accepts;
@@ -396,18 +392,17 @@ __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restr
         if (clo <= chi) scale = fmaxf(scale, fmaxf(chi - clo, fmaxf(fabsf(clo), fabsf(chi))));
     }
     const float pad_abs = 8e-6f * scale;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int m = 0; m < ls; ++m) {   // union of the padded member bounds
-        const int pos = leaf * ls + m;
-        if (pos >= n_surf) break;
-        const float *bx = boxes + 6 * (size_t)order[pos];
-        if (!(bx[0] <= bx[3])) continue;
+    const float *bx = boxes + 6 * (size_t)order[leaf];
+    float lo[3], hi[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float a = bx[k], b = bx[3 + k];
-            float pad = 1e-4f * (b - a) + pad_abs;
-            lo[k] = fminf(lo[k], a - pad); hi[k] = fmaxf(hi[k], b + pad);
-        }
+    for (int k = 0; k < 3; ++k) {
+        float a = bx[k], b = bx[3 + k];
+        float pad = 1e-4f * (b - a) + pad_abs;
+        lo[k] = a - pad; hi[k] = b + pad;
+    }
+    if (!(bx[0] <= bx[3])) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
     }
     int p = leaf_parent[leaf];
     if (n == 1) {
@@ -540,18 +535,14 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
         morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, scene_i, n, h->codes, h->order);
         count_launch();
         if (radix_sort_pairs(h->codes, h->codes_alt, h->order, h->order_alt, n, 4, h->radix_hist, s)) return 1;
-        h->built_leaf_size = h->leaf_size;
-    }
-    const int ls = h->built_leaf_size;
-    const int m = (n + ls - 1) / ls;                 // clusters == leaves
-    const int n_internal = m > 1 ? m - 1 : 1;
-    if (!refit_only) {
-        hierarchy_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->codes, ls, m, h->nodes, h->leaf_parent, h->node_parent);
+        int n_int = n > 1 ? n - 1 : 1;
+        hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
         count_launch();
     }
     IRGS_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(int) * (size_t)n, s));
-    refit_kernel<<<(m + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, ls, m, scene_i,
-                                                 h->nodes, h->flags, h->scene + 6);
+    refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, scene_i, h->nodes,
+                                                 h->flags, h->scene + 6);
+    const int n_internal = n > 1 ? n - 1 : 1;
     quant_frame_kernel<<<1, 32, 0, s>>>(h->scene);
     quantize_nodes_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, n_internal, h->scene, h->qnodes);
     count_launch(3);

@@ -71,22 +71,19 @@ __device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, f
             } else if (hL) { cur = d.x; continue; }
             else if (hR) { cur = d.y; continue; }
         } else {
-            const int first = (~cur) * p.leaf_size;
-            for (int m = 0; m < p.leaf_size && first + m < p.a.n_surf; ++m) {   // the surfels of this leaf
-                if (STATS) ++n_leaf;
-                float t, alpha; int g;
-                if (leaf_test(r, p.recs + first + m, alpha_min, back_culling, t, g, alpha)) {
-                    bool after = key_less(t_last, g_last, t, g);
-                    bool fits = cnt < KBUF || key_less(t, g, bt[(KBUF - 1) * TB], bg[(KBUF - 1) * TB]);
-                    if (after && fits) {
-                        int i = cnt < KBUF ? cnt++ : KBUF - 1;
-                        while (i > 0 && key_less(t, g, bt[(i - 1) * TB], bg[(i - 1) * TB])) {
-                            bt[i * TB] = bt[(i - 1) * TB]; bg[i * TB] = bg[(i - 1) * TB]; ba[i * TB] = ba[(i - 1) * TB];
-                            --i;
-                        }
-                        bt[i * TB] = t; bg[i * TB] = g; ba[i * TB] = alpha;
-                        if (cnt == KBUF) t_hi = bt[(KBUF - 1) * TB];
+            if (STATS) ++n_leaf;
+            float t, alpha; int g;
+            if (leaf_test(r, p.recs + (~cur), alpha_min, back_culling, t, g, alpha)) {
+                bool after = key_less(t_last, g_last, t, g);
+                bool fits = cnt < KBUF || key_less(t, g, bt[(KBUF - 1) * TB], bg[(KBUF - 1) * TB]);
+                if (after && fits) {
+                    int i = cnt < KBUF ? cnt++ : KBUF - 1;
+                    while (i > 0 && key_less(t, g, bt[(i - 1) * TB], bg[(i - 1) * TB])) {
+                        bt[i * TB] = bt[(i - 1) * TB]; bg[i * TB] = bg[(i - 1) * TB]; ba[i * TB] = ba[(i - 1) * TB];
+                        --i;
                     }
+                    bt[i * TB] = t; bg[i * TB] = g; ba[i * TB] = alpha;
+                    if (cnt == KBUF) t_hi = bt[(KBUF - 1) * TB];
                 }
             }
         }
@@ -365,12 +362,8 @@ __global__ void __launch_bounds__(TB) intersection_test_kernel(const KParams p, 
             else if (hL) { cur = d.x; continue; }
             else if (hR) { cur = d.y; continue; }
         } else {
-            const int first = (~cur) * p.leaf_size;
-            for (int m = 0; m < p.leaf_size && first + m < a.n_surf && !found; ++m) {
-                float t, alpha; int g;
-                found = leaf_test(r, p.recs + first + m, a.alpha_min, 0, t, g, alpha);
-            }
-            if (found) break;
+            float t, alpha; int g;
+            if (leaf_test(r, p.recs + (~cur), a.alpha_min, 0, t, g, alpha)) { found = true; break; }
         }
         if (sp == 0) break;
         cur = stack_n[--sp];
@@ -418,7 +411,6 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
     p.a = a;
     p.nodes = h->qnodes;
     p.qframe = h->scene + 12;
-    p.leaf_size = h->built_leaf_size;
     p.recs = h->recs;
     p.counter = h->counter + h->slot;
     p.stats = h->stats;

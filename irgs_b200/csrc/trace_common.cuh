@@ -26,7 +26,6 @@ struct KParams {
     TraceArgs a;
     const QNode *nodes;
     const float *qframe;   // [6] quantisation frame: lo xyz, extent xyz
-    int leaf_size;         // surfels per leaf: leaf reference ~c covers records c*leaf_size .. +leaf_size-1 (< n_surf)
     const SurfelRec *recs;
     unsigned long long *counter;
     unsigned long long *stats;

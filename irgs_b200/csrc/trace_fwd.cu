@@ -42,9 +42,9 @@ constexpr int SSTK = 32;           // traversal stack entries kept in shared mem
 #endif
 constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #ifndef IRGS_PQ
-#define IRGS_PQ 20
+#define IRGS_PQ 6
 #endif
-constexpr int PQ = IRGS_PQ;               // pending-surfel queue entries per lane (>= 2 * max leaf size + 1)
+constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     const TraceArgs &a = p.a;
     const float alpha_min = a.alpha_min, T_min = a.T_min;
     const int back_culling = a.back_culling;
-    const int leaf_size = p.leaf_size;
     uint4 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
     uint4 *my_cand = warp_cand + (size_t)lane * KB;
     unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
@@ -116,8 +115,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         // ------------------------------------------------------------------ BVH walk, NODE sub-phase
         const int thr = pool_empty ? 1 : MIN_ACTIVE;
         unsigned walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
-        // (a node visit can queue two leaves' surfels: the loop is left for the LEAF sub-phase before a queue could overflow)
-        while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 2 * leaf_size)) {
+        // (a node visit can queue two leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
+        while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 2)) {
             if (phase == PH_TRAV && cur != CUR_NONE) {
                 const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
                 if (STATS) ++st_nodes;
@@ -130,18 +129,12 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 const bool h_near = rightNear ? hR : hL, h_far = rightNear ? hL : hR;
                 int next = CUR_NONE;
                 if (h_near) {
-                    if (c_near < 0) {
-                        const int first = (~c_near) * leaf_size;
-                        for (int m = 0; m < leaf_size; ++m)
-                            if (first + m < a.n_surf) { pend[pn * 32] = first + m; ++pn; }
-                    } else next = c_near;
+                    if (c_near < 0) { pend[pn * 32] = c_near; ++pn; }
+                    else next = c_near;
                 }
                 if (h_far) {
-                    if (c_far < 0) {
-                        const int first = (~c_far) * leaf_size;
-                        for (int m = 0; m < leaf_size; ++m)
-                            if (first + m < a.n_surf) { pend[pn * 32] = first + m; ++pn; }
-                    } else if (next == CUR_NONE) next = c_far;
+                    if (c_far < 0) { pend[pn * 32] = c_far; ++pn; }
+                    else if (next == CUR_NONE) next = c_far;
                     else {
                         if (sp < SSTK) stk[sp * 32] = c_far;
                         else if (sp < STACK) stack_spill[sp - SSTK] = c_far;
@@ -158,7 +151,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         while (__any_sync(FULL, phase == PH_TRAV && pn > 0)) {
             if (phase == PH_TRAV && pn > 0) {
                 --pn;
-                const int leaf = pend[pn * 32];
+                const int leaf = ~pend[pn * 32];
                 const float4 *src = reinterpret_cast<const float4 *>(p.recs + leaf);
                 const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
                 if (STATS) ++st_leaf;
@@ -346,7 +339,7 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p;
-    p.a = a; p.nodes = h->qnodes; p.qframe = h->scene + 12; p.leaf_size = h->built_leaf_size; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
+    p.a = a; p.nodes = h->qnodes; p.qframe = h->scene + 12; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
     if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31)) {

@@ -8,12 +8,11 @@ dev = torch.device("cuda:0")
 class A: surfels=300000; img=int(os.environ.get("IMG", 320)); spp=256
 def factory(sc, inp):
     tr = GaussianTracer(transmittance_min=synth.T_MIN, device=dev)
-    if os.environ.get("LEAF"): tr.set_option("leaf_size", int(os.environ["LEAF"]))
     tr.build_from_surfels(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], synth.ALPHA_MIN)
     return tr
 sc, inp, tr, ro, rd = bench.build_workload(A, dev, 0, 1, factory)
 args = (inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"], synth.ALPHA_MIN)
-for srt in (0,):
+for srt in (0, 1 << 17):
   tr.set_option("sort_rays_min", srt)
   for n in (1 << 22, 1 << 24):
     n = min(n, ro.shape[0]); best = 1e9

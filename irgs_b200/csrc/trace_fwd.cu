@@ -42,7 +42,7 @@ constexpr int SSTK = 32;           // traversal stack entries kept in shared mem
 #endif
 constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #ifndef IRGS_PQ
-#define IRGS_PQ 6
+#define IRGS_PQ 12
 #endif
 constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };

@@ -429,6 +429,64 @@ def test_deferred_gradient_accumulation_equals_sum_of_calls(small_scene):
     assert not tr._fused.any()
 
 
+# ---------------------------------------------------------------------------------------------- parameter-level API
+def test_trace_from_surfel_parameters_gradients_reach_scales_and_rotations(small_scene):
+    """irgs_b200.surfels.SurfelScene: means / scales / rotations / opacities in, gradients back to all of them;
+    checked against the float64 autograd twin fed through the same (torch) glue."""
+    from irgs_b200.surfels import SurfelScene, surfel_frames
+    from tests import torch_twin
+    sc, inp = small_scene
+    o, d = _rays(inp, "secondary")
+    o, d = o[:1536], d[:1536]
+    ref = oracle.trace_forward(_oracle_scene(inp), o, d, hit_cap=96)
+    safe = torch.from_numpy(_safe(ref) & (ref["hit_count"] <= 96))
+    gout = {k: v * (safe[:, None] if v.dim() == 2 else safe) for k, v in _gout(o.shape[0], inp["features"].shape[1]).items()}
+    names = ("color", "normal", "feature", "depth", "alpha")
+    keys = ("means", "scales", "rotations", "opacity")
+
+    leaf = {k: sc[k].to(DEV).clone().requires_grad_(True) for k in keys}
+    scene = SurfelScene(transmittance_min=synth.T_MIN, alpha_min=synth.ALPHA_MIN)
+    scene.build(leaf["means"], leaf["scales"], leaf["rotations"], leaf["opacity"], synth.CAMERA_CENTER)
+    out = scene.trace(o.to(DEV), d.to(DEV), leaf["means"], leaf["scales"], leaf["rotations"], leaf["opacity"],
+                      sc["shs"].to(DEV), sc["features"].to(DEV), camera_center=synth.CAMERA_CENTER, normalize=False)
+    assert np.array_equal(out["hit_count"].cpu().numpy()[safe.numpy()], ref["hit_count"][safe.numpy()])
+    sum((out[n] * gout[n].to(DEV)).sum() for n in names).backward()
+
+    tw = {k: sc[k].double().clone().requires_grad_(True) for k in keys}
+    ru, rv, nrm = surfel_frames(tw["means"], tw["scales"], tw["rotations"], synth.CAMERA_CENTER)
+    outs = torch_twin.composite(o.double(), d.double(), tw["means"], tw["opacity"], ru, rv, nrm, sc["features"].double(),
+                                sc["shs"].double(), torch.from_numpy(ref["hits"]).long(),
+                                torch.from_numpy(ref["hit_count"]).long())
+    sum((t * gout[n].double()).sum() for n, t in zip(names, outs)).backward()
+    for k in keys:
+        a, b = leaf[k].grad.cpu().numpy(), tw[k].grad.numpy()
+        assert np.any(b) and _cos(a, b) >= 0.9999, (k, _cos(a, b))
+    # saturated rays are normalised like GaussianModel.trace does (scene/gaussian_model.py:751-756)
+    outn = scene.trace(o.to(DEV), d.to(DEV), leaf["means"], leaf["scales"], leaf["rotations"], leaf["opacity"],
+                       sc["shs"].to(DEV), sc["features"].to(DEV), camera_center=synth.CAMERA_CENTER)
+    sat = out["alpha"] >= 1 - synth.T_MIN
+    assert bool(sat.any()) and bool((outn["alpha"][sat] == 1).all()) and torch.equal(outn["alpha"][~sat], out["alpha"][~sat])
+
+
+def test_one_million_surfels_refit_equals_rebuild():
+    """C5 shape: 1M surfels, parameters perturbed, update (refit) vs fresh build give bit-identical traces."""
+    sc = synth.make_scene(1000000, device=DEV)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    tr = _tracer(inp)
+    gen = torch.Generator(DEV).manual_seed(2)
+    moved = dict(inp)
+    moved["means3D"] = inp["means3D"] + 1e-3 * torch.randn(inp["means3D"].shape, device=DEV, generator=gen)
+    tr.update_from_surfels(moved["means3D"], moved["opacity"], moved["ru"], moved["rv"], moved["normals"], synth.ALPHA_MIN)
+    idx = torch.randint(0, 1000000, (512,), device=DEV, generator=gen)
+    o, d = synth.secondary_rays(moved["means3D"][idx].cpu() + 0.01 * moved["normals"][idx].cpu(), moved["normals"][idx].cpu(), 256)
+    o, d = o.reshape(-1, 3).to(DEV), d.reshape(-1, 3).to(DEV)
+    args = (moved["means3D"], moved["opacity"], moved["ru"], moved["rv"], moved["normals"], None, moved["shs"], synth.ALPHA_MIN)
+    a = tr.trace_with_hits(o, d, *args)
+    b = _tracer(moved).trace_with_hits(o, d, *args)
+    _assert_same_trace(a, b)
+    assert int(a["hit_count"].sum()) > 0
+
+
 # ---------------------------------------------------------------------------------------------- host-buffer C ABI
 def test_host_buffer_entry_points_match_device_path(small_scene):
     from irgs_b200 import _lib

@@ -270,6 +270,13 @@ def run_ours(args):
     except Exception:
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    traffic = None
+    try:  # DRAM bytes of one forward launch from the committed ncu --set full capture (profiles/), same launch size
+        tj = json.load(open(os.path.join(ROOT, "profiles", "fwd_kernel_traffic.json")))
+        if tj.get("rays_per_launch") == chunk:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     S, (V, P, H) = canonical_counters(inp, rays_o, rays_d)
     bytes_per_ray = 24 + 32 + 32 * V + 64 * P + 192 * H  # BASELINE.md section 4, forward, S = 0
     achieved = bytes_per_ray * fwd_rays / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None
@@ -285,7 +292,8 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "algorithmic_bytes_per_ray": bytes_per_ray,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_ray * chunk,
+                     "algorithmic_bytes_per_ray": bytes_per_ray,
                      "canonical_counters_per_ray": {"V_boxes": V, "P_surfel_tests": P, "H_hits": H},
                      "kernel_ms_per_step": fwd_ms / args.steps, "kernel_share_of_step": fwd_ms / args.steps / ms,
                      "note": "algorithmic bytes follow BASELINE.md section 4 on the oracle's canonical LBVH; most node and "

@@ -38,8 +38,8 @@ static_assert(sizeof(SurfelRec) == 64, "record must be 64 bytes");
 // conservatively (lo rounded down, hi up) to 16 bits per coordinate on a grid spanning the padded root bound:
 //   per child: w0 = lo.x | lo.y << 16,  w1 = lo.z | hi.x << 16,  w2 = hi.y | hi.z << 16,  w3 = child reference
 // child reference: >= 0 internal node, < 0 leaf ~pos, IRGS_CHILD_NONE = no child (empty bound).
-// Coordinate q decodes to frame_lo + q/65536 * frame_ext; the ray walk folds the decode into one fma per plane by
-// building the float 1 + q/65536 directly in the mantissa.
+// Coordinate q decodes to frame_lo + q * cell; the ray walk folds the decode into one byte-permute (assembling the
+// float 2^23 + q) and one fma per plane.
 struct __align__(16) QNode {
     uint4 l, r;
 };
@@ -64,7 +64,7 @@ struct irgs_tracer {
     int *radix_hist = nullptr;          // [256 * n_tiles]
     int64_t radix_tiles_cap = 0;
     float *scene = nullptr;             // [24]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats),
-                                        //       12-14 quantisation frame lo, 15-17 frame extent
+                                        //       12-14 quantisation frame lo, 15-17 cell size
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
     unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
     int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)

@@ -433,31 +433,31 @@ __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restr
 }
 
 // Step 6: quantised traversal copy of the nodes (see QNode in internal.cuh).
+// Frame: code q decodes to frame_lo + q * cell with cell = root extent / 65520 and frame_lo = root lo - 4 cells, so
+// every bound quantises into [4, 65524]; lo is rounded down and hi up, then each is moved outward by two more cells:
+// the ray walk evaluates the plane as fma(2^23 + q, cell/d, (frame_lo - 2^23 cell - o)/d), whose two rounded
+// constants can be off by up to ~one cell in space (see trace_common.cuh).
 __global__ void quant_frame_kernel(float *scene) {
-    // frame: lo = root lo; extent slightly larger than the root's so that code 65535 decodes beyond the root hi
     const int k = threadIdx.x;
     if (k < 3) {
         const float lo = scene[6 + k], hi = scene[9 + k];
-        float ext = (hi >= lo) ? (hi - lo) : 0.f;
-        ext = ext * (65536.0f / 65535.0f) * (1.0f + 8e-6f) + 1e-30f;
-        scene[12 + k] = lo;
-        scene[15 + k] = ext;
+        const float ext = (hi >= lo) ? (hi - lo) : 0.f;
+        const float cell = fmaxf(ext / 65520.0f, 1e-30f);
+        scene[12 + k] = lo - 4.0f * cell;
+        scene[15 + k] = cell;
     }
 }
-__device__ __forceinline__ float qdecode(unsigned q, float lo, float ext) {
-    return fmaf(__uint_as_float(0x3F800000u | (q << 7)), ext, lo - ext);
-}
-__device__ __forceinline__ unsigned quant_lo(float x, float lo, float ext) {
-    int q = (int)floorf((x - lo) / ext * 65536.0f);
+__device__ __forceinline__ unsigned quant_lo(float x, float lo, float cell) {
+    int q = (int)floorf((x - lo) / cell);
     q = min(max(q, 0), 65535);
-    while (q > 0 && qdecode((unsigned)q, lo, ext) > x) --q;
-    return (unsigned)q;
+    while (q > 0 && fmaf((float)q, cell, lo) > x) --q;
+    return (unsigned)max(q - 2, 0);
 }
-__device__ __forceinline__ unsigned quant_hi(float x, float lo, float ext) {
-    int q = (int)ceilf((x - lo) / ext * 65536.0f);
+__device__ __forceinline__ unsigned quant_hi(float x, float lo, float cell) {
+    int q = (int)ceilf((x - lo) / cell);
     q = min(max(q, 0), 65535);
-    while (q < 65535 && qdecode((unsigned)q, lo, ext) < x) ++q;
-    return (unsigned)q;
+    while (q < 65535 && fmaf((float)q, cell, lo) < x) ++q;
+    return (unsigned)min(q + 2, 65535);
 }
 __global__ void quantize_nodes_kernel(const Node *__restrict__ nodes, int n_int, const float *__restrict__ scene,
                                       QNode *__restrict__ qnodes) {

@@ -97,18 +97,18 @@ __device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, i
 // ------------------------------------------------------------------------------------------------ traversal
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz;
-    // slab-test constants for quantised planes: t = fma(1 + q/65536, a, b)
+    // slab-test constants for quantised planes: t = fma(2^23 + q, a, b)
     float ax, ay, az, bx, by, bz;
 };
 
-// The slab test evaluates t = (plane - o) / d as ONE fma per plane.  For a plane stored as the 16-bit code q on the
-// frame (lo, ext): plane = lo + q/65536 * ext = (lo - ext) + v * ext with v = 1 + q/65536 built directly in a float's
-// mantissa, so t = v * (ext/d) + (lo - ext - o)/d.  The fma carries an absolute error of about
-// (|o| + |plane - o|) * 2^-23 in SPACE (the error in t scales with 1/d exactly like the t-extent of a spatial pad
-// does), independent of how small a direction component is; the leaf bounds are padded in space at refit time
-// (lbvh.cu: 8e-6 x scene scale + 1e-4 x extent) and quantised conservatively, so the interval test needs no slack.
-// Ray origins are assumed to lie within ~16 scene diameters (beyond that the reference's own float32 plane arithmetic
-// is equally fuzzy).
+// The slab test evaluates t = (plane - o) / d as ONE fma per plane, with ONE byte-permute to decode the plane: a
+// plane stored as the 16-bit code q on the frame (lo, cell) is lo + q * cell; the float v = 2^23 + q is assembled
+// by PRMT from the code's two bytes and the constant 0x4B000000, and t = v * (cell/d) + (lo - 2^23 cell - o)/d.
+// The two rounded constants make the decoded plane uncertain by up to ~one cell in SPACE (2^23 * 2^-24 = half a
+// cell each), independent of how small a direction component is (the error in t scales with 1/d exactly like the
+// t-extent of a spatial pad does); the build therefore moves every quantised plane two cells outward on top of the
+// float pad of the leaf bounds (lbvh.cu), and the interval test needs no slack.  Ray origins are assumed to lie
+// within ~16 scene diameters (beyond that the reference's own float32 plane arithmetic is equally fuzzy).
 __device__ __forceinline__ void ray_setup(RayCtx &r, const float *__restrict__ qframe) {
     const float tiny = 1e-30f;  // a zero component would give 0 * inf = NaN
     const float sx = fabsf(r.dx) > tiny ? r.dx : copysignf(tiny, r.dx);
@@ -116,13 +116,14 @@ __device__ __forceinline__ void ray_setup(RayCtx &r, const float *__restrict__ q
     const float sz = fabsf(r.dz) > tiny ? r.dz : copysignf(tiny, r.dz);
     const float ix = 1.0f / sx, iy = 1.0f / sy, iz = 1.0f / sz;
     const float lx = __ldg(qframe), ly = __ldg(qframe + 1), lz = __ldg(qframe + 2);
-    const float ex = __ldg(qframe + 3), ey = __ldg(qframe + 4), ez = __ldg(qframe + 5);
-    r.ax = ex * ix; r.ay = ey * iy; r.az = ez * iz;
-    r.bx = (lx - ex - r.ox) * ix; r.by = (ly - ey - r.oy) * iy; r.bz = (lz - ez - r.oz) * iz;
+    const float cx = __ldg(qframe + 3), cy = __ldg(qframe + 4), cz = __ldg(qframe + 5);
+    const float two23 = 8388608.0f;
+    r.ax = cx * ix; r.ay = cy * iy; r.az = cz * iz;
+    r.bx = (lx - two23 * cx - r.ox) * ix; r.by = (ly - two23 * cy - r.oy) * iy; r.bz = (lz - two23 * cz - r.oz) * iz;
 }
 
-__device__ __forceinline__ float qlo16(unsigned w) { return __uint_as_float(((w << 7) & 0x007FFF80u) | 0x3F800000u); }
-__device__ __forceinline__ float qhi16(unsigned w) { return __uint_as_float(((w >> 9) & 0x007FFF80u) | 0x3F800000u); }
+__device__ __forceinline__ float qlo16(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
+__device__ __forceinline__ float qhi16(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
 // one child of a quantised node: w = (lo.x|lo.y<<16, lo.z|hi.x<<16, hi.y|hi.z<<16, ref)
 __device__ __forceinline__ bool slab(const RayCtx &r, const uint4 w, float t_lo, float t_hi, float &tn) {

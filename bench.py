@@ -7,7 +7,7 @@
 
 A step = one forward + backward pass of the tracer over ALL rays of the workload (processed in chunks of --chunk rays,
 like the reference's renderer chunks its pixels, gaussian_renderer/__init__.py:314-322) followed by the single
-all-reduce of the fused per-surfel gradient buffer.  Rays are sharded contiguously over ranks (strong scaling: the total
+all-reduce of the fused per-surfel gradient buffer.  Pixel bundles are dealt to the ranks in blocks of 32 pixels, round-robin (strong scaling: the total
 is fixed), surfels and the acceleration structure are replicated.  One JSON line is printed by rank 0.
 """
 import argparse
@@ -99,20 +99,23 @@ def build_workload(args, device, rank, world, tracer_factory):
         outs = tracer.trace(o, d, inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"],
                             synth.ALPHA_MIN)
     pts, nrm = synth.shading_points_from_primary(o, d, outs[3], outs[4], outs[1])
-    pb, pe = parallel.shard_range(args.img * args.img, rank, world)
-    n_pix = pe - pb
+    # this rank's pixel bundles: blocks of 32 consecutive pixels dealt round-robin (load balance; world 1: all pixels)
+    pix = parallel.shard_interleaved(args.img * args.img, rank, world, block=32)
+    n_pix = pix.numel()
     rays_o = torch.empty(n_pix * args.spp, 3, device=device)
     rays_d = torch.empty(n_pix * args.spp, 3, device=device)
     gen = torch.Generator().manual_seed(synth.RAY_SEED)
-    azim = torch.rand(args.img * args.img, 1, generator=gen)[pb:pe].to(device)
+    azim = torch.rand(args.img * args.img, 1, generator=gen)[pix].to(device)
+    pix = pix.to(device)
+    pts, nrm = pts[pix], nrm[pix]
     step_pix = 1 << 14
     for b in range(0, n_pix, step_pix):
         e = min(b + step_pix, n_pix)
-        dirs = synth.fibonacci_hemisphere(nrm[pb + b:pb + e], args.spp, False)
+        dirs = synth.fibonacci_hemisphere(nrm[b:e], args.spp, False)
         # random azimuth per pixel (training mode of utils/graphics_utils.py:31-32), applied as a rotation about the normal
-        dirs = _rotate_about(dirs, nrm[pb + b:pb + e], azim[b:e] * 2 * np.pi)
+        dirs = _rotate_about(dirs, nrm[b:e], azim[b:e] * 2 * np.pi)
         rays_d[b * args.spp:e * args.spp] = dirs.reshape(-1, 3)
-        rays_o[b * args.spp:e * args.spp] = (pts[pb + b:pb + e, None] + dirs * synth.LIGHT_T_MIN).reshape(-1, 3)
+        rays_o[b * args.spp:e * args.spp] = (pts[b:e, None] + dirs * synth.LIGHT_T_MIN).reshape(-1, 3)
     return sc, inp, tracer, rays_o, rays_d
 
 
@@ -187,7 +190,12 @@ def run_ours(args):
     tracer.accumulate_grads = True
     fwd_events = []
 
+    pre_flush = []
+
     def step(record):
+        if record:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         for b in range(0, n_local, chunk):
             e = min(b + chunk, n_local)
             if record:
@@ -200,6 +208,10 @@ def run_ours(args):
                 fwd_events.append((e0, e1, e - b))
             torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]],
                                     [gout[0][:e - b], gout[1][:e - b], gout[3][:e - b], gout[4][:e - b]])
+        if record:  # per-rank compute time before the collective (load-balance diagnostics)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            pre_flush.append((ev0, ev))
         return tracer.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape))  # the one all-reduce
 
     def sync_all():
@@ -224,6 +236,15 @@ def run_ours(args):
     launches = int(lib.irgs_launch_count())
     ms = parallel.max_over_ranks(t0.elapsed_time(t1), device) / args.steps
     clk = clocks.stop() if rank == 0 else None
+    # compute time of this rank per step, excluding the wait inside the all-reduce
+    own = [a.elapsed_time(b) for a, b in pre_flush]
+    own_ms = torch.tensor([float(np.median(own))], device=device, dtype=torch.float64)
+    if world > 1:
+        allr = [torch.zeros_like(own_ms) for _ in range(world)]
+        torch.distributed.all_gather(allr, own_ms)
+        rank_ms = [float(x.item()) for x in allr]
+    else:
+        rank_ms = [float(own_ms.item())]
     fwd_ms = sum(a.elapsed_time(b) for a, b, _ in fwd_events)
     fwd_rays = sum(n for _, _, n in fwd_events)
     checksum = float(grads["shs"].abs().sum().item())
@@ -286,10 +307,10 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C3: {args.surfels} surfels, {args.img}x{args.img}x{args.spp} secondary rays, fwd+bwd",
                    "rays_per_step": n_total, "chunk_rays": chunk, "sh_degree": 3, "features": 0,
-                   "parallelism": f"ray-sharded dp{world}, surfels+BVH replicated, one all-reduce of N x 64 floats",
+                   "parallelism": f"ray-sharded dp{world} (32-pixel blocks round-robin), surfels+BVH replicated, one all-reduce of N x 64 floats",
                    "l2": "inputs (3.9 GB of rays per step) exceed L2; no flush needed",
                    "shading_points": "all 640k bundles start on the surface (missed pixels re-assigned to hit pixels)"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
         "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_ray * chunk,

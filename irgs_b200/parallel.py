@@ -24,6 +24,17 @@ def shard_range(n_items, rank, world, align=1):
     return b * align, e * align
 
 
+def shard_interleaved(n_units, rank, world, block=32):
+    """Load-balanced shard: the units (pixel bundles) are cut into blocks of `block` consecutive units that are dealt
+    round-robin to the ranks, so every rank receives samples from the whole image (a contiguous split of the C3 image
+    left the slowest of 8 ranks with 1.35x the mean work).  Returns the sorted int64 unit indices of `rank`; the shards
+    of all ranks partition range(n_units) and their sizes differ by at most one block."""
+    if block < 1 or world < 1 or not 0 <= rank < world:
+        raise ValueError("bad shard arguments")
+    idx = torch.arange(n_units, dtype=torch.int64)
+    return idx[(idx // block) % world == rank]
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).
     Returns (rank, local_rank, world).  A single process (no WORLD_SIZE) is rank 0 of 1 and initialises nothing."""

@@ -72,3 +72,19 @@ def test_ray_sharding_plus_one_allreduce_matches_single_process(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     err, scale = np.load(os.path.join(str(tmp_path), "err.npy"))
     assert scale > 0 and err <= 1e-5 * scale
+
+
+def test_shard_interleaved_partitions_and_balances():
+    for n, world, block in ((640000, 8, 32), (1000, 3, 7), (5, 4, 2), (64, 1, 32)):
+        seen = torch.zeros(n, dtype=torch.int64)
+        sizes = []
+        for r in range(world):
+            idx = parallel.shard_interleaved(n, r, world, block)
+            assert torch.all(idx[1:] > idx[:-1]) if idx.numel() > 1 else True
+            seen[idx] += 1
+            sizes.append(idx.numel())
+        assert torch.all(seen == 1)
+        assert max(sizes) - min(sizes) <= block
+    assert torch.equal(parallel.shard_interleaved(10, 0, 1), torch.arange(10))
+    with pytest.raises(ValueError):
+        parallel.shard_interleaved(10, 2, 2)

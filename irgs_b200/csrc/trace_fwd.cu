@@ -45,6 +45,7 @@ constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #define IRGS_PQ 12
 #endif
 constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
+static_assert(32 * PQ <= (8 + NFMAX) * 32, "the flattened leaf list aliases the COMP scratch");
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -74,7 +75,6 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     const float alpha_min = a.alpha_min, T_min = a.T_min;
     const int back_culling = a.back_culling;
     uint4 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
-    uint4 *my_cand = warp_cand + (size_t)lane * KB;
     unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
 
     int phase = PH_FETCH;
@@ -148,20 +148,63 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         }
 
         // ------------------------------------------------------------------ BVH walk, LEAF sub-phase
-        while (__any_sync(FULL, phase == PH_TRAV && pn > 0)) {
-            if (phase == PH_TRAV && pn > 0) {
-                --pn;
-                const int leaf = ~pend[pn * 32];
-                const float4 *src = reinterpret_cast<const float4 *>(p.recs + leaf);
-                const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
-                if (STATS) ++st_leaf;
+        // The pending leaves of ALL lanes are flattened into one warp-wide list (shared memory) and tested 32 at a
+        // time, one (ray, surfel) pair per lane whoever owns the ray: the owner's ray and depth window come through
+        // shuffles.  (Each lane draining its own queue ran this code at 5.7 of 32 lanes: profiles/r01_fwd_regions_v7q.txt.)
+        // A lane submits at most as many leaves as its candidate row has room for; the rest stay queued (PH_FULL).
+        for (;;) {
+            const int m = (phase == PH_TRAV) ? min(pn, KB - cnt) : 0;
+            if (!__any_sync(FULL, m > 0)) break;
+            int incl = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            const int start = incl - m;
+            const int n_items = __shfl_sync(FULL, incl, 31);
+            int *flat = reinterpret_cast<int *>(ws.scratch);   // [32 * PQ] at most; the COMP phase is not running now
+            __syncwarp();
+            for (int k = 0; k < m; ++k) { --pn; flat[start + k] = (int)(lane << 27) | ~pend[pn * 32]; }
+            __syncwarp();
+            for (int base = 0; base < n_items; base += 32) {
+                const int idx = base + (int)lane;
+                const bool has = idx < n_items;
+                const int e = has ? flat[idx] : (int)(lane << 27);
+                const int owner = (int)((unsigned)e >> 27);
+                float4 q0, q1, q2, q3;
+                q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has) {
+                    const float4 *src = reinterpret_cast<const float4 *>(p.recs + (e & 0x07ffffff));
+                    q0 = __ldg(src); q1 = __ldg(src + 1); q2 = __ldg(src + 2); q3 = __ldg(src + 3);
+                    if (STATS) ++st_leaf;
+                }
+                RayCtx ro;
+                ro.ox = __shfl_sync(FULL, r.ox, owner); ro.oy = __shfl_sync(FULL, r.oy, owner); ro.oz = __shfl_sync(FULL, r.oz, owner);
+                ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);
+                const float o_tlast = __shfl_sync(FULL, t_last, owner), o_thi = __shfl_sync(FULL, t_hi, owner);
+                const int o_glast = __shfl_sync(FULL, g_last, owner), o_ghi = __shfl_sync(FULL, g_hi, owner);
+                const int o_start = __shfl_sync(FULL, start, owner), o_m = __shfl_sync(FULL, m, owner);
+                const int o_cnt = __shfl_sync(FULL, cnt, owner);
                 float t, alpha; int g;
-                if (leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
-                    key_less(t_last, g_last, t, g) && key_less(t, g, t_hi, g_hi)) {
-                    my_cand[cnt] = make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), 0u);
-                    if (++cnt == KB) phase = PH_FULL;   // pending leaves stay queued until the row has been trimmed
+                const bool ok = has && leaf_eval(ro, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
+                                key_less(o_tlast, o_glast, t, g) && key_less(t, g, o_thi, o_ghi);
+                const unsigned acc = __ballot_sync(FULL, ok);
+                // the items of one owner are contiguous in the list: bits [lo, hi) of this round
+                if (ok) {
+                    const int lo = max(o_start - base, 0), hi = min(o_start + o_m - base, 32);
+                    const unsigned rmask = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    warp_cand[(size_t)owner * KB + o_cnt + __popc(acc & rmask & lt_mask)] =
+                        make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), 0u);
+                }
+                {
+                    const int lo = min(max(start - base, 0), 32), hi = min(max(start + m - base, 0), 32);
+                    const unsigned hm = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+                    const unsigned lm = lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u);
+                    cnt += __popc(acc & hm & ~lm);
                 }
             }
+            if (phase == PH_TRAV && cnt == KB) phase = PH_FULL;   // pending leaves stay queued until the row has been trimmed
         }
         // the walk of this pass is complete once the stack, the current node and the leaf queue are all empty
         if (phase == PH_TRAV && cur == CUR_NONE && pn == 0) phase = PH_COMP;

@@ -132,7 +132,9 @@ int64_t irgs_launch_count(void);
 void irgs_reset_launch_count(void);
 
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
- * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  Returns non-zero for unknown names. */
+ * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
+ * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.
+ * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 
 /* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with

@@ -368,6 +368,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
         return 0;
     }
+    if (strcmp(name, "bwd_mode") == 0) {
+        h->bwd_mode = value == 1 ? 1 : 0;
+        return 0;
+    }
     return fail("unknown option");
 }
 

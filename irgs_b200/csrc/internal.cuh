@@ -79,6 +79,7 @@ struct irgs_tracer {
                                             // measured on B200: the sort costs more than it saves, profiles/r01_notes.md)
     unsigned long long *stats = nullptr;    // [4]
     int stats_enabled = 0;
+    int bwd_mode = 0;                       // 0: hit-parallel replay (default), 1: thread-per-ray replay
     bool built = false;
     // host-streaming resources
     cudaStream_t hs[2] = {nullptr, nullptr};

@@ -243,6 +243,279 @@ __global__ void __launch_bounds__(TB) trace_backward_replay_kernel(const KParams
     }
 }
 
+// Hit-parallel replay: ONE HIT PER LANE.  A warp owns 32 consecutive rays; their saved hit lists are flattened (prefix sum
+// of the hit counts) and processed 32 hits at a time whichever ray they belong to:
+//   * the hit's ray (origin, direction, final outputs, output gradients) comes from the owning lane through shuffles;
+//   * the sequential quantities of gaussiantrace_backward.cu:61-98 become segmented warp scans, a segment being the run
+//     of lanes that hold hits of one ray: T is a segmented prefix product of (1 - alpha), and the "what is still to
+//     come" terms (C_final - C_i, ...) are segmented exclusive SUFFIX sums of the w * c contributions, which have no
+//     cancellation (the reference subtracts two nearly equal running sums);  a ray whose list straddles two rounds
+//     carries T and the remainders over in registers (lane 31 of one round -> the first segment of the next);
+//   * every lane writes the 64-float gradient row of its hit to shared memory; the warp then adds the rows to the
+//     fused buffer with one 16-byte reduction per lane, sixteen consecutive lanes covering one 256-byte row, i.e. 2
+//     cache lines per hit instead of 16 scattered requests.
+// ncu on the thread-per-ray replay (profiles/r01_bwd_replay_regions.txt): 7.96 of 32 lanes active, L1TEX 85 % busy
+// with the scattered reductions.
+constexpr int BROW = 76;   // floats per shared-memory row: 64 gradient floats + 6 ray-gradient terms, 76 % 32 == 12 (conflict-free float4 stores)
+
+template <bool FEAT>
+__global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p) {
+    __shared__ __align__(16) float s_rows[TB / 32][32 * BROW];
+    const TraceArgs &a = p.a;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float *rows = s_rows[threadIdx.x >> 5];
+    const int64_t ray0 = ((int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * 32;
+    if (ray0 >= a.n_rays) return;
+    const int64_t my_ray = ray0 + lane;
+    const bool valid = my_ray < a.n_rays;
+    const int cnt = valid ? a.hit_count[my_ray] : 0;
+    // gaussiantrace_backward.cu:13-14: rays whose forward alpha is exactly zero contribute nothing
+    const bool has = valid && cnt > 0 && cnt <= a.hit_cap && a.alpha[my_ray] != 0.f;
+    RayCtx r;
+    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f;
+    float fin[8], gout[8];   // C(3) N(3) D O of the forward / their incoming gradients
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { fin[j] = 0.f; gout[j] = 0.f; }
+    int64_t gr = 0;
+    if (has) {
+        load_ray(a, my_ray, r);
+        gr = a.gout_period > 0 ? (a.gout_offset + my_ray) % a.gout_period : my_ray;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            fin[j] = a.color[3 * my_ray + j]; fin[3 + j] = a.normal[3 * my_ray + j];
+            gout[j] = __ldg(a.gC + 3 * gr + j); gout[3 + j] = __ldg(a.gN + 3 * gr + j);
+        }
+        fin[6] = a.depth[my_ray]; fin[7] = a.alpha[my_ray];
+        gout[6] = __ldg(a.gD + gr); gout[7] = __ldg(a.gO + gr);
+    }
+    const int c_eff = has ? cnt : 0;
+    int incl = c_eff;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int start = incl - c_eff;
+    const int total = __shfl_sync(FULL, incl, 31);
+    float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+    float carryT = 1.f, carry_rem[8], carry_remF[FEAT ? NFMAX : 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) carry_rem[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) carry_remF[j] = 0.f;
+    const int nvec = ((a.deg + 1) * (a.deg + 1) * 3 + 3) >> 2;
+
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        const bool act = idx < total;
+        // owner = number of lanes whose inclusive count is <= idx (binary lifting over shuffles)
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int v = __shfl_sync(FULL, incl, owner + step - 1);
+            if (v <= idx) owner += step;
+        }
+        owner = act ? owner : lane;
+        const int o_start = __shfl_sync(FULL, start, owner), n_o = __shfl_sync(FULL, c_eff, owner);
+        const int k = act ? idx - o_start : 0;
+        const int64_t ray = ray0 + owner;
+        RayCtx ro;
+        ro.ox = __shfl_sync(FULL, r.ox, owner); ro.oy = __shfl_sync(FULL, r.oy, owner); ro.oz = __shfl_sync(FULL, r.oz, owner);
+        ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);
+        float F[8], gO[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { F[j] = __shfl_sync(FULL, fin[j], owner); gO[j] = __shfl_sync(FULL, gout[j], owner); }
+        const int64_t o_gr = __shfl_sync(FULL, gr, owner);
+        // segment of this lane's ray inside the round
+        const int first = act ? lane - k : lane, last = act ? lane + (n_o - 1 - k) : lane;
+        const int seg_lo = max(first, 0), seg_hi = min(last, 31);
+        const bool straddles_in = first < 0;
+
+        // ---- the hit itself (same arithmetic as bwd_hit / the forward)
+        float t = 0.f, alpha = 0.f, G = 0.f, op = 0.f, og = 0.f, dg = 1.f, m = 1.f, pu = 0.f, pv = 0.f;
+        float nx = 0.f, ny = 0.f, nz = 0.f, ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        float relx = 0.f, rely = 0.f, relz = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+        float c[3] = {0.f, 0.f, 0.f};
+        float feat[FEAT ? NFMAX : 1], Ff[FEAT ? NFMAX : 1], gF[FEAT ? NFMAX : 1];
+#pragma unroll
+        for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) { feat[j] = 0.f; Ff[j] = 0.f; gF[j] = 0.f; }
+        float Y[16];
+        int g = 0;
+        if (act) {
+            g = __ldg(a.hits + ray * a.hit_cap + k);
+            sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
+            const float *pm = a.means + 3 * (size_t)g, *pn = a.normals + 3 * (size_t)g, *pa = a.ru + 3 * (size_t)g,
+                        *pb = a.rv + 3 * (size_t)g;
+            const float mx = __ldg(pm), my = __ldg(pm + 1), mz = __ldg(pm + 2);
+            nx = __ldg(pn); ny = __ldg(pn + 1); nz = __ldg(pn + 2);
+            ax = __ldg(pa); ay = __ldg(pa + 1); az = __ldg(pa + 2);
+            bx = __ldg(pb); by = __ldg(pb + 1); bz = __ldg(pb + 2);
+            op = __ldg(a.opacity + g);
+            relx = __fsub_rn(ro.ox, mx); rely = __fsub_rn(ro.oy, my); relz = __fsub_rn(ro.oz, mz);
+            og = dot3_rn(nx, ny, nz, relx, rely, relz);
+            dg = dot3_rn(nx, ny, nz, ro.dx, ro.dy, ro.dz);
+            const float den = fmaxf(1e-6f, __fmul_rn(dg, dg));
+            t = __fdiv_rn(__fmul_rn(-og, dg), den);
+            m = (-dg > 0.f) ? 1.f : -1.f;
+            px = __fmaf_rn(t, ro.dx, relx); py = __fmaf_rn(t, ro.dy, rely); pz = __fmaf_rn(t, ro.dz, relz);
+            pu = dot3_rn(ax, ay, az, px, py, pz); pv = dot3_rn(bx, by, bz, px, py, pz);
+            G = __expf(__fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv))));
+            alpha = fminf(0.99f, __fmul_rn(op, G));
+            sh_color(a.shs, a.K, a.deg, g, Y, c);
+            if (FEAT) {
+#pragma unroll
+                for (int j = 0; j < NFMAX; ++j)
+                    if (j < a.S) {
+                        feat[j] = __ldg(a.features + (size_t)g * a.S + j);
+                        Ff[j] = a.feature[ray * a.S + j];
+                        gF[j] = __ldg(a.gF + o_gr * a.S + j);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) Y[j] = 0.f;
+        }
+        const float nf[3] = {m * nx, m * ny, m * nz};
+
+        // ---- transmittance: segmented inclusive prefix product of (1 - alpha)
+        float incT = act ? (1.f - alpha) : 1.f;
+        bool up_ok[5], dn_ok[5];
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5) { up_ok[s5] = lane - (1 << s5) >= seg_lo; dn_ok[s5] = lane + (1 << s5) <= seg_hi; }
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5) {
+            const float v = __shfl_up_sync(FULL, incT, 1 << s5);
+            if (up_ok[s5]) incT *= v;
+        }
+        float exclT = __shfl_up_sync(FULL, incT, 1);
+        if (lane <= seg_lo) exclT = 1.f;
+        const float T0 = straddles_in ? carryT : 1.f;
+        const float T_before = T0 * exclT, T = T0 * incT;   // T: after this hit, like s.T in bwd_hit
+        const float w = act ? T_before * alpha : 0.f;
+
+        // ---- "still to come" terms: segmented exclusive suffix sums of the compositing contributions
+        float x[8] = {w * c[0], w * c[1], w * c[2], w * nf[0], w * nf[1], w * nf[2], w * t, w};
+        float R[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float e = __shfl_down_sync(FULL, x[j], 1);
+            if (!dn_ok[0]) e = 0.f;
+#pragma unroll
+            for (int s5 = 0; s5 < 5; ++s5) {
+                const float v = __shfl_down_sync(FULL, e, 1 << s5);
+                if (dn_ok[s5]) e += v;
+            }
+            const float seg_total = __shfl_sync(FULL, e + x[j], seg_lo);
+            const float rem_after = (straddles_in ? carry_rem[j] : F[j]) - seg_total;
+            R[j] = rem_after + e;
+            carry_rem[j] = __shfl_sync(FULL, rem_after, 31);
+        }
+        float RF[FEAT ? NFMAX : 1];
+        if (FEAT) {
+#pragma unroll
+            for (int j = 0; j < NFMAX; ++j) {
+                RF[j] = 0.f;
+                if (j < a.S) {
+                    const float xf = w * feat[j];
+                    float e = __shfl_down_sync(FULL, xf, 1);
+                    if (!dn_ok[0]) e = 0.f;
+#pragma unroll
+                    for (int s5 = 0; s5 < 5; ++s5) {
+                        const float v = __shfl_down_sync(FULL, e, 1 << s5);
+                        if (dn_ok[s5]) e += v;
+                    }
+                    const float seg_total = __shfl_sync(FULL, e + xf, seg_lo);
+                    const float rem_after = (straddles_in ? carry_remF[j] : Ff[j]) - seg_total;
+                    RF[j] = rem_after + e;
+                    carry_remF[j] = __shfl_sync(FULL, rem_after, 31);
+                }
+            }
+        }
+        carryT = __shfl_sync(FULL, T, 31);
+
+        // ---- gradient of this hit (gaussiantrace_backward.cu:100-166)
+        float dL_dalpha = gO[6] * (T * t - R[6]) + gO[7] * (1.f - F[7]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dL_dalpha += gO[j] * (T * c[j] - R[j]) + gO[3 + j] * (T * nf[j] - R[3 + j]);
+        if (FEAT) {
+#pragma unroll
+            for (int j = 0; j < NFMAX; ++j) dL_dalpha += gF[j] * (T * feat[j] - RF[j]);
+        }
+        dL_dalpha /= (1.f - alpha);
+        const float dL_do = dL_dalpha * G;
+        const float dL_dG = dL_dalpha * op;
+        const float dpu = -dL_dG * G * pu, dpv = -dL_dG * G * pv;
+        const float dposx = dpu * ax + dpv * bx, dposy = dpu * ay + dpv * by, dposz = dpu * az + dpv * bz;
+        const float dL_dd = gO[6] * w + (dposx * ro.dx + dposy * ro.dy + dposz * ro.dz);
+        const float dL_dog = -dL_dd / dg;
+        const float dL_ddg = dL_dd * og / fmaxf(1e-6f, dg * dg);
+        const float dnx = m * gO[3] * w + dL_ddg * ro.dx + dL_dog * relx;
+        const float dny = m * gO[4] * w + dL_ddg * ro.dy + dL_dog * rely;
+        const float dnz = m * gO[5] * w + dL_ddg * ro.dz + dL_dog * relz;
+        __syncwarp();
+        {
+            float4 *row = reinterpret_cast<float4 *>(rows + lane * BROW);
+            if (act) {
+                row[0] = make_float4(-dposx - dL_dog * nx, -dposy - dL_dog * ny, -dposz - dL_dog * nz, dL_do);
+                row[1] = make_float4(dpu * px, dpu * py, dpu * pz, dpv * px);
+                row[2] = make_float4(dpv * py, dpv * pz, dnx, dny);
+                row[3] = make_float4(dnz, 0.f, 0.f, 0.f);
+                const float gc[3] = {gO[0] * w, gO[1] * w, gO[2] * w};
+#pragma unroll
+                for (int v = 0; v < 12; ++v) {
+                    float4 q;
+                    q.x = Y[(4 * v) / 3] * gc[(4 * v) % 3];
+                    q.y = Y[(4 * v + 1) / 3] * gc[(4 * v + 1) % 3];
+                    q.z = Y[(4 * v + 2) / 3] * gc[(4 * v + 2) % 3];
+                    q.w = Y[(4 * v + 3) / 3] * gc[(4 * v + 3) % 3];
+                    row[4 + v] = q;
+                }
+                if (FEAT) {
+#pragma unroll
+                    for (int j = 0; j < NFMAX; ++j)
+                        if (j < a.S) atomicAdd(a.grad_features + (size_t)g * a.S + j, gF[j] * w);
+                }
+            }
+        }
+        // ---- ray gradients: segmented sums of the per-hit terms, collected by the owning lane
+        {
+            float y[6] = {dposx + dL_dog * nx, dposy + dL_dog * ny, dposz + dL_dog * nz,
+                          t * dposx + dL_ddg * nx, t * dposy + dL_ddg * ny, t * dposz + dL_ddg * nz};
+            // where (if anywhere) this lane's OWN ray has hits in this round
+            const int my_lo = max(start - base, 0);
+            const bool mine_here = has && start < base + 32 && start + c_eff > base;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                float e = act ? y[j] : 0.f;
+#pragma unroll
+                for (int s5 = 0; s5 < 5; ++s5) {
+                    const float v = __shfl_down_sync(FULL, e, 1 << s5);
+                    if (dn_ok[s5]) e += v;
+                }
+                const float tot = __shfl_sync(FULL, e, mine_here ? my_lo : lane);
+                if (mine_here) { if (j < 3) go[j] += tot; else gd[j - 3] += tot; }
+            }
+        }
+        __syncwarp();
+        // ---- per-surfel gradients: sixteen consecutive lanes add one 256-byte row with 16-byte reductions
+        const int n_here = min(32, total - base);
+        const int col = lane & 15;
+        for (int j = 0; j < n_here; j += 2) {
+            const int rowi = j + (lane >> 4);
+            const int g_r = __shfl_sync(FULL, g, rowi & 31);
+            if (rowi < n_here && col < 4 + nvec) {
+                const float4 v = *reinterpret_cast<const float4 *>(rows + rowi * BROW + 4 * col);
+                atomicAdd(reinterpret_cast<float4 *>(a.grad_fused + (size_t)g_r * IRGS_GRAD_STRIDE) + col, v);
+            }
+        }
+    }
+    if (valid && cnt <= a.hit_cap) {  // rays with longer lists are written by the re-trace kernel
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { a.g_rays_o[3 * my_ray + j] = go[j]; a.g_rays_d[3 * my_ray + j] = gd[j]; }
+    }
+}
+
 // One ray of the re-trace backward (the reference's scheme): same ordered passes as the forward, gradients applied
 // per hit.
 template <bool FEAT>
@@ -442,8 +715,13 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     const bool feat = a.S > 0;
     if (a.hits != nullptr && a.hit_count != nullptr) {
         const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
-        if (feat) trace_backward_replay_kernel<true><<<grid, TB, 0, s>>>(p);
-        else trace_backward_replay_kernel<false><<<grid, TB, 0, s>>>(p);
+        if (h->bwd_mode == 1) {   // thread-per-ray replay (kept for comparison: irgs_set_option("bwd_mode", 1))
+            if (feat) trace_backward_replay_kernel<true><<<grid, TB, 0, s>>>(p);
+            else trace_backward_replay_kernel<false><<<grid, TB, 0, s>>>(p);
+        } else {
+            if (feat) trace_backward_flat_kernel<true><<<grid, TB, 0, s>>>(p);
+            else trace_backward_flat_kernel<false><<<grid, TB, 0, s>>>(p);
+        }
         count_launch();
         IRGS_CHECK(cudaGetLastError());
         return feat ? launch_persistent(h, trace_backward_retrace_kernel<true, true>, p, a.n_rays, s)

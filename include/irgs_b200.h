@@ -134,6 +134,7 @@ void irgs_reset_launch_count(void);
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
  * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.
+ * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
  * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 

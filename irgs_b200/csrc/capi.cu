@@ -93,6 +93,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     cudaDeviceSynchronize();
     cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
+    cudaFree(h->ploc_cid); cudaFree(h->ploc_box); cudaFree(h->ploc_nn); cudaFree(h->ploc_counts); cudaFree(h->ploc_offs); cudaFree(h->ploc_totals);
     cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 2; ++k) { cudaFree(h->rsort_keys[i][k]); cudaFree(h->rsort_vals[i][k]); }
@@ -366,6 +367,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
     if (!h || !name) return fail("null argument");
     if (strcmp(name, "sort_rays_min") == 0) {
         h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
+        return 0;
+    }
+    if (strcmp(name, "builder") == 0) {   // takes effect at the next build_bvh / build_from_surfels
+        h->builder = value == 1 ? 1 : 0;
         return 0;
     }
     if (strcmp(name, "bwd_mode") == 0) {

@@ -61,6 +61,10 @@ struct irgs_tracer {
     int *leaf_parent = nullptr;         // [n]   parent*2+side
     int *node_parent = nullptr;         // [n]   parent*2+side, -1 for the root
     int *flags = nullptr;               // [n]   bottom-up arrival counters
+    int *ploc_cid = nullptr;            // [2][cap] PLOC cluster -> node reference (ping-pong)
+    float *ploc_box = nullptr;          // [2][cap] PLOC cluster bounds, 8 floats each
+    int *ploc_nn = nullptr, *ploc_counts = nullptr, *ploc_offs = nullptr, *ploc_totals = nullptr;
+    int builder = 0;                    // 0: PLOC over the Morton order (default), 1: Karras LBVH
     int *radix_hist = nullptr;          // [256 * n_tiles]
     int64_t radix_tiles_cap = 0;
     float *scene = nullptr;             // [24]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats),

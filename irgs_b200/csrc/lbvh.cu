@@ -356,6 +356,184 @@ __global__ void hierarchy_kernel(const uint32_t *__restrict__ codes, int n, Node
     nodes[i].d = make_int4(left, right, 0, 0);
 }
 
+// Step 4b: PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) instead of the Karras hierarchy.
+// The Morton-sorted leaves are the initial clusters; every iteration each cluster looks PLOC_R places to either side
+// for the neighbour whose union with it has the smallest surface area, mutual nearest neighbours are merged into a
+// new node, and the cluster array is compacted in order.  On the C3 rays the resulting tree needs 40 % fewer node
+// visits than the Karras LBVH over the same Morton order (scripts/exp/exp_bvh.c: 87 -> 52.5 per ray), for ~50
+// iterations of four small kernels at build time; refits (update_bvh) are unaffected.
+// Nodes are numbered from the top down as they are created (the last merge, the root, gets index 0), children of
+// neighbouring clusters next to each other.
+constexpr int PLOC_R = 8;
+constexpr int PLOC_TB = 256;     // nearest-neighbour search block
+constexpr int PLOC_SB = 1024;    // compaction block
+
+struct __align__(16) PlocBox { float4 lo, hi; };
+
+__global__ void ploc_init_kernel(const float *__restrict__ boxes, const int *__restrict__ order, int n,
+                                 int *__restrict__ cid, PlocBox *__restrict__ cbox) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const float *b = boxes + 6 * (size_t)order[pos];
+    PlocBox x;
+    if (b[0] <= b[3]) { x.lo = make_float4(b[0], b[1], b[2], 0.f); x.hi = make_float4(b[3], b[4], b[5], 0.f); }
+    else { x.lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f); x.hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f); }
+    cid[pos] = ~pos;
+    cbox[pos] = x;
+}
+
+__device__ __forceinline__ float union_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
+    const float ex = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
+    const float ey = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y);
+    const float ez = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return __fmaf_rn(ex, ey, __fmaf_rn(ey, ez, __fmul_rn(ez, ex)));   // symmetric in (a, b): mutual choices are consistent
+}
+
+__global__ void __launch_bounds__(PLOC_TB) ploc_nn_kernel(const PlocBox *__restrict__ cbox, int m, int *__restrict__ nn) {
+    __shared__ float4 s_lo[PLOC_TB + 2 * PLOC_R], s_hi[PLOC_TB + 2 * PLOC_R];
+    const int base = blockIdx.x * PLOC_TB - PLOC_R;
+    for (int t = threadIdx.x; t < PLOC_TB + 2 * PLOC_R; t += PLOC_TB) {
+        const int j = base + t;
+        if (j >= 0 && j < m) { s_lo[t] = cbox[j].lo; s_hi[t] = cbox[j].hi; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * PLOC_TB + threadIdx.x;
+    if (i >= m) return;
+    const float4 lo = s_lo[threadIdx.x + PLOC_R], hi = s_hi[threadIdx.x + PLOC_R];
+    float best = INFINITY;
+    int bj = -1;
+#pragma unroll
+    for (int dlt = -PLOC_R; dlt <= PLOC_R; ++dlt) {
+        const int j = i + dlt;
+        if (dlt == 0 || j < 0 || j >= m) continue;
+        const float ar = union_area(lo, hi, s_lo[threadIdx.x + PLOC_R + dlt], s_hi[threadIdx.x + PLOC_R + dlt]);
+        if (ar < best || bj < 0) { best = ar; bj = j; }   // ties (and non-finite areas): the lowest index
+    }
+    nn[i] = bj;
+}
+
+// flags of cluster i: bit 0 = survives the compaction (not the upper half of a merged pair), bit 16 = creates a node
+__device__ __forceinline__ int ploc_flags(const int *__restrict__ nn, int m, int i) {
+    if (i >= m) return 0;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && nn[j] == i;
+    return (mutual && i > j ? 0 : 1) | (mutual && i < j ? (1 << 16) : 0);
+}
+
+__device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int &block_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sums[lane] = winc - w;
+        if (lane == 31) warp_sums[32] = winc;
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    return warp_sums[wid] + inc - v;
+}
+
+__global__ void __launch_bounds__(PLOC_SB) ploc_count_kernel(const int *__restrict__ nn, int m, int *__restrict__ counts) {
+    __shared__ int ws[33];
+    int total;
+    block_excl_scan(ploc_flags(nn, m, blockIdx.x * PLOC_SB + threadIdx.x), ws, total);
+    if (threadIdx.x == 0) counts[blockIdx.x] = total;   // survivors | merges << 16 (both < 2^16 per block)
+}
+
+// exclusive scan of the per-block (survivors, merges) counts, single block; totals[0] = clusters after the iteration,
+// totals[1] = nodes created
+__global__ void __launch_bounds__(1024) ploc_scan_kernel(const int *__restrict__ counts, int n_blocks, int2 *__restrict__ offs,
+                                                         int *__restrict__ totals) {
+    __shared__ int ws_a[33], ws_b[33];
+    int run_a = 0, run_b = 0;
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int c = b < n_blocks ? counts[b] : 0;
+        int ta, tb;
+        const int ea = block_excl_scan(c & 0xffff, ws_a, ta);
+        const int eb = block_excl_scan(c >> 16, ws_b, tb);
+        if (b < n_blocks) offs[b] = make_int2(run_a + ea, run_b + eb);
+        run_a += ta; run_b += tb;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = run_a; totals[1] = run_b; }
+}
+
+__global__ void __launch_bounds__(PLOC_SB) ploc_scatter_kernel(const int *__restrict__ nn, int m, const int *__restrict__ cid_in,
+                                                               const PlocBox *__restrict__ cbox_in,
+                                                               const int2 *__restrict__ offs, const int *__restrict__ totals,
+                                                               int free_hi, int *__restrict__ cid_out,
+                                                               PlocBox *__restrict__ cbox_out, Node *__restrict__ nodes,
+                                                               int *__restrict__ leaf_parent, int *__restrict__ node_parent) {
+    __shared__ int ws[33];
+    const int i = blockIdx.x * PLOC_SB + threadIdx.x;
+    const int f = ploc_flags(nn, m, i);
+    int total;
+    const int ex = block_excl_scan(f, ws, total);
+    if (i >= m || !(f & 1)) return;
+    const int2 off = offs[blockIdx.x];
+    const int dst = off.x + (ex & 0xffff);
+    if (f >> 16) {
+        const int j = nn[i];
+        const int id = free_hi - totals[1] + off.y + (ex >> 16);   // new node
+        const int cl = cid_in[i], cr = cid_in[j];
+        const PlocBox a = cbox_in[i], b = cbox_in[j];
+        PlocBox u;
+        u.lo = make_float4(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z), 0.f);
+        u.hi = make_float4(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z), 0.f);
+        nodes[id].d = make_int4(cl, cr, 0, 0);
+        if (cl < 0) leaf_parent[~cl] = 2 * id; else node_parent[cl] = 2 * id;
+        if (cr < 0) leaf_parent[~cr] = 2 * id + 1; else node_parent[cr] = 2 * id + 1;
+        if (id == 0) node_parent[0] = -1;
+        cid_out[dst] = id;
+        cbox_out[dst] = u;
+    } else {
+        cid_out[dst] = cid_in[i];
+        cbox_out[dst] = cbox_in[i];
+    }
+}
+
+int ploc_build(irgs_tracer *h, cudaStream_t s) {
+    const int n = (int)h->n;
+    int *cid[2] = {h->ploc_cid, h->ploc_cid + h->cap};
+    PlocBox *cbox[2] = {reinterpret_cast<PlocBox *>(h->ploc_box), reinterpret_cast<PlocBox *>(h->ploc_box) + h->cap};
+    ploc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, n, cid[0], cbox[0]);
+    count_launch();
+    int m = n, free_hi = n - 1, cur = 0;
+    while (m > 1) {
+        const int nb = (m + PLOC_SB - 1) / PLOC_SB;
+        ploc_nn_kernel<<<(m + PLOC_TB - 1) / PLOC_TB, PLOC_TB, 0, s>>>(cbox[cur], m, h->ploc_nn);
+        ploc_count_kernel<<<nb, PLOC_SB, 0, s>>>(h->ploc_nn, m, h->ploc_counts);
+        ploc_scan_kernel<<<1, 1024, 0, s>>>(h->ploc_counts, nb, reinterpret_cast<int2 *>(h->ploc_offs), h->ploc_totals);
+        ploc_scatter_kernel<<<nb, PLOC_SB, 0, s>>>(h->ploc_nn, m, cid[cur], cbox[cur], reinterpret_cast<const int2 *>(h->ploc_offs),
+                                                   h->ploc_totals, free_hi, cid[cur ^ 1], cbox[cur ^ 1], h->nodes,
+                                                   h->leaf_parent, h->node_parent);
+        count_launch(4);
+        int tot[2] = {0, 0};
+        IRGS_CHECK(cudaMemcpyAsync(tot, h->ploc_totals, sizeof tot, cudaMemcpyDeviceToHost, s));
+        IRGS_CHECK(cudaStreamSynchronize(s));
+        if (tot[1] < 1 || tot[0] != m - tot[1]) { set_error("PLOC iteration made no progress"); return 1; }
+        m = tot[0];
+        free_hi -= tot[1];
+        cur ^= 1;
+    }
+    if (free_hi != 0) { set_error("PLOC node count mismatch"); return 1; }
+    return 0;
+}
+
 // Step 5: bottom-up bounds.  Each leaf thread writes its (padded) bound into its parent's slot and climbs; the
 // second arrival at a node reads the sibling slot, forms the union and continues.
 __device__ __forceinline__ void store_slot(Node *nd, int side, const float lo[3], const float hi[3]) {
@@ -499,7 +677,10 @@ int lbvh_reserve(irgs_tracer *h, int64_t n) {
     if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->qnodes, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
         !realloc_dev(h->codes_alt, (size_t)c) || !realloc_dev(h->order, (size_t)c) || !realloc_dev(h->order_alt, (size_t)c) ||
         !realloc_dev(h->leaf_parent, (size_t)c) || !realloc_dev(h->node_parent, (size_t)c) ||
-        !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c))
+        !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c) || !realloc_dev(h->ploc_cid, (size_t)c * 2) ||
+        !realloc_dev(h->ploc_box, (size_t)c * 2 * 8) || !realloc_dev(h->ploc_nn, (size_t)c) ||
+        !realloc_dev(h->ploc_counts, (size_t)(c / PLOC_SB + 2)) || !realloc_dev(h->ploc_offs, (size_t)(c / PLOC_SB + 2) * 2) ||
+        !realloc_dev(h->ploc_totals, 2))
         return 1;
     int64_t tiles = (c + RS_TILE - 1) / RS_TILE;
     if (!realloc_dev(h->radix_hist, (size_t)tiles * 256)) return 1;
@@ -536,8 +717,12 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
         count_launch();
         if (radix_sort_pairs(h->codes, h->codes_alt, h->order, h->order_alt, n, 4, h->radix_hist, s)) return 1;
         int n_int = n > 1 ? n - 1 : 1;
-        hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
-        count_launch();
+        if (h->builder == 0 && n > 2) {
+            if (ploc_build(h, s)) return 1;
+        } else {
+            hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
+            count_launch();
+        }
     }
     IRGS_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(int) * (size_t)n, s));
     refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, scene_i, h->nodes,

@@ -285,6 +285,30 @@ def test_bounds_match_oracle_and_root_contains_everything(small_scene):
     assert (root[:3] <= b[valid, :3].min(0)).all() and (root[3:] >= b[valid, 3:].max(0)).all()
 
 
+def test_ploc_and_karras_trees_give_bit_identical_results_and_ploc_visits_fewer_nodes(small_scene):
+    """The two builders (PLOC clustering, default; Karras LBVH) produce different topologies over the same leaves: the
+    traced results must not depend on it at all, and the PLOC tree must be the cheaper one to walk."""
+    from irgs_b200.raytracer import GaussianTracer
+    sc, inp = small_scene
+    g = _gpu(inp)
+    o, d = _rays(inp, "secondary")
+    outs, stats = [], []
+    for builder in (0, 1):
+        tr = GaussianTracer(transmittance_min=synth.T_MIN)
+        tr.set_option("builder", builder)
+        tr.build_from_surfels(g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], synth.ALPHA_MIN)
+        tr.set_stats(True)
+        with torch.no_grad():
+            res = tr.trace(o.to(DEV), d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], g["features"],
+                           g["shs"], synth.ALPHA_MIN)
+        outs.append([t.cpu().numpy() for t in res] + [tr.last_hit_count.cpu().numpy()])
+        stats.append(tr.get_stats())
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert stats[0][2] == stats[1][2] and stats[0][2] > 0          # same composited hits
+    assert stats[0][0] < 0.85 * stats[1][0], stats                 # PLOC: clearly fewer node visits
+
+
 def test_proxy_build_and_surfel_build_give_identical_results(small_scene):
     sc, inp = small_scene
     g = _gpu(inp)

@@ -55,7 +55,8 @@ __device__ __forceinline__ int collect_pass(const KParams &p, const RayCtx &r, f
     const int back_culling = p.a.back_culling;
     for (;;) {
         if (cur >= 0) {
-            const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
+            uint4 wl, wr;
+                ldg256(&p.nodes[cur], wl, wr);
             const int2 d = make_int2((int)wl.w, (int)wr.w);
             if (STATS) ++n_nodes;
             float tnL, tnR;
@@ -626,7 +627,8 @@ __global__ void __launch_bounds__(TB) intersection_test_kernel(const KParams p, 
     bool found = false;
     for (;;) {
         if (cur >= 0) {
-            const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
+            uint4 wl, wr;
+                ldg256(&p.nodes[cur], wl, wr);
             const int2 d = make_int2((int)wl.w, (int)wr.w);
             float tnL, tnR;
             bool hL = slab(r, wl, 0.f, IRGS_T_SCENE_MAX, tnL);

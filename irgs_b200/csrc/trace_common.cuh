@@ -31,6 +31,19 @@ struct KParams {
     unsigned long long *stats;
 };
 
+// 256-bit read-only loads (sm_100a: LDG.E.256): a 32-byte quantised node or half a surfel record in ONE request.  The
+// walk is bound by the L1TEX data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 73 % of peak), not by DRAM or L2.
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
 // fixed-order dot product, bit-identical to dot3() of oracle/surfel_oracle.c
 __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
     return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
@@ -68,14 +81,23 @@ __device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, i
     if (K == 16) {
         const float4 *p = reinterpret_cast<const float4 *>(shs + (size_t)g * 48);
         const int nvec = (nb * 3 + 3) >> 2;
+        const bool wide = (reinterpret_cast<size_t>(shs) & 31) == 0;   // rows are 192 B: 32-byte aligned iff the base is
 #pragma unroll
-        for (int v = 0; v < 12; ++v) {
+        for (int v = 0; v < 12; v += 2) {
             if (v < nvec) {
-                float4 q = __ldg(p + v);
+                float4 q, q2;
+                if (wide) ldg256(p + v, q, q2);
+                else { q = __ldg(p + v); q2 = __ldg(p + v + 1); }
                 acc[(4 * v) % 3] += Y[(4 * v) / 3] * q.x;
                 acc[(4 * v + 1) % 3] += Y[(4 * v + 1) / 3] * q.y;
                 acc[(4 * v + 2) % 3] += Y[(4 * v + 2) / 3] * q.z;
                 acc[(4 * v + 3) % 3] += Y[(4 * v + 3) / 3] * q.w;
+                if (v + 1 < nvec) {
+                    acc[(4 * v + 4) % 3] += Y[(4 * v + 4) / 3] * q2.x;
+                    acc[(4 * v + 5) % 3] += Y[(4 * v + 5) / 3] * q2.y;
+                    acc[(4 * v + 6) % 3] += Y[(4 * v + 6) / 3] * q2.z;
+                    acc[(4 * v + 7) % 3] += Y[(4 * v + 7) / 3] * q2.w;
+                }
             }
         }
     } else {
@@ -161,8 +183,10 @@ __device__ __forceinline__ bool leaf_eval(const RayCtx &r, const float4 r0, cons
 
 __device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
                                           int back_culling, float &t_out, int &g_out, float &alpha_out) {
-    return leaf_eval(r, __ldg(&rec->r0), __ldg(&rec->r1), __ldg(&rec->r2), __ldg(&rec->r3), alpha_min, back_culling, t_out,
-                     g_out, alpha_out);
+    float4 q0, q1, q2, q3;
+    ldg256(&rec->r0, q0, q1);
+    ldg256(&rec->r2, q2, q3);
+    return leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t_out, g_out, alpha_out);
 }
 
 __device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }

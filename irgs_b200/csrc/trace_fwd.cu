@@ -44,8 +44,11 @@ constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #ifndef IRGS_PQ
 #define IRGS_PQ 12
 #endif
-constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
-static_assert(32 * PQ <= (8 + NFMAX) * 32, "the flattened leaf list aliases the COMP scratch");
+constexpr int PQ = IRGS_PQ;
+#ifndef IRGS_COMP_MIN
+#define IRGS_COMP_MIN 24
+#endif
+constexpr int COMP_MIN = IRGS_COMP_MIN;   // candidates that must be waiting before a packed compositing round is run               // pending-leaf queue entries per lane
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -59,6 +62,10 @@ struct WarpSmem {
     float scratch[(8 + NFMAX) * 32];   // co-operative sort / accumulation scratch
     int pend[PQ * 32];        // pending leaves [entry][lane]
     int stack[SSTK * 32];     // traversal stack [entry][lane]
+    // per-segment table of the packed COMP phase
+    int seg_lo[32], seg_nc[32];
+    float seg_T[32];
+    int64_t seg_ray[32];
 };
 
 template <bool FEAT, bool STATS>
@@ -118,7 +125,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         // (a node visit can queue two leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
         while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 2)) {
             if (phase == PH_TRAV && cur != CUR_NONE) {
-                const uint4 wl = __ldg(&p.nodes[cur].l), wr = __ldg(&p.nodes[cur].r);
+                uint4 wl, wr;
+                ldg256(&p.nodes[cur], wl, wr);
                 if (STATS) ++st_nodes;
                 float tnL, tnR;
                 const bool hL = slab(r, wl, t_lo, t_hi, tnL);
@@ -148,10 +156,12 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         }
 
         // ------------------------------------------------------------------ BVH walk, LEAF sub-phase
-        // The pending leaves of ALL lanes are flattened into one warp-wide list (shared memory) and tested 32 at a
-        // time, one (ray, surfel) pair per lane whoever owns the ray: the owner's ray and depth window come through
-        // shuffles.  (Each lane draining its own queue ran this code at 5.7 of 32 lanes: profiles/r01_fwd_regions_v7q.txt.)
-        // A lane submits at most as many leaves as its candidate row has room for; the rest stay queued (PH_FULL).
+        // The pending leaves of ALL lanes form one warp-wide list (prefix sum of the queue lengths) that is tested 32
+        // items at a time, one (ray, surfel) pair per lane whoever owns the ray: item -> owner by a binary search over
+        // the prefix sums (shuffles), the leaf straight from the owner's queue column in shared memory, the owner's ray
+        // and depth window through shuffles.  (Each lane draining its own queue ran this code at 5.7 of 32 lanes:
+        // profiles/r01_fwd_regions_v7q.txt.)  A lane submits at most as many leaves as its candidate row has room
+        // for; the rest stay queued (PH_FULL).
         for (;;) {
             const int m = (phase == PH_TRAV) ? min(pn, KB - cnt) : 0;
             if (!__any_sync(FULL, m > 0)) break;
@@ -163,20 +173,25 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             }
             const int start = incl - m;
             const int n_items = __shfl_sync(FULL, incl, 31);
-            int *flat = reinterpret_cast<int *>(ws.scratch);   // [32 * PQ] at most; the COMP phase is not running now
-            __syncwarp();
-            for (int k = 0; k < m; ++k) { --pn; flat[start + k] = (int)(lane << 27) | ~pend[pn * 32]; }
-            __syncwarp();
+            __syncwarp();   // queue columns written in the NODE sub-phase are read by other lanes below
             for (int base = 0; base < n_items; base += 32) {
                 const int idx = base + (int)lane;
                 const bool has = idx < n_items;
-                const int e = has ? flat[idx] : (int)(lane << 27);
-                const int owner = (int)((unsigned)e >> 27);
+                int owner = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, owner + step - 1);
+                    if (v <= idx) owner += step;
+                }
+                owner = has ? owner : (int)lane;
+                const int o_start = __shfl_sync(FULL, start, owner), o_m = __shfl_sync(FULL, m, owner);
+                const int o_pn = __shfl_sync(FULL, pn, owner), o_cnt = __shfl_sync(FULL, cnt, owner);
                 float4 q0, q1, q2, q3;
                 q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (has) {
-                    const float4 *src = reinterpret_cast<const float4 *>(p.recs + (e & 0x07ffffff));
-                    q0 = __ldg(src); q1 = __ldg(src + 1); q2 = __ldg(src + 2); q3 = __ldg(src + 3);
+                    const int leaf = ~ws.pend[(o_pn - 1 - (idx - o_start)) * 32 + owner];   // popped from the top
+                    const float4 *src = reinterpret_cast<const float4 *>(p.recs + leaf);
+                    ldg256(src, q0, q1); ldg256(src + 2, q2, q3);
                     if (STATS) ++st_leaf;
                 }
                 RayCtx ro;
@@ -184,8 +199,6 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);
                 const float o_tlast = __shfl_sync(FULL, t_last, owner), o_thi = __shfl_sync(FULL, t_hi, owner);
                 const int o_glast = __shfl_sync(FULL, g_last, owner), o_ghi = __shfl_sync(FULL, g_hi, owner);
-                const int o_start = __shfl_sync(FULL, start, owner), o_m = __shfl_sync(FULL, m, owner);
-                const int o_cnt = __shfl_sync(FULL, cnt, owner);
                 float t, alpha; int g;
                 const bool ok = has && leaf_eval(ro, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
                                 key_less(o_tlast, o_glast, t, g) && key_less(t, g, o_thi, o_ghi);
@@ -204,10 +217,60 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     cnt += __popc(acc & hm & ~lm);
                 }
             }
+            pn -= m;
             if (phase == PH_TRAV && cnt == KB) phase = PH_FULL;   // pending leaves stay queued until the row has been trimmed
         }
         // the walk of this pass is complete once the stack, the current node and the leaf queue are all empty
         if (phase == PH_TRAV && cur == CUR_NONE && pn == 0) phase = PH_COMP;
+
+        // ------------------------------------------------------------------ FULL rows: co-operative sort + trim / split
+        unsigned work = __ballot_sync(FULL, phase == PH_FULL);
+        while (work != 0u) {
+            const int L = __ffs(work) - 1;
+            work &= work - 1u;
+            __syncwarp();  // lane L's appended candidates are visible to the whole warp
+            // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
+            const uint4 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
+            float my_t = __uint_as_float(e.x), my_a = __uint_as_float(e.z); int my_g = (int)e.y;
+            int rank = 0;
+            for (int j = 0; j < KB; ++j) {
+                const float tj = __shfl_sync(FULL, my_t, j);
+                const int gj = __shfl_sync(FULL, my_g, j);
+                rank += key_less(tj, gj, my_t, my_g) ? 1 : 0;
+            }
+            {
+                float *s_f = ws.scratch;
+                int *s_i = reinterpret_cast<int *>(ws.scratch);
+                s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a;
+                __syncwarp();
+                my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane];
+                __syncwarp();
+            }
+            // transmittance chain in the reference's sequential order
+            float Tc = __shfl_sync(FULL, T, L);
+            int n_comp = KB;
+            bool term = false;
+            for (int i = 0; i < KB; ++i) {
+                const float ai = __shfl_sync(FULL, my_a, i);
+                Tc *= (1.f - ai);
+                if (Tc < T_min) { n_comp = i + 1; term = true; break; }
+            }
+            // terminated: keep the composited prefix and clip the walk to it; otherwise split the depth range at the
+            // KB/2-th candidate and leave the rest of the ray to a following pass
+            // (a row that terminates only at its very last entry cannot be trimmed: it is split like any other)
+            const bool split = !(term && n_comp < KB);
+            const int keep = split ? KB / 2 : n_comp;
+            const float t_end = __shfl_sync(FULL, my_t, keep - 1);
+            const int g_end = __shfl_sync(FULL, my_g, keep - 1);
+            if ((int)lane < keep)
+                warp_cand[(size_t)L * KB + lane] = make_uint4(__float_as_uint(my_t), (unsigned)my_g, __float_as_uint(my_a), 0u);
+            if ((int)lane == L) {
+                cnt = keep; t_hi = t_end; g_hi = g_end;
+                if (split) more = true;
+                // resume the walk; if nothing is left to walk the row is composited right away
+                phase = (cur == CUR_NONE && pn == 0) ? PH_COMP : PH_TRAV;
+            }
+        }
 
         // ------------------------------------------------------------------ lanes whose pass found nothing
         if (phase == PH_COMP && cnt == 0) {
@@ -217,70 +280,92 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             phase = PH_FETCH;
         }
 
-        // ------------------------------------------------------------------ co-operative sort / trim / composite
-        unsigned work = __ballot_sync(FULL, phase >= PH_COMP);
-        while (work != 0u) {
-            const int L = __ffs(work) - 1;
-            work &= work - 1u;
-            __syncwarp();  // lane L's appended candidates are visible to the whole warp
-            const int n = __shfl_sync(FULL, cnt, L);
-            const bool is_full = __shfl_sync(FULL, phase, L) == PH_FULL;
-            // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
+        // ------------------------------------------------------------------ co-operative sort + composite, several rays at once
+        // The finished rows of as many lanes as fit are packed into the 32 lanes (one candidate per lane, a ray's
+        // candidates in consecutive lanes = a segment); ranking, the transmittance chain and the accumulation run per
+        // segment, all segments side by side.  (One ray at a time, these loops were 30 % of all issued instructions with
+        // 12.7 of 32 lanes holding a candidate on average.)
+        // Compositing waits until enough candidates have piled up to fill most of a packed round, or until the walk is
+        // about to run short of lanes anyway.
+        unsigned comp = __ballot_sync(FULL, phase == PH_COMP);
+        if (comp != 0u) {
+            const int waiting = __reduce_add_sync(FULL, phase == PH_COMP ? cnt : 0);
+            const int still_walking = __popc(__ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE));
+            if (waiting < COMP_MIN && still_walking >= thr) comp = 0u;
+        }
+        while (comp != 0u) {
+            __syncwarp();  // appended candidates are visible to the whole warp
+            const bool is_comp = (comp >> lane) & 1u;
+            int incl = is_comp ? cnt : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            const unsigned gmask = __ballot_sync(FULL, is_comp && incl <= 32);   // a prefix of the waiting lanes; never empty
+            comp &= ~gmask;
+            const int g_last_lane = 31 - __clz(gmask);
+            const int gtotal = __shfl_sync(FULL, incl, g_last_lane);
+            incl = min(incl, gtotal);
+            const bool in_group = (gmask >> lane) & 1u;
+            const int c2 = in_group ? cnt : 0;
+            const int start2 = incl - c2;
+            const int maxn = __reduce_max_sync(FULL, c2);
+            // candidate of this lane: owner = number of lanes whose inclusive count is <= lane
+            const bool act = (int)lane < gtotal;
+            int owner = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int v = __shfl_sync(FULL, incl, owner + step - 1);
+                if (v <= (int)lane) owner += step;
+            }
+            owner = act ? owner : (int)lane;
+            const int o_start2 = __shfl_sync(FULL, start2, owner), o_c2 = __shfl_sync(FULL, c2, owner);
+            const int seg_lo = act ? o_start2 : (int)lane;
+            const int n_o = act ? o_c2 : 0;
+            int k = (int)lane - seg_lo;
             float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX;
-            if ((int)lane < n) {
-                const uint4 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
+            if (act) {
+                const uint4 e = __ldcg(&warp_cand[(size_t)owner * KB + k]);
                 my_t = __uint_as_float(e.x); my_g = (int)e.y; my_a = __uint_as_float(e.z);
             }
             int rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const float tj = __shfl_sync(FULL, my_t, j);
-                const int gj = __shfl_sync(FULL, my_g, j);
-                rank += key_less(tj, gj, my_t, my_g) ? 1 : 0;
+            for (int j = 0; j < maxn; ++j) {
+                const int src = (seg_lo + j) & 31;
+                const float tj = __shfl_sync(FULL, my_t, src);
+                const int gj = __shfl_sync(FULL, my_g, src);
+                rank += (j < n_o && key_less(tj, gj, my_t, my_g)) ? 1 : 0;
             }
             {
                 float *s_f = ws.scratch;
                 int *s_i = reinterpret_cast<int *>(ws.scratch);
-                if ((int)lane < n) { s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a; }
+                if (act) { s_f[seg_lo + rank] = my_t; s_i[32 + seg_lo + rank] = my_g; s_f[64 + seg_lo + rank] = my_a; }
                 __syncwarp();
-                if ((int)lane < n) { my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; }
+                if (act) { my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; }
                 __syncwarp();
             }
-            // transmittance chain in the reference's sequential order (bit-identical termination decisions)
-            float Tc = __shfl_sync(FULL, T, L);
+            // transmittance chain of every segment in the reference's sequential order (bit-identical termination decisions)
+            float Tc = __shfl_sync(FULL, T, owner);
             float my_w = 0.f;
-            int n_comp = n;
+            int n_comp = n_o;
             bool term = false;
-            for (int i = 0; i < n; ++i) {
-                const float ai = __shfl_sync(FULL, my_a, i);
-                if ((int)lane == i) my_w = Tc * ai;
-                Tc *= (1.f - ai);
-                if (Tc < T_min) { n_comp = i + 1; term = true; break; }
-            }
-            if (is_full) {
-                // terminated: keep the composited prefix; otherwise split the depth range at the KB/2-th candidate
-                // (a row that terminates only at its very last entry cannot be trimmed: it is split like any other)
-                const bool split = !(term && n_comp < KB);
-                const int keep = split ? KB / 2 : n_comp;
-                const float t_end = __shfl_sync(FULL, my_t, keep - 1);
-                const int g_end = __shfl_sync(FULL, my_g, keep - 1);
-                if ((int)lane < keep)
-                    warp_cand[(size_t)L * KB + lane] = make_uint4(__float_as_uint(my_t), (unsigned)my_g, __float_as_uint(my_a), 0u);
-                if ((int)lane == L) {
-                    cnt = keep; t_hi = t_end; g_hi = g_end;
-                    if (split) more = true;
-                    // resume the walk; if nothing is left to walk the row is composited right away
-                    phase = (cur == CUR_NONE && pn == 0) ? PH_COMP : PH_TRAV;
+            for (int i = 0; i < maxn; ++i) {
+                const float ai = __shfl_sync(FULL, my_a, (seg_lo + i) & 31);
+                if (i < n_o && !term) {
+                    if (k == i) my_w = Tc * ai;
+                    Tc *= (1.f - ai);
+                    if (Tc < T_min) { n_comp = i + 1; term = true; }
                 }
-                if (__shfl_sync(FULL, phase, L) == PH_COMP) work |= (1u << L);
-                continue;
             }
-            const float dxl = __shfl_sync(FULL, r.dx, L), dyl = __shfl_sync(FULL, r.dy, L), dzl = __shfl_sync(FULL, r.dz, L);
+            const float dxl = __shfl_sync(FULL, r.dx, owner), dyl = __shfl_sync(FULL, r.dy, owner), dzl = __shfl_sync(FULL, r.dz, owner);
+            const int64_t ray_o = __shfl_sync(FULL, ray, owner);
+            const int total_o = __shfl_sync(FULL, total, owner);
             // shade one hit per lane
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dd = 0.f, oo = 0.f;
+            float c0 = 0.f, c1 = 0.f, c2c = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dd = 0.f, oo = 0.f;
             float f[FEAT ? NFMAX : 1];
 #pragma unroll
             for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) f[j] = 0.f;
-            const bool mine = (int)lane < n_comp;
+            const bool mine = act && k < n_comp;
             if (mine) {
                 float Y[16];
                 sh_basis(a.deg, dxl, dyl, dzl, Y);
@@ -290,7 +375,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 const float m = (-dg > 0.f) ? 1.f : -1.f;
                 float c[3];
                 sh_color(a.shs, a.K, a.deg, my_g, Y, c);
-                c0 = my_w * c[0]; c1 = my_w * c[1]; c2 = my_w * c[2];
+                c0 = my_w * c[0]; c1 = my_w * c[1]; c2c = my_w * c[2];
                 n0 = my_w * m * nx; n1 = my_w * m * ny; n2 = my_w * m * nz;
                 dd = my_w * my_t; oo = my_w;
                 if (FEAT) {
@@ -298,18 +383,15 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     for (int j = 0; j < NFMAX; ++j)
                         if (j < a.S) f[j] = my_w * __ldg(a.features + (size_t)my_g * a.S + j);
                 }
+                if (a.hits != nullptr && total_o + k < a.hit_cap) a.hits[ray_o * a.hit_cap + total_o + k] = my_g;
             }
-            const int64_t ray_L = __shfl_sync(FULL, ray, L);
-            const int total_L = __shfl_sync(FULL, total, L);
-            if (a.hits != nullptr && mine && total_L + (int)lane < a.hit_cap) a.hits[ray_L * a.hit_cap + total_L + lane] = my_g;
-            // Sequential accumulation in depth order, exactly like the reference's loop (and the oracle's): channel k of
-            // the ray's outputs is owned by lane k, which adds the n_comp terms one after the other to the running value
-            // in global memory (pre-zeroed by the launcher).  The result is therefore independent of how the hits were
-            // grouped into passes and of the acceleration structure's topology.
+            // Sequential accumulation in depth order, exactly like the reference's loop (and the oracle's): one lane per
+            // (ray, output channel) adds that ray's n_comp terms one after the other to the running value in global
+            // memory (pre-zeroed by the launcher).  The result is therefore independent of how the hits were grouped
+            // into passes and of the acceleration structure's topology.
             {
-                float *s_c = ws.scratch;   // [channel][hit]
-                __syncwarp();
-                s_c[0 * 32 + lane] = c0; s_c[1 * 32 + lane] = c1; s_c[2 * 32 + lane] = c2;
+                float *s_c = ws.scratch;   // [channel][lane]
+                s_c[0 * 32 + lane] = c0; s_c[1 * 32 + lane] = c1; s_c[2 * 32 + lane] = c2c;
                 s_c[3 * 32 + lane] = n0; s_c[4 * 32 + lane] = n1; s_c[5 * 32 + lane] = n2;
                 s_c[6 * 32 + lane] = dd; s_c[7 * 32 + lane] = oo;
                 if (FEAT) {
@@ -317,25 +399,37 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     for (int j = 0; j < NFMAX; ++j)
                         if (j < a.S) s_c[(8 + j) * 32 + lane] = f[j];
                 }
-                __syncwarp();
-                const int n_ch = 8 + (FEAT ? a.S : 0);
-                if ((int)lane < n_ch) {
-                    float *dst;
-                    if (lane < 3) dst = a.color + 3 * ray_L + lane;
-                    else if (lane < 6) dst = a.normal + 3 * ray_L + (lane - 3);
-                    else if (lane == 6) dst = a.depth + ray_L;
-                    else if (lane == 7) dst = a.alpha + ray_L;
-                    else dst = a.feature + ray_L * a.S + (lane - 8);
-                    float acc = *dst;
-                    for (int i = 0; i < n_comp; ++i) acc += s_c[lane * 32 + i];
-                    *dst = acc;
+                // per-segment table, written by the first lane of each segment
+                if (act && k == 0) {
+                    const int sidx = __popc(gmask & ((1u << owner) - 1u));
+                    ws.seg_lo[sidx] = seg_lo; ws.seg_nc[sidx] = term ? -n_comp : n_comp; ws.seg_T[sidx] = Tc;
+                    ws.seg_ray[sidx] = ray_o;
                 }
                 __syncwarp();
+                const int n_ch = 8 + (FEAT ? a.S : 0);
+                const int pairs = __popc(gmask) * n_ch;
+                for (int pr = (int)lane; pr < pairs; pr += 32) {
+                    const int sidx = pr / n_ch, ch = pr - sidx * n_ch;
+                    const int lo = ws.seg_lo[sidx], nc = abs(ws.seg_nc[sidx]);
+                    const int64_t rr = ws.seg_ray[sidx];
+                    float *dst;
+                    if (ch < 3) dst = a.color + 3 * rr + ch;
+                    else if (ch < 6) dst = a.normal + 3 * rr + (ch - 3);
+                    else if (ch == 6) dst = a.depth + rr;
+                    else if (ch == 7) dst = a.alpha + rr;
+                    else dst = a.feature + rr * a.S + (ch - 8);
+                    float accv = *dst;
+                    for (int i = 0; i < nc; ++i) accv += s_c[ch * 32 + lo + i];
+                    *dst = accv;
+                }
             }
-            if ((int)lane == L) {
-                T = Tc;
-                total += n_comp;
-                if (!term && more) {
+            if (in_group) {
+                const int sidx = __popc(gmask & lt_mask);
+                const int nc_signed = ws.seg_nc[sidx];
+                const bool term_L = nc_signed < 0;
+                T = ws.seg_T[sidx];
+                total += abs(nc_signed);
+                if (!term_L && more) {
                     // this pass covered the depth range up to (t_hi, g_hi) completely without terminating: the next
                     // pass continues strictly after it
                     t_last = t_hi; g_last = g_hi;
@@ -349,6 +443,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     phase = PH_FETCH;
                 }
             }
+            __syncwarp();
         }
     }
     if (STATS) {

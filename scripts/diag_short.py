@@ -12,7 +12,7 @@ def factory(sc, inp):
     return tr
 sc, inp, tr, ro, rd = bench.build_workload(A, dev, 0, 1, factory)
 args = (inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"], synth.ALPHA_MIN)
-for srt in (0, 1 << 17):
+for srt in ((0, 1 << 17) if os.environ.get('SORT') else (0,)):
   tr.set_option("sort_rays_min", srt)
   for n in (1 << 22, 1 << 24):
     n = min(n, ro.shape[0]); best = 1e9

@@ -85,7 +85,7 @@ static float (*wbox)[8][6];
 
 int main(int argc, char **argv) {
     int N = atoi(argv[2]), R = atoi(argv[4]), mode = atoi(argv[5]), radius = argc > 6 ? atoi(argv[6]) : 16;
-    int W = argc > 7 ? atoi(argv[7]) : 2;
+    int W = argc > 7 ? atoi(argv[7]) : 2; int FIXED = 0; if (W < 0) { W = -W; FIXED = 1; }
     box = malloc(sizeof(float[6]) * N); FILE *f = fopen(argv[1], "rb"); if (fread(box, 24, N, f) != (size_t)N) return 1; fclose(f);
     float (*rays)[7] = malloc(sizeof(float[7]) * R); f = fopen(argv[3], "rb"); if (fread(rays, 28, R, f) != (size_t)R) return 1; fclose(f);
     nodes = malloc(sizeof(BNode) * N);
@@ -128,6 +128,9 @@ int main(int argc, char **argv) {
         int *stackb = malloc(sizeof(int) * 2 * N), *stackw = malloc(sizeof(int) * 2 * N); int sp = 0;
         n_w = 1; stackb[0] = root; stackw[0] = 0; sp = 1;
         while (sp) { --sp; int b = stackb[sp], w = stackw[sp]; int ch[8]; int nch = 2; ch[0] = nodes[b].left; ch[1] = nodes[b].right;
+            if (FIXED) { int c0 = ch[0], c1 = ch[1]; nch = 0; if (c0 >= 0) { ch[nch++] = nodes[c0].left; ch[nch++] = nodes[c0].right; } else ch[nch++] = c0;
+                if (c1 >= 0) { ch[nch++] = nodes[c1].left; ch[nch++] = nodes[c1].right; } else ch[nch++] = c1; }
+            else
             while (nch < W) { int best = -1; float ba = -1; for (int i = 0; i < nch; ++i) if (ch[i] >= 0) { float a = area1(nodes[ch[i]].lo, nodes[ch[i]].hi); if (a > ba) { ba = a; best = i; } }
                 if (best < 0) break; int c = ch[best]; ch[best] = nodes[c].left; ch[nch++] = nodes[c].right; }
             wn[w].nch = nch;

@@ -94,7 +94,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
     cudaFree(h->ploc_cid); cudaFree(h->ploc_box); cudaFree(h->ploc_nn); cudaFree(h->ploc_counts); cudaFree(h->ploc_offs); cudaFree(h->ploc_totals);
-    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
+    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->inv_order); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 2; ++k) { cudaFree(h->rsort_keys[i][k]); cudaFree(h->rsort_vals[i][k]); }
         cudaFree(h->rsort_hist[i]);
@@ -374,7 +374,7 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         return 0;
     }
     if (strcmp(name, "bwd_mode") == 0) {
-        h->bwd_mode = value == 1 ? 1 : 0;
+        h->bwd_mode = (value == 1 || value == 2) ? (int)value : 0;
         return 0;
     }
     return fail("unknown option");

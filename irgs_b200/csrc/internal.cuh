@@ -24,8 +24,8 @@ struct __align__(16) Node {
 static_assert(sizeof(Node) == 64, "node must be 64 bytes");
 
 // Per-leaf surfel record in Morton order, packed from the caller's arrays at every trace call (64 bytes):
-//   r0 = (mu.x, mu.y, mu.z, opacity)   r1 = (n.x, n.y, n.z, bits(surfel id))
-//   r2 = (ru.x, ru.y, ru.z, rv.x)      r3 = (rv.y, rv.z, 0, 0)
+//   r0 = (mu.x, mu.y, mu.z, support radius^2)   r1 = (n.x, n.y, n.z, bits(surfel id))
+//   r2 = (ru.x, ru.y, ru.z, rv.x)               r3 = (rv.y, rv.z, opacity, 0)
 struct __align__(16) SurfelRec {
     float4 r0, r1, r2, r3;
 };
@@ -70,6 +70,7 @@ struct irgs_tracer {
     float *scene = nullptr;             // [24]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats),
                                         //       12-14 quantisation frame lo, 15-17 cell size
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
+    int *inv_order = nullptr;           // [n] surfel id -> leaf position (written with the records)
     unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
     int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)
     uint4 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t, id, alpha, -)

@@ -677,7 +677,7 @@ int lbvh_reserve(irgs_tracer *h, int64_t n) {
     if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->qnodes, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
         !realloc_dev(h->codes_alt, (size_t)c) || !realloc_dev(h->order, (size_t)c) || !realloc_dev(h->order_alt, (size_t)c) ||
         !realloc_dev(h->leaf_parent, (size_t)c) || !realloc_dev(h->node_parent, (size_t)c) ||
-        !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c) || !realloc_dev(h->ploc_cid, (size_t)c * 2) ||
+        !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c) || !realloc_dev(h->inv_order, (size_t)c) || !realloc_dev(h->ploc_cid, (size_t)c * 2) ||
         !realloc_dev(h->ploc_box, (size_t)c * 2 * 8) || !realloc_dev(h->ploc_nn, (size_t)c) ||
         !realloc_dev(h->ploc_counts, (size_t)(c / PLOC_SB + 2)) || !realloc_dev(h->ploc_offs, (size_t)(c / PLOC_SB + 2) * 2) ||
         !realloc_dev(h->ploc_totals, 2))

@@ -24,21 +24,42 @@ namespace irgs {
 
 // ------------------------------------------------------------------------------------------------ pack
 // Gather the caller's five per-surfel arrays into 64-byte records in leaf (Morton) order, once per trace call,
-// so that one leaf test is two (early reject) or four 16-byte loads from adjacent lines.
+// so that one leaf test is one (early reject) or two 32-byte loads from one line; also the inverse map surfel -> leaf
+// position, through which the backward replay reaches the same records.
+// r0.w is the squared radius of the surfel's support { alpha >= alpha_min } around mu: the in-plane map p -> (ru.p, rv.p)
+// has smallest singular value sqrt(lambda_min), so |p|^2 <= 2 ln(opacity / alpha_min) / lambda_min on the support.
 __global__ void pack_records_kernel(const int *__restrict__ order, int n, const float *__restrict__ means,
                                     const float *__restrict__ opacity, const float *__restrict__ ru,
-                                    const float *__restrict__ rv, const float *__restrict__ normals,
-                                    SurfelRec *__restrict__ recs) {
+                                    const float *__restrict__ rv, const float *__restrict__ normals, float alpha_min,
+                                    SurfelRec *__restrict__ recs, int *__restrict__ inv_order) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int g = order[i];
     const float *m = means + 3 * (size_t)g, *nn = normals + 3 * (size_t)g, *a = ru + 3 * (size_t)g, *b = rv + 3 * (size_t)g;
+    const float op = opacity[g];
+    float rmax2 = -1.f;   // opacity <= alpha_min: never a hit
+    if (op > alpha_min) {
+        rmax2 = INFINITY;  // degenerate frames: no early reject
+        const float n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+        if (n2 > 0.f) {
+            const float an = (a[0] * nn[0] + a[1] * nn[1] + a[2] * nn[2]), bn = (b[0] * nn[0] + b[1] * nn[1] + b[2] * nn[2]);
+            const float aa = a[0] * a[0] + a[1] * a[1] + a[2] * a[2] - an * an / n2;
+            const float dd = b[0] * b[0] + b[1] * b[1] + b[2] * b[2] - bn * bn / n2;
+            const float ab = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] - an * bn / n2;
+            const float h = 0.5f * (aa - dd);
+            const float lmin = 0.5f * (aa + dd) - sqrtf(h * h + ab * ab);
+            const float r2 = 2.0f * logf(op / alpha_min);
+            // the subtraction loses relative accuracy when the frame is very anisotropic: trust it only when well conditioned
+            if (lmin > 1e-3f * (aa + dd)) rmax2 = r2 / lmin * 1.001f + 1e-12f;
+        }
+    }
     SurfelRec r;
-    r.r0 = make_float4(m[0], m[1], m[2], opacity[g]);
+    r.r0 = make_float4(m[0], m[1], m[2], rmax2);
     r.r1 = make_float4(nn[0], nn[1], nn[2], __int_as_float(g));
     r.r2 = make_float4(a[0], a[1], a[2], b[0]);
-    r.r3 = make_float4(b[1], b[2], 0.f, 0.f);
+    r.r3 = make_float4(b[1], b[2], op, 0.f);
     recs[i] = r;
+    inv_order[g] = i;
 }
 
 // One pass: collect the <= KBUF nearest candidates strictly after (t_last, g_last), ascending, into the shared
@@ -259,7 +280,7 @@ __global__ void __launch_bounds__(TB) trace_backward_replay_kernel(const KParams
 // with the scattered reductions.
 constexpr int BROW = 76;   // floats per shared-memory row: 64 gradient floats + 6 ray-gradient terms, 76 % 32 == 12 (conflict-free float4 stores)
 
-template <bool FEAT>
+template <bool FEAT, bool BULK>
 __global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p) {
     __shared__ __align__(16) float s_rows[TB / 32][32 * BROW];
     const TraceArgs &a = p.a;
@@ -346,13 +367,16 @@ __global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p
         if (act) {
             g = __ldg(a.hits + ray * a.hit_cap + k);
             sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
-            const float *pm = a.means + 3 * (size_t)g, *pn = a.normals + 3 * (size_t)g, *pa = a.ru + 3 * (size_t)g,
-                        *pb = a.rv + 3 * (size_t)g;
-            const float mx = __ldg(pm), my = __ldg(pm + 1), mz = __ldg(pm + 2);
-            nx = __ldg(pn); ny = __ldg(pn + 1); nz = __ldg(pn + 2);
-            ax = __ldg(pa); ay = __ldg(pa + 1); az = __ldg(pa + 2);
-            bx = __ldg(pb); by = __ldg(pb + 1); bz = __ldg(pb + 2);
-            op = __ldg(a.opacity + g);
+            // the surfel's packed record (re-packed from the saved inputs before this launch): two 32-byte loads
+            float4 q0, q1, q2, q3;
+            const SurfelRec *rec = p.recs + __ldg(p.inv_order + g);
+            ldg256(&rec->r0, q0, q1);
+            ldg256(&rec->r2, q2, q3);
+            const float mx = q0.x, my = q0.y, mz = q0.z;
+            nx = q1.x; ny = q1.y; nz = q1.z;
+            ax = q2.x; ay = q2.y; az = q2.z;
+            bx = q2.w; by = q3.x; bz = q3.y;
+            op = q3.z;
             relx = __fsub_rn(ro.ox, mx); rely = __fsub_rn(ro.oy, my); relz = __fsub_rn(ro.oz, mz);
             og = dot3_rn(nx, ny, nz, relx, rely, relz);
             dg = dot3_rn(nx, ny, nz, ro.dx, ro.dy, ro.dz);
@@ -454,6 +478,7 @@ __global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p
         const float dnx = m * gO[3] * w + dL_ddg * ro.dx + dL_dog * relx;
         const float dny = m * gO[4] * w + dL_ddg * ro.dy + dL_dog * rely;
         const float dnz = m * gO[5] * w + dL_ddg * ro.dz + dL_dog * relz;
+        if (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous round's rows have been read
         __syncwarp();
         {
             float4 *row = reinterpret_cast<float4 *>(rows + lane * BROW);
@@ -498,19 +523,35 @@ __global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p
                 if (mine_here) { if (j < 3) go[j] += tot; else gd[j - 3] += tot; }
             }
         }
+        if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy row writes -> async proxy
         __syncwarp();
-        // ---- per-surfel gradients: sixteen consecutive lanes add one 256-byte row with 16-byte reductions
-        const int n_here = min(32, total - base);
-        const int col = lane & 15;
-        for (int j = 0; j < n_here; j += 2) {
-            const int rowi = j + (lane >> 4);
-            const int g_r = __shfl_sync(FULL, g, rowi & 31);
-            if (rowi < n_here && col < 4 + nvec) {
-                const float4 v = *reinterpret_cast<const float4 *>(rows + rowi * BROW + 4 * col);
-                atomicAdd(reinterpret_cast<float4 *>(a.grad_fused + (size_t)g_r * IRGS_GRAD_STRIDE) + col, v);
+        // ---- per-surfel gradients
+        if (BULK) {
+            // one bulk reduction (TMA unit, UBLKRED.ADD.F32) per hit adds the whole row to the fused buffer.  ncu on the
+            // 16-byte vector reductions: the L1TEX data pipe spends one wavefront per LANE on a reduction however
+            // well the addresses coalesce (1.65 M wavefronts per SM and launch = hits x 16), which bounded the kernel.
+            if (act) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows + lane * BROW);
+                float *dst = a.grad_fused + (size_t)g * IRGS_GRAD_STRIDE;
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"((4 + nvec) * 16) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else {
+            // sixteen consecutive lanes add one 256-byte row with 16-byte reductions
+            const int n_here = min(32, total - base);
+            const int col = lane & 15;
+            for (int j = 0; j < n_here; j += 2) {
+                const int rowi = j + (lane >> 4);
+                const int g_r = __shfl_sync(FULL, g, rowi & 31);
+                if (rowi < n_here && col < 4 + nvec) {
+                    const float4 v = *reinterpret_cast<const float4 *>(rows + rowi * BROW + 4 * col);
+                    atomicAdd(reinterpret_cast<float4 *>(a.grad_fused + (size_t)g_r * IRGS_GRAD_STRIDE) + col, v);
+                }
             }
         }
     }
+    if (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until it has been read
     if (valid && cnt <= a.hit_cap) {  // rays with longer lists are written by the re-trace kernel
 #pragma unroll
         for (int j = 0; j < 3; ++j) { a.g_rays_o[3 * my_ray + j] = go[j]; a.g_rays_d[3 * my_ray + j] = gd[j]; }
@@ -687,6 +728,7 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
     p.nodes = h->qnodes;
     p.qframe = h->scene + 12;
     p.recs = h->recs;
+    p.inv_order = h->inv_order;
     p.counter = h->counter + h->slot;
     p.stats = h->stats;
     return p;
@@ -694,7 +736,8 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
 
 int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     const int n = (int)h->n;
-    pack_records_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->order, n, a.means, a.opacity, a.ru, a.rv, a.normals, h->recs);
+    pack_records_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->order, n, a.means, a.opacity, a.ru, a.rv, a.normals, a.alpha_min, h->recs,
+                                                         h->inv_order);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;
@@ -721,8 +764,13 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
             if (feat) trace_backward_replay_kernel<true><<<grid, TB, 0, s>>>(p);
             else trace_backward_replay_kernel<false><<<grid, TB, 0, s>>>(p);
         } else {
-            if (feat) trace_backward_flat_kernel<true><<<grid, TB, 0, s>>>(p);
-            else trace_backward_flat_kernel<false><<<grid, TB, 0, s>>>(p);
+            if (h->bwd_mode == 2) {   // 16-byte vector reductions instead of bulk reductions (comparison)
+                if (feat) trace_backward_flat_kernel<true, false><<<grid, TB, 0, s>>>(p);
+                else trace_backward_flat_kernel<false, false><<<grid, TB, 0, s>>>(p);
+            } else {
+                if (feat) trace_backward_flat_kernel<true, true><<<grid, TB, 0, s>>>(p);
+                else trace_backward_flat_kernel<false, true><<<grid, TB, 0, s>>>(p);
+            }
         }
         count_launch();
         IRGS_CHECK(cudaGetLastError());

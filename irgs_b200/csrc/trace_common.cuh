@@ -27,6 +27,7 @@ struct KParams {
     const QNode *nodes;
     const float *qframe;   // [6] quantisation frame: lo xyz, extent xyz
     const SurfelRec *recs;
+    const int *inv_order;   // surfel id -> leaf position
     unsigned long long *counter;
     unsigned long long *stats;
 };
@@ -157,26 +158,32 @@ __device__ __forceinline__ bool slab(const RayCtx &r, const uint4 w, float t_lo,
     return (int)w.w != IRGS_CHILD_NONE && tn <= tf;
 }
 
-// Plane hit of a packed record (already in registers).  Arithmetic order == eval_surfel() of
-// oracle/surfel_oracle.c (gaussiantrace_forward.cu:61-81).  Returns true for a compositing candidate.
-__device__ __forceinline__ bool leaf_eval(const RayCtx &r, const float4 r0, const float4 r1, const float4 r2,
-                                          const float4 r3, float alpha_min, int back_culling, float &t_out, int &g_out,
-                                          float &alpha_out) {
+// Plane hit of a packed record, in two stages so that the second half of the record is only fetched for pairs that pass
+// the first.  Arithmetic order == eval_surfel() of oracle/surfel_oracle.c (gaussiantrace_forward.cu:61-81).
+// Stage 1 (r0 = mu, support radius^2; r1 = normal, id): depth, range / facing tests, hit point relative to mu, and the
+// conservative early reject |pos|^2 > radius^2 (no alpha >= alpha_min is possible there; see pack_records_kernel).
+__device__ __forceinline__ bool leaf_stage1(const RayCtx &r, const float4 r0, const float4 r1, int back_culling,
+                                            float &t_out, int &g_out, float &px, float &py, float &pz) {
     float relx = __fsub_rn(r.ox, r0.x), rely = __fsub_rn(r.oy, r0.y), relz = __fsub_rn(r.oz, r0.z);
     float og = dot3_rn(r1.x, r1.y, r1.z, relx, rely, relz);
     float dg = dot3_rn(r1.x, r1.y, r1.z, r.dx, r.dy, r.dz);
     float dg2 = __fmul_rn(dg, dg);
     float den = fmaxf(1e-6f, dg2);
     float t = __fdiv_rn(__fmul_rn(-og, dg), den);
-    t_out = t; g_out = __float_as_int(r1.w); alpha_out = 0.f;
+    t_out = t; g_out = __float_as_int(r1.w);
+    px = __fmaf_rn(t, r.dx, relx); py = __fmaf_rn(t, r.dy, rely); pz = __fmaf_rn(t, r.dz, relz);
     if (!(dg2 >= 1e-6f)) return false;  // grazing pair: the clamped formula is no longer the geometric hit (see oracle)
     if (!(t > T_EPS && t < IRGS_T_SCENE_MAX)) return false;
     if (back_culling && !(-dg > 0.0f)) return false;
-    float px = __fmaf_rn(t, r.dx, relx), py = __fmaf_rn(t, r.dy, rely), pz = __fmaf_rn(t, r.dz, relz);
+    return !(__fmaf_rn(pz, pz, __fmaf_rn(py, py, __fmul_rn(px, px))) > r0.w);
+}
+// Stage 2 (r2 = ru, rv.x; r3 = rv.yz, opacity): the Gaussian response.  Returns true for a compositing candidate.
+__device__ __forceinline__ bool leaf_stage2(const float4 r2, const float4 r3, float px, float py, float pz, float alpha_min,
+                                            float &alpha_out) {
     float pu = dot3_rn(r2.x, r2.y, r2.z, px, py, pz);
     float pv = dot3_rn(r2.w, r3.x, r3.y, px, py, pz);
     float power = __fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv)));
-    float alpha = fminf(0.99f, __fmul_rn(r0.w, __expf(power)));
+    float alpha = fminf(0.99f, __fmul_rn(r3.z, __expf(power)));
     alpha_out = alpha;
     return alpha >= alpha_min;
 }
@@ -184,9 +191,12 @@ __device__ __forceinline__ bool leaf_eval(const RayCtx &r, const float4 r0, cons
 __device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
                                           int back_culling, float &t_out, int &g_out, float &alpha_out) {
     float4 q0, q1, q2, q3;
+    float px, py, pz;
     ldg256(&rec->r0, q0, q1);
+    alpha_out = 0.f;
+    if (!leaf_stage1(r, q0, q1, back_culling, t_out, g_out, px, py, pz)) return false;
     ldg256(&rec->r2, q2, q3);
-    return leaf_eval(r, q0, q1, q2, q3, alpha_min, back_culling, t_out, g_out, alpha_out);
+    return leaf_stage2(q2, q3, px, py, pz, alpha_min, alpha_out);
 }
 
 __device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }

@@ -45,6 +45,10 @@ constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #define IRGS_PQ 12
 #endif
 constexpr int PQ = IRGS_PQ;
+#ifndef IRGS_LEAF_2STAGE
+#define IRGS_LEAF_2STAGE 0
+#endif
+constexpr bool LEAF_2STAGE = IRGS_LEAF_2STAGE != 0;
 #ifndef IRGS_COMP_MIN
 #define IRGS_COMP_MIN 24
 #endif
@@ -188,10 +192,11 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 const int o_pn = __shfl_sync(FULL, pn, owner), o_cnt = __shfl_sync(FULL, cnt, owner);
                 float4 q0, q1, q2, q3;
                 q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                int leaf = 0;
                 if (has) {
-                    const int leaf = ~ws.pend[(o_pn - 1 - (idx - o_start)) * 32 + owner];   // popped from the top
-                    const float4 *src = reinterpret_cast<const float4 *>(p.recs + leaf);
-                    ldg256(src, q0, q1); ldg256(src + 2, q2, q3);
+                    leaf = ~ws.pend[(o_pn - 1 - (idx - o_start)) * 32 + owner];   // popped from the top
+                    ldg256(p.recs + leaf, q0, q1);
+                    if (!LEAF_2STAGE) ldg256(&p.recs[leaf].r2, q2, q3);
                     if (STATS) ++st_leaf;
                 }
                 RayCtx ro;
@@ -199,16 +204,22 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);
                 const float o_tlast = __shfl_sync(FULL, t_last, owner), o_thi = __shfl_sync(FULL, t_hi, owner);
                 const int o_glast = __shfl_sync(FULL, g_last, owner), o_ghi = __shfl_sync(FULL, g_hi, owner);
-                float t, alpha; int g;
-                const bool ok = has && leaf_eval(ro, q0, q1, q2, q3, alpha_min, back_culling, t, g, alpha) &&
-                                key_less(o_tlast, o_glast, t, g) && key_less(t, g, o_thi, o_ghi);
+                float t, alpha = 0.f, px, py, pz; int g;
+                bool ok = has && leaf_stage1(ro, q0, q1, back_culling, t, g, px, py, pz) &&
+                          key_less(o_tlast, o_glast, t, g) && key_less(t, g, o_thi, o_ghi);
+                if (ok) {
+                    // fetching the second half of the record only now saves L1TEX wavefronts but serialises two L2
+                    // latencies: measured 2 % slower than issuing both loads up front (profiles/r01_sweeps.txt)
+                    if (LEAF_2STAGE) ldg256(&p.recs[leaf].r2, q2, q3);
+                    ok = leaf_stage2(q2, q3, px, py, pz, alpha_min, alpha);
+                }
                 const unsigned acc = __ballot_sync(FULL, ok);
                 // the items of one owner are contiguous in the list: bits [lo, hi) of this round
                 if (ok) {
                     const int lo = max(o_start - base, 0), hi = min(o_start + o_m - base, 32);
                     const unsigned rmask = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
                     warp_cand[(size_t)owner * KB + o_cnt + __popc(acc & rmask & lt_mask)] =
-                        make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), 0u);
+                        make_uint4(__float_as_uint(t), (unsigned)g, __float_as_uint(alpha), (unsigned)leaf);
                 }
                 {
                     const int lo = min(max(start - base, 0), 32), hi = min(max(start + m - base, 0), 32);
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             __syncwarp();  // lane L's appended candidates are visible to the whole warp
             // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
             const uint4 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
-            float my_t = __uint_as_float(e.x), my_a = __uint_as_float(e.z); int my_g = (int)e.y;
+            float my_t = __uint_as_float(e.x), my_a = __uint_as_float(e.z); int my_g = (int)e.y, my_p = (int)e.w;
             int rank = 0;
             for (int j = 0; j < KB; ++j) {
                 const float tj = __shfl_sync(FULL, my_t, j);
@@ -241,9 +252,9 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             {
                 float *s_f = ws.scratch;
                 int *s_i = reinterpret_cast<int *>(ws.scratch);
-                s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a;
+                s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a; s_i[96 + rank] = my_p;
                 __syncwarp();
-                my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane];
+                my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; my_p = s_i[96 + lane];
                 __syncwarp();
             }
             // transmittance chain in the reference's sequential order
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const float t_end = __shfl_sync(FULL, my_t, keep - 1);
             const int g_end = __shfl_sync(FULL, my_g, keep - 1);
             if ((int)lane < keep)
-                warp_cand[(size_t)L * KB + lane] = make_uint4(__float_as_uint(my_t), (unsigned)my_g, __float_as_uint(my_a), 0u);
+                warp_cand[(size_t)L * KB + lane] = make_uint4(__float_as_uint(my_t), (unsigned)my_g, __float_as_uint(my_a), (unsigned)my_p);
             if ((int)lane == L) {
                 cnt = keep; t_hi = t_end; g_hi = g_end;
                 if (split) more = true;
@@ -324,10 +335,10 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const int seg_lo = act ? o_start2 : (int)lane;
             const int n_o = act ? o_c2 : 0;
             int k = (int)lane - seg_lo;
-            float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX;
+            float my_t = INFINITY, my_a = 0.f; int my_g = INT_MAX, my_p = 0;
             if (act) {
                 const uint4 e = __ldcg(&warp_cand[(size_t)owner * KB + k]);
-                my_t = __uint_as_float(e.x); my_g = (int)e.y; my_a = __uint_as_float(e.z);
+                my_t = __uint_as_float(e.x); my_g = (int)e.y; my_a = __uint_as_float(e.z); my_p = (int)e.w;
             }
             int rank = 0;
             for (int j = 0; j < maxn; ++j) {
@@ -339,9 +350,9 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             {
                 float *s_f = ws.scratch;
                 int *s_i = reinterpret_cast<int *>(ws.scratch);
-                if (act) { s_f[seg_lo + rank] = my_t; s_i[32 + seg_lo + rank] = my_g; s_f[64 + seg_lo + rank] = my_a; }
+                if (act) { s_f[seg_lo + rank] = my_t; s_i[32 + seg_lo + rank] = my_g; s_f[64 + seg_lo + rank] = my_a; s_i[96 + seg_lo + rank] = my_p; }
                 __syncwarp();
-                if (act) { my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; }
+                if (act) { my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; my_p = s_i[96 + lane]; }
                 __syncwarp();
             }
             // transmittance chain of every segment in the reference's sequential order (bit-identical termination decisions)
@@ -369,8 +380,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             if (mine) {
                 float Y[16];
                 sh_basis(a.deg, dxl, dyl, dzl, Y);
-                const float nx = __ldg(a.normals + 3 * (size_t)my_g), ny = __ldg(a.normals + 3 * (size_t)my_g + 1),
-                            nz = __ldg(a.normals + 3 * (size_t)my_g + 2);
+                const float4 rn = __ldg(&p.recs[my_p].r1);   // the surfel's normal, from its packed record
+                const float nx = rn.x, ny = rn.y, nz = rn.z;
                 const float dg = dot3_rn(nx, ny, nz, dxl, dyl, dzl);
                 const float m = (-dg > 0.f) ? 1.f : -1.f;
                 float c[3];
@@ -477,7 +488,7 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p;
-    p.a = a; p.nodes = h->qnodes; p.qframe = h->scene + 12; p.recs = h->recs; p.counter = h->counter + h->slot; p.stats = h->stats;
+    p.a = a; p.nodes = h->qnodes; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + h->slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
     if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31)) {

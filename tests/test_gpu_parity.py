@@ -110,6 +110,35 @@ def test_forward_matches_oracle(small_scene, kind, deg, back_culling, mode):
     assert np.abs(out["alpha"] - ref["alpha"]).max() < 5e-2
 
 
+def test_skewed_and_anisotropic_surfel_frames(small_scene):
+    """ru / rv as a caller may pass them: not orthogonal, not in the plane, anisotropy up to 100:1.  The analytic bounds
+    and the support-radius early reject must stay conservative: the hit lists equal the oracle's brute force."""
+    sc, inp = small_scene
+    inp = dict(inp)
+    g = torch.Generator().manual_seed(77)
+    n = inp["ru"].shape[0]
+    mix = 0.6 * (torch.rand(n, 1, generator=g) - 0.5)
+    ru = inp["ru"] + mix * inp["rv"] + 0.3 * torch.randn(n, 1, generator=g) * inp["normals"] * inp["ru"].norm(dim=1, keepdim=True)
+    rv = inp["rv"] * torch.exp(2.3 * (torch.rand(n, 1, generator=g) - 0.5) * 2)   # stretch rv by 0.1 .. 10
+    inp["ru"], inp["rv"] = ru.contiguous(), rv.contiguous()
+    o, d = _rays(inp, "secondary", seed=5)
+    S = _oracle_scene(inp)
+    ref = oracle.trace_forward(S, o, d, hit_cap=64)
+    tr = _tracer(_gpu(inp))
+    gi = _gpu(inp)
+    with torch.no_grad():
+        res = tr.trace_with_hits(o.to(DEV), d.to(DEV), gi["means3D"], gi["opacity"], gi["ru"], gi["rv"], gi["normals"],
+                                 gi["features"], gi["shs"], synth.ALPHA_MIN, hit_cap=64)
+    safe = _safe(ref)
+    assert safe.mean() > 0.9 and (ref["hit_count"] > 0).mean() > 0.2
+    hc, hits = res["hit_count"].cpu().numpy(), res["hits"].cpu().numpy()
+    assert np.array_equal(hc[safe], ref["hit_count"][safe])
+    ok = safe & (ref["hit_count"] <= 64)
+    assert np.array_equal(hits[ok], ref["hits"][ok])
+    for name in ("color", "normal", "feature", "depth", "alpha"):
+        assert np.abs(res[name].cpu().numpy() - ref[name])[safe].max() <= 1e-4, name
+
+
 def test_axis_aligned_and_nearly_axis_aligned_rays(small_scene):
     """Direction components that are exactly zero or tiny must neither break the slab test nor disable culling."""
     sc, inp = small_scene

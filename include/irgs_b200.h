@@ -131,6 +131,44 @@ int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int 
 int64_t irgs_launch_count(void);
 void irgs_reset_launch_count(void);
 
+/* ---- Fused incident-ray generation -------------------------------------------------------------
+ * Replaces the caller-side ray construction of /root/reference/gaussian_renderer/__init__.py:324-332,376
+ * (sample_incident_rays; `position.unsqueeze(1) + incident_dirs * light_t_min`) and utils/graphics_utils.py:19-47,133-165
+ * (fibonacci_sphere_sampling, rotation_between_z): the n_points * sample_num rays are generated inside the tracing
+ * kernels from one (position, normal, azimuth) triple per shading point instead of being read from a [P, S, 3] pair of
+ * arrays.  Ray index = point * sample_num + sample, outputs are laid out [P, S, ...].  azimuth[p] is the per-point
+ * `rand * 2 pi` of the reference's training mode; NULL = evaluation mode (no random rotation).  All device pointers. */
+typedef struct {
+    const float *position;   /* [P,3] shading points */
+    const float *normals;    /* [P,3] unit shading normals */
+    const float *azimuth;    /* [P] or NULL */
+    int64_t n_points;
+    int32_t sample_num;      /* S, pipe.diffuse_sample_num */
+    float t_min;             /* pipe.light_t_min */
+} irgs_incident_t;
+
+/* The generated rays themselves, [P,S,3] each (either output may be NULL): for shading code that needs the directions. */
+int irgs_incident_rays(const irgs_incident_t *gen, float *rays_o, float *rays_d, void *stream);
+
+/* irgs_trace_forward / irgs_trace_backward on generated rays.  The backward additionally returns dL/dposition [P,3] and
+ * dL/dR [P,9] (R = rotation_between_z(normal), row-major; zero on its constant -identity branch), reduced over the S samples
+ * of each point from the per-ray gradients, which are left in the two [P*S,3] scratch arrays. */
+int irgs_trace_forward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, int S, int K, int deg, const float *means,
+                                const float *opacity, const float *ru, const float *rv, const float *normals,
+                                const float *features, const float *shs, float *out_color, float *out_normal,
+                                float *out_feature, float *out_depth, float *out_alpha, int32_t *out_hit_count,
+                                int32_t *out_hits, int hit_cap, float alpha_min, float T_min, int back_culling,
+                                void *stream);
+int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, int S, int K, int deg, const float *means,
+                                 const float *opacity, const float *ru, const float *rv, const float *normals,
+                                 const float *features, const float *shs, const float *color, const float *normal,
+                                 const float *feature, const float *depth, const float *alpha, const int32_t *hit_count,
+                                 const int32_t *hits, int hit_cap, const float *gout_color, const float *gout_normal,
+                                 const float *gout_feature, const float *gout_depth, const float *gout_alpha,
+                                 float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_position,
+                                 float *grad_rotation, float *grad_fused, float *grad_features, float alpha_min, float T_min,
+                                 int back_culling, void *stream);
+
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
  * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.

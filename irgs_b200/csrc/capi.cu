@@ -196,12 +196,25 @@ int irgs_intersection_test(irgs_tracer_t *h, int64_t n_rays, const float *rays_o
     return launch_intersection_test(h, a, out, s);
 }
 
-int irgs_trace_forward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
-                       const float *rays_d, const float *means, const float *opacity, const float *ru,
-                       const float *rv, const float *normals, const float *features, const float *shs,
-                       float *out_color, float *out_normal, float *out_feature, float *out_depth, float *out_alpha,
-                       int32_t *out_hit_count, int32_t *out_hits, int hit_cap, float alpha_min, float T_min,
-                       int back_culling, void *stream) {
+static int validate_incident(const irgs_incident_t *gen) {
+    if (!gen) return fail("null incident-ray descriptor");
+    if (gen->n_points < 0) return fail("n_points < 0");
+    if (gen->sample_num < 1) return fail("sample_num must be positive");
+    if (gen->n_points > 0 && (!gen->position || !gen->normals)) return fail("position / normals must not be null");
+    return 0;
+}
+static void set_generator(TraceArgs &a, const irgs_incident_t *gen) {
+    if (!gen) return;
+    a.gen_pos = gen->position; a.gen_nrm = gen->normals; a.gen_azim = gen->azimuth;
+    a.gen_S = gen->sample_num; a.gen_tmin = gen->t_min;
+}
+
+static int trace_forward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int64_t n_rays, int S, int K, int deg,
+                              const float *rays_o, const float *rays_d, const float *means, const float *opacity,
+                              const float *ru, const float *rv, const float *normals, const float *features,
+                              const float *shs, float *out_color, float *out_normal, float *out_feature, float *out_depth,
+                              float *out_alpha, int32_t *out_hit_count, int32_t *out_hits, int hit_cap, float alpha_min,
+                              float T_min, int back_culling, void *stream) {
     if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
     if (n_rays == 0) return 0;
     if (out_hits && hit_cap == 0) out_hits = nullptr;
@@ -209,10 +222,72 @@ int irgs_trace_forward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, 
     cudaStream_t s = (cudaStream_t)stream;
     TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
                             alpha_min, T_min, back_culling);
+    set_generator(a, gen);
     a.color = out_color; a.normal = out_normal; a.feature = out_feature; a.depth = out_depth; a.alpha = out_alpha;
     a.hit_count = out_hit_count; a.hits = out_hits; a.hit_cap = hit_cap;
     if (launch_pack_records(h, a, s)) return 1;
     return launch_trace_forward(h, a, s);
+}
+
+int irgs_trace_forward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
+                       const float *rays_d, const float *means, const float *opacity, const float *ru,
+                       const float *rv, const float *normals, const float *features, const float *shs,
+                       float *out_color, float *out_normal, float *out_feature, float *out_depth, float *out_alpha,
+                       int32_t *out_hit_count, int32_t *out_hits, int hit_cap, float alpha_min, float T_min,
+                       int back_culling, void *stream) {
+    if (n_rays > 0 && (!rays_o || !rays_d)) return fail("rays_o / rays_d must not be null");
+    return trace_forward_impl(h, nullptr, n_rays, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
+                              out_color, out_normal, out_feature, out_depth, out_alpha, out_hit_count, out_hits, hit_cap,
+                              alpha_min, T_min, back_culling, stream);
+}
+
+int irgs_trace_forward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, int S, int K, int deg, const float *means,
+                                const float *opacity, const float *ru, const float *rv, const float *normals,
+                                const float *features, const float *shs, float *out_color, float *out_normal,
+                                float *out_feature, float *out_depth, float *out_alpha, int32_t *out_hit_count,
+                                int32_t *out_hits, int hit_cap, float alpha_min, float T_min, int back_culling,
+                                void *stream) {
+    if (validate_incident(gen)) return 1;
+    return trace_forward_impl(h, gen, gen->n_points * gen->sample_num, S, K, deg, nullptr, nullptr, means, opacity, ru, rv,
+                              normals, features, shs, out_color, out_normal, out_feature, out_depth, out_alpha,
+                              out_hit_count, out_hits, hit_cap, alpha_min, T_min, back_culling, stream);
+}
+
+int irgs_incident_rays(const irgs_incident_t *gen, float *rays_o, float *rays_d, void *stream) {
+    if (validate_incident(gen)) return 1;
+    return launch_incident_rays(gen->position, gen->normals, gen->azimuth, gen->n_points, gen->sample_num, gen->t_min, rays_o,
+                                rays_d, (cudaStream_t)stream);
+}
+
+static int trace_backward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int64_t n_rays, int S, int K, int deg,
+                               const float *rays_o, const float *rays_d, const float *means, const float *opacity,
+                               const float *ru, const float *rv, const float *normals, const float *features,
+                               const float *shs, const float *color, const float *normal, const float *feature,
+                               const float *depth, const float *alpha, const int32_t *hit_count, const int32_t *hits,
+                               int hit_cap, const float *gout_color, const float *gout_normal, const float *gout_feature,
+                               const float *gout_depth, const float *gout_alpha, float *grad_rays_o, float *grad_rays_d,
+                               float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
+                               void *stream) {
+    if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
+    if (n_rays == 0) return 0;
+    if (!grad_fused) return fail("grad_fused must not be null");
+    if (!grad_rays_o || !grad_rays_d) return fail("grad_rays_o / grad_rays_d must not be null");
+    if (S > 0 && !grad_features) return fail("grad_features must not be null when S > 0");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
+                            alpha_min, T_min, back_culling);
+    set_generator(a, gen);
+    a.color = const_cast<float *>(color); a.normal = const_cast<float *>(normal);
+    a.feature = const_cast<float *>(feature); a.depth = const_cast<float *>(depth); a.alpha = const_cast<float *>(alpha);
+    if (hits && hit_count && hit_cap > 0) {
+        a.hit_count = const_cast<int32_t *>(hit_count); a.hits = const_cast<int32_t *>(hits); a.hit_cap = hit_cap;
+    }
+    a.gC = gout_color; a.gN = gout_normal; a.gF = gout_feature; a.gD = gout_depth; a.gO = gout_alpha;
+    a.g_rays_o = grad_rays_o; a.g_rays_d = grad_rays_d; a.grad_fused = grad_fused; a.grad_features = grad_features;
+    // the records must be consistent with the arrays handed to this call
+    if (launch_pack_records(h, a, s)) return 1;
+    return launch_trace_backward(h, a, s);
 }
 
 int irgs_trace_backward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o,
@@ -224,24 +299,33 @@ int irgs_trace_backward(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg,
                         const float *gout_depth, const float *gout_alpha, float *grad_rays_o, float *grad_rays_d,
                         float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
                         void *stream) {
-    if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
-    if (n_rays == 0) return 0;
-    if (!grad_fused) return fail("grad_fused must not be null");
-    if (S > 0 && !grad_features) return fail("grad_features must not be null when S > 0");
+    if (n_rays > 0 && (!rays_o || !rays_d)) return fail("rays_o / rays_d must not be null");
+    return trace_backward_impl(h, nullptr, n_rays, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
+                               color, normal, feature, depth, alpha, hit_count, hits, hit_cap, gout_color, gout_normal,
+                               gout_feature, gout_depth, gout_alpha, grad_rays_o, grad_rays_d, grad_fused, grad_features,
+                               alpha_min, T_min, back_culling, stream);
+}
+
+int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, int S, int K, int deg, const float *means,
+                                 const float *opacity, const float *ru, const float *rv, const float *normals,
+                                 const float *features, const float *shs, const float *color, const float *normal,
+                                 const float *feature, const float *depth, const float *alpha, const int32_t *hit_count,
+                                 const int32_t *hits, int hit_cap, const float *gout_color, const float *gout_normal,
+                                 const float *gout_feature, const float *gout_depth, const float *gout_alpha,
+                                 float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_position,
+                                 float *grad_rotation, float *grad_fused, float *grad_features, float alpha_min, float T_min,
+                                 int back_culling, void *stream) {
+    if (validate_incident(gen)) return 1;
+    if (gen->n_points > 0 && (!grad_position || !grad_rotation)) return fail("grad_position / grad_rotation must not be null");
+    if (trace_backward_impl(h, gen, gen->n_points * gen->sample_num, S, K, deg, nullptr, nullptr, means, opacity, ru, rv,
+                            normals, features, shs, color, normal, feature, depth, alpha, hit_count, hits, hit_cap,
+                            gout_color, gout_normal, gout_feature, gout_depth, gout_alpha, scratch_grad_rays_o,
+                            scratch_grad_rays_d, grad_fused, grad_features, alpha_min, T_min, back_culling, stream))
+        return 1;
     DeviceGuard guard(h->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
-                            alpha_min, T_min, back_culling);
-    a.color = const_cast<float *>(color); a.normal = const_cast<float *>(normal);
-    a.feature = const_cast<float *>(feature); a.depth = const_cast<float *>(depth); a.alpha = const_cast<float *>(alpha);
-    if (hits && hit_count && hit_cap > 0) {
-        a.hit_count = const_cast<int32_t *>(hit_count); a.hits = const_cast<int32_t *>(hits); a.hit_cap = hit_cap;
-    }
-    a.gC = gout_color; a.gN = gout_normal; a.gF = gout_feature; a.gD = gout_depth; a.gO = gout_alpha;
-    a.g_rays_o = grad_rays_o; a.g_rays_d = grad_rays_d; a.grad_fused = grad_fused; a.grad_features = grad_features;
-    // the re-trace path needs records consistent with the arrays handed to this call
-    if (launch_pack_records(h, a, s)) return 1;
-    return launch_trace_backward(h, a, s);
+    return launch_incident_backward(gen->position, gen->normals, gen->azimuth, gen->n_points, gen->sample_num, gen->t_min,
+                                    scratch_grad_rays_o, scratch_grad_rays_d, grad_position, grad_rotation,
+                                    (cudaStream_t)stream);
 }
 
 int irgs_unpack_grads(const float *grad_fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,

@@ -124,6 +124,11 @@ struct TraceArgs {
     float *color, *normal, *feature, *depth, *alpha;
     int32_t *hit_count, *hits;
     int hit_cap;
+    // fused incident-ray generation: when gen_pos != nullptr the rays are not read from rays_o / rays_d
+    // but generated from (shading point, normal, azimuth) and the sample index: ray = point * gen_S + sample
+    const float *gen_pos, *gen_nrm, *gen_azim;   // [P,3], [P,3], [P] or nullptr (no random rotation)
+    int gen_S;
+    float gen_tmin;
     const int *ray_order;  // forward: optional processing order (coherence sort); results are still written per ray id
     // backward
     const float *gC, *gN, *gF, *gD, *gO;
@@ -135,6 +140,11 @@ int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s);
+int launch_incident_backward(const float *position, const float *normals, const float *azimuth, int64_t n_points,
+                             int sample_num, float t_min, const float *g_rays_o, const float *g_rays_d, float *grad_position,
+                             float *grad_rotation, cudaStream_t s);
+int launch_incident_rays(const float *position, const float *normals, const float *azimuth, int64_t n_points, int sample_num,
+                         float t_min, float *rays_o, float *rays_d, cudaStream_t s);
 int launch_unpack_grads(const float *fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,
                         float *gn, float *gsh, cudaStream_t s);
 

@@ -687,6 +687,69 @@ __global__ void __launch_bounds__(TB) intersection_test_kernel(const KParams p, 
     out[ray] = found ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------ incident rays
+// The generated rays written out (for callers that also shade with the directions, and for tests).
+__global__ void incident_rays_kernel(const float *__restrict__ position, const float *__restrict__ normals,
+                                     const float *__restrict__ azimuth, int64_t n_rays, int S, float t_min,
+                                     float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    TraceArgs a;
+    a.gen_pos = position; a.gen_nrm = normals; a.gen_azim = azimuth; a.gen_S = S; a.gen_tmin = t_min;
+    RayCtx r;
+    load_ray(a, ray, r);
+    if (rays_o) { rays_o[3 * ray] = r.ox; rays_o[3 * ray + 1] = r.oy; rays_o[3 * ray + 2] = r.oz; }
+    if (rays_d) { rays_d[3 * ray] = r.dx; rays_d[3 * ray + 1] = r.dy; rays_d[3 * ray + 2] = r.dz; }
+}
+
+// Chain rule from the per-ray gradients of the tracer back to the shading point: one warp per point.
+//   o = x + t_min d,  d = v / |v|,  v = R(n) zs   =>   dL/dx = sum_s g_o,   dL/dd = g_d + t_min g_o,
+//   dL/dv = (dL/dd - d (d . dL/dd)) / |v|,   dL/dR = sum_s dL/dv zs^T   (zero on the constant -identity branch).
+// dL/dn follows from dL/dR through rotation_between_z (9 numbers per point, done by the caller: irgs_b200/incident.py).
+__global__ void __launch_bounds__(128) incident_backward_kernel(const float *__restrict__ position,
+                                                                const float *__restrict__ normals,
+                                                                const float *__restrict__ azimuth, int64_t n_points, int S,
+                                                                float t_min, const float *__restrict__ g_rays_o,
+                                                                const float *__restrict__ g_rays_d,
+                                                                float *__restrict__ grad_position,
+                                                                float *__restrict__ grad_rotation) {
+    const int64_t pt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= n_points) return;
+    const float nx = __ldg(normals + 3 * pt), ny = __ldg(normals + 3 * pt + 1), nz = __ldg(normals + 3 * pt + 2);
+    const float az = azimuth ? __ldg(azimuth + pt) : 0.f;
+    float acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+    for (int s = lane; s < S; s += 32) {
+        const int64_t ray = pt * S + s;
+        const IncidentSample q = incident_sample(nx, ny, nz, s, S, azimuth != nullptr, az);
+        const float dx = __fdiv_rn(q.vx, q.len), dy = __fdiv_rn(q.vy, q.len), dz = __fdiv_rn(q.vz, q.len);
+        const float gox = g_rays_o[3 * ray], goy = g_rays_o[3 * ray + 1], goz = g_rays_o[3 * ray + 2];
+        const float gdx = g_rays_d[3 * ray] + t_min * gox, gdy = g_rays_d[3 * ray + 1] + t_min * goy,
+                    gdz = g_rays_d[3 * ray + 2] + t_min * goz;
+        acc[0] += gox; acc[1] += goy; acc[2] += goz;
+        if (q.rotated && q.len > 1e-12f) {
+            const float dd = dx * gdx + dy * gdy + dz * gdz;
+            const float gvx = (gdx - dx * dd) / q.len, gvy = (gdy - dy * dd) / q.len, gvz = (gdz - dz * dd) / q.len;
+            acc[3] += gvx * q.zx; acc[4] += gvx * q.zy; acc[5] += gvx * q.zz;
+            acc[6] += gvy * q.zx; acc[7] += gvy * q.zy; acc[8] += gvy * q.zz;
+            acc[9] += gvz * q.zx; acc[10] += gvz * q.zy; acc[11] += gvz * q.zz;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) grad_position[3 * pt + j] = acc[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) grad_rotation[9 * pt + j] = acc[3 + j];
+    }
+}
+
 __global__ void unpack_grads_kernel(const float *__restrict__ fused, int64_t n, int K, float *__restrict__ gm,
                                     float *__restrict__ go, float *__restrict__ gru, float *__restrict__ grv,
                                     float *__restrict__ gn, float *__restrict__ gsh) {
@@ -785,6 +848,28 @@ int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, c
     KParams p = make_params(h, a);
     const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
     intersection_test_kernel<<<grid, TB, 0, s>>>(p, out);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_incident_rays(const float *position, const float *normals, const float *azimuth, int64_t n_points, int sample_num,
+                         float t_min, float *rays_o, float *rays_d, cudaStream_t s) {
+    const int64_t n_rays = n_points * sample_num;
+    if (n_rays <= 0) return 0;
+    incident_rays_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, s>>>(position, normals, azimuth, n_rays, sample_num, t_min,
+                                                                          rays_o, rays_d);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_incident_backward(const float *position, const float *normals, const float *azimuth, int64_t n_points,
+                             int sample_num, float t_min, const float *g_rays_o, const float *g_rays_d, float *grad_position,
+                             float *grad_rotation, cudaStream_t s) {
+    if (n_points <= 0) return 0;
+    incident_backward_kernel<<<(unsigned)((n_points * 32 + 127) / 128), 128, 0, s>>>(
+        position, normals, azimuth, n_points, sample_num, t_min, g_rays_o, g_rays_d, grad_position, grad_rotation);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;

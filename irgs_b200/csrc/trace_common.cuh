@@ -201,7 +201,54 @@ __device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__re
 
 __device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }
 
+// ------------------------------------------------------------------------------------------------ incident rays
+// Sample `s` of the Fibonacci hemisphere around `normal`, the reference's fibonacci_sphere_sampling +
+// rotation_between_z (utils/graphics_utils.py:19-47,133-165) with its order of float32 operations (restated and pinned
+// in oracle/incident.py); azim is the per-point `rand * 2 pi` of the training mode (0 and has_azim = false otherwise).
+// zs = the sample around +z, v = R zs (not yet normalised), len = max(|v|, 1e-12); rotated = false on the -identity branch.
+struct IncidentSample { float zx, zy, zz, vx, vy, vz, len; bool rotated; };
+__device__ __forceinline__ IncidentSample incident_sample(float nx, float ny, float nz, int s, int S, bool has_azim, float azim) {
+    IncidentSample o;
+    const float idx = (float)s;
+    const float z = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, idx), (float)(2 * S - 1))), 0.17364817766693033f);
+    const float rad = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(z, z)));
+    float theta = __fmul_rn(2.399963229728653f, idx);
+    if (has_azim) theta = __fadd_rn(azim, theta);
+    o.zy = __fmul_rn(cosf(theta), rad);
+    o.zx = __fmul_rn(sinf(theta), rad);
+    o.zz = z;
+    o.rotated = __fadd_rn(nz, 1.0f) > 0.0f;
+    if (o.rotated) {
+        const float v1 = -ny, v2 = nx;
+        const float c = fmaxf(__fadd_rn(nz, 1.0f), 1e-7f);
+        const float v11 = __fmul_rn(v1, v1), v22 = __fmul_rn(v2, v2), v12 = __fmul_rn(v1, v2);
+        const float r00 = __fadd_rn(1.0f, __fdiv_rn(-v22, c)), r01 = __fdiv_rn(v12, c), r02 = v2;
+        const float r10 = r01, r11 = __fadd_rn(1.0f, __fdiv_rn(-v11, c)), r12 = -v1;
+        const float r20 = -v2, r21 = v1, r22 = __fadd_rn(1.0f, __fdiv_rn(__fsub_rn(-v22, v11), c));
+        o.vx = __fmaf_rn(r02, o.zz, __fmaf_rn(r01, o.zy, __fmul_rn(r00, o.zx)));
+        o.vy = __fmaf_rn(r12, o.zz, __fmaf_rn(r11, o.zy, __fmul_rn(r10, o.zx)));
+        o.vz = __fmaf_rn(r22, o.zz, __fmaf_rn(r21, o.zy, __fmul_rn(r20, o.zx)));
+    } else {   // graphics_utils.py:163-164: -identity
+        o.vx = -o.zx; o.vy = -o.zy; o.vz = -o.zz;
+    }
+    const float len = __fsqrt_rn(__fmaf_rn(o.vz, o.vz, __fmaf_rn(o.vy, o.vy, __fmul_rn(o.vx, o.vx))));
+    o.len = fmaxf(len, 1e-12f);   // F.normalize: v / max(|v|, eps)
+    return o;
+}
+
 __device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
+    if (a.gen_pos != nullptr) {
+        // gaussian_renderer/__init__.py:376: origin = position + dir * light_t_min, generated instead of read
+        const int64_t pt = ray / a.gen_S;
+        const int s = (int)(ray - pt * a.gen_S);
+        const IncidentSample q = incident_sample(__ldg(a.gen_nrm + 3 * pt), __ldg(a.gen_nrm + 3 * pt + 1), __ldg(a.gen_nrm + 3 * pt + 2),
+                                                 s, a.gen_S, a.gen_azim != nullptr, a.gen_azim ? __ldg(a.gen_azim + pt) : 0.f);
+        r.dx = __fdiv_rn(q.vx, q.len); r.dy = __fdiv_rn(q.vy, q.len); r.dz = __fdiv_rn(q.vz, q.len);
+        r.ox = __fadd_rn(__ldg(a.gen_pos + 3 * pt), __fmul_rn(r.dx, a.gen_tmin));
+        r.oy = __fadd_rn(__ldg(a.gen_pos + 3 * pt + 1), __fmul_rn(r.dy, a.gen_tmin));
+        r.oz = __fadd_rn(__ldg(a.gen_pos + 3 * pt + 2), __fmul_rn(r.dz, a.gen_tmin));
+        return;
+    }
     r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
     r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
 }

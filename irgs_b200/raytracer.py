@@ -248,6 +248,30 @@ class GaussianTracer:
         return (color.view(*prefix, 3), normal.view(*prefix, 3), feature.view(*prefix, S), depth.view(*prefix),
                 alpha.view(*prefix))
 
+    def trace_incident(self, position, normals_pt, sample_num, means3D, opacity, ru, rv, normals, features, shs, alpha_min,
+                       azimuth=None, t_min=0.05, deg=3, back_culling=False):
+        """`sample_incident_rays` + `trace` of the reference's rendering_equation in one call (gaussian_renderer/
+        __init__.py:324-332,376): the P x sample_num incident rays are generated inside the kernels (irgs_b200/incident.py).
+        position, normals_pt [P,3]; azimuth [P] = the training mode's `rand * 2 pi` (None: evaluation mode).
+        Returns (color [P,S,3], normal [P,S,3], feature [P,S,F], depth [P,S], alpha [P,S]); differentiable w.r.t.
+        position, normals_pt and the surfel parameters."""
+        from . import incident
+        dummy = position.new_zeros(1, 3)
+        _, _, means3D, opacity, ru, rv, normals, features, shs = self._prep(dummy, dummy, means3D, opacity, ru, rv, normals,
+                                                                            features, shs)
+        position, normals_pt = position.contiguous(), normals_pt.contiguous()
+        azimuth = azimuth.contiguous().view(-1) if azimuth is not None else None
+        incident._check(position, normals_pt, azimuth, self.impl.device)
+        P, S, F = position.shape[0], int(sample_num), features.shape[-1]
+        if P == 0:
+            z = lambda *s: torch.zeros(*s, device=position.device, dtype=torch.float32)  # noqa: E731
+            return z(0, S, 3), z(0, S, 3), z(0, S, F), z(0, S), z(0, S)
+        color, normal, feature, depth, alpha, hit_count = incident._IncidentTrace.apply(
+            self, position, normals_pt, azimuth, S, float(t_min), means3D, opacity, ru, rv, normals, features, shs,
+            float(alpha_min), int(deg), bool(back_culling))
+        self.last_hit_count = hit_count.view(P, S)
+        return color.view(P, S, 3), normal.view(P, S, 3), feature.view(P, S, F), depth.view(P, S), alpha.view(P, S)
+
     @torch.no_grad()
     def trace_with_hits(self, rays_o, rays_d, means3D, opacity, ru, rv, normals, features, shs, alpha_min, deg=3,
                         back_culling=False, hit_cap=None):

@@ -151,3 +151,28 @@ def test_oracle_matches_reference_golden(path):
     """Pin the oracle against outputs of the UNMODIFIED reference tracer (OptiX) recorded on a B200."""
     from tests.golden_util import check_against_golden, oracle_runner
     check_against_golden(path, oracle_runner)
+
+
+def test_incident_sampling_oracle_matches_reference_golden():
+    """oracle/incident.py (numpy restatement of utils/graphics_utils.py:19-47,133-165) against vectors recorded from the
+    unmodified reference functions (oracle/gen_golden_incident.py)."""
+    import os
+    from oracle import incident
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_incident.npz"))
+    n = g["normals"]
+    assert np.array_equal(incident.rotation_between_z(n), g["rotation"])
+    for S in (24, 256):
+        assert np.abs(incident.incident_dirs(n, S) - g[f"dirs_eval_{S}"]).max() <= 3e-7
+        assert np.abs(incident.incident_dirs(n, S, g[f"azimuth_{S}"]) - g[f"dirs_train_{S}"]).max() <= 3e-7
+        assert float(g[f"area_{S}"]) == np.float32(2 * np.pi)
+    o, d = incident.incident_rays(np.ones((n.shape[0], 3), np.float32), n, 24, None, 0.05)
+    assert np.abs(o - (1 + 0.05 * d)).max() <= 1e-7 and o.shape == (n.shape[0], 24, 3)
+
+
+def test_torch_rotation_between_z_matches_reference_golden():
+    import os
+    import torch
+    from irgs_b200.incident import rotation_between_z
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_incident.npz"))
+    R = rotation_between_z(torch.from_numpy(g["normals"])).numpy()
+    assert np.abs(R - g["rotation"]).max() <= 1e-7

@@ -39,6 +39,7 @@ def parse():
     p.add_argument("--img", type=int, default=IMG)
     p.add_argument("--spp", type=int, default=SPP)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     p.add_argument("--ref-rays", type=int, default=1 << 22, help="rays per step of the reference arm's bounded sample")
@@ -116,6 +117,7 @@ def build_workload(args, device, rank, world, tracer_factory):
         dirs = _rotate_about(dirs, nrm[b:e], azim[b:e] * 2 * np.pi)
         rays_d[b * args.spp:e * args.spp] = dirs.reshape(-1, 3)
         rays_o[b * args.spp:e * args.spp] = (pts[b:e, None] + dirs * synth.LIGHT_T_MIN).reshape(-1, 3)
+    build_workload.points = (pts, nrm, azim.view(-1) * 2 * np.pi)   # per-pixel inputs of the fused-generation measurement
     return sc, inp, tracer, rays_o, rays_d
 
 
@@ -254,6 +256,41 @@ def run_ours(args):
     fwd_rays = sum(n for _, _, n in fwd_events)
     checksum = float(grads["shs"].abs().sum().item())
 
+    # the same step with the rays generated inside the kernels (trace_incident) from the per-pixel
+    # (position, normal, azimuth) instead of being read from the two [R,3] arrays; the reference's own sampling scheme,
+    # i.e. the same distribution of rays as the materialised ones (not the identical rays)
+    fused_gen = None
+    if not args.no_fused:
+        pts, nrm, azim = build_workload.points
+        pts_leaf, nrm_leaf = pts.clone().requires_grad_(True), nrm.clone().requires_grad_(True)
+        pchunk = max(1, chunk // args.spp)   # chunk is a multiple of spp for the C3 shapes
+        gout_f = [g.view(chunk // args.spp, args.spp, *g.shape[1:]) if g.numel() else g for g in gout]
+
+        def fused_step():
+            for b in range(0, pts.shape[0], pchunk):
+                e = min(b + pchunk, pts.shape[0])
+                outs = tracer.trace_incident(pts_leaf[b:e], nrm_leaf[b:e], args.spp, leaf["means3D"], leaf["opacity"], leaf["ru"],
+                                             leaf["rv"], leaf["normals"], None, leaf["shs"], synth.ALPHA_MIN, azimuth=azim[b:e],
+                                             t_min=synth.LIGHT_T_MIN)
+                torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]],
+                                        [gout_f[0][:e - b], gout_f[1][:e - b], gout_f[3][:e - b], gout_f[4][:e - b]])
+            pts_leaf.grad = None; nrm_leaf.grad = None
+            return tracer.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape))
+
+        for _ in range(min(args.warmup, 2)):
+            fused_step()
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fg = fused_step()
+        f1.record()
+        sync_all()
+        fms = parallel.max_over_ranks(f0.elapsed_time(f1), device) / args.steps
+        fused_gen = {"value": n_total / (fms * 1e-3), "unit": "rays/s", "ms_per_step": fms,
+                     "api": "GaussianTracer.trace_incident (irgs_trace_forward_incident / irgs_trace_backward_incident)",
+                     "input_bytes_per_step": int(pts.shape[0] * 28), "grad_checksum": float(fg["shs"].abs().sum().item())}
+
     # end to end through the C ABI on HOST buffers: rays pinned on the host, copied in per chunk inside the timed region;
     # the step's result (fused per-surfel gradients after the all-reduce) is read back to the host
     e2e = None
@@ -315,7 +352,7 @@ def run_ours(args):
                    "parallelism": f"ray-sharded dp{world} (32-pixel blocks round-robin), surfels+BVH replicated, one all-reduce of N x 64 floats",
                    "l2": "inputs (3.9 GB of rays per step) exceed L2; no flush needed",
                    "shading_points": "all 640k bundles start on the surface (missed pixels re-assigned to hit pixels)"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
+        "e2e": e2e, "fused_generation": fused_gen, "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
         "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_ray * chunk,

@@ -151,8 +151,8 @@ typedef struct {
 int irgs_incident_rays(const irgs_incident_t *gen, float *rays_o, float *rays_d, void *stream);
 
 /* irgs_trace_forward / irgs_trace_backward on generated rays.  The backward additionally returns dL/dposition [P,3] and
- * dL/dR [P,9] (R = rotation_between_z(normal), row-major; zero on its constant -identity branch), reduced over the S samples
- * of each point from the per-ray gradients, which are left in the two [P*S,3] scratch arrays. */
+ * dL/dnormal [P,3] of the shading points (through rotation_between_z; zero on its constant -identity branch), reduced over the
+ * S samples of each point from the per-ray gradients, which are left in the two [P*S,3] scratch arrays. */
 int irgs_trace_forward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, int S, int K, int deg, const float *means,
                                 const float *opacity, const float *ru, const float *rv, const float *normals,
                                 const float *features, const float *shs, float *out_color, float *out_normal,
@@ -166,7 +166,7 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
                                  const int32_t *hits, int hit_cap, const float *gout_color, const float *gout_normal,
                                  const float *gout_feature, const float *gout_depth, const float *gout_alpha,
                                  float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_position,
-                                 float *grad_rotation, float *grad_fused, float *grad_features, float alpha_min, float T_min,
+                                 float *grad_normal_pt, float *grad_fused, float *grad_features, float alpha_min, float T_min,
                                  int back_culling, void *stream);
 
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in

@@ -313,10 +313,10 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
                                  const int32_t *hits, int hit_cap, const float *gout_color, const float *gout_normal,
                                  const float *gout_feature, const float *gout_depth, const float *gout_alpha,
                                  float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_position,
-                                 float *grad_rotation, float *grad_fused, float *grad_features, float alpha_min, float T_min,
+                                 float *grad_normal_pt, float *grad_fused, float *grad_features, float alpha_min, float T_min,
                                  int back_culling, void *stream) {
     if (validate_incident(gen)) return 1;
-    if (gen->n_points > 0 && (!grad_position || !grad_rotation)) return fail("grad_position / grad_rotation must not be null");
+    if (gen->n_points > 0 && (!grad_position || !grad_normal_pt)) return fail("grad_position / grad_normal_pt must not be null");
     if (trace_backward_impl(h, gen, gen->n_points * gen->sample_num, S, K, deg, nullptr, nullptr, means, opacity, ru, rv,
                             normals, features, shs, color, normal, feature, depth, alpha, hit_count, hits, hit_cap,
                             gout_color, gout_normal, gout_feature, gout_depth, gout_alpha, scratch_grad_rays_o,
@@ -324,7 +324,7 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
         return 1;
     DeviceGuard guard(h->device);
     return launch_incident_backward(gen->position, gen->normals, gen->azimuth, gen->n_points, gen->sample_num, gen->t_min,
-                                    scratch_grad_rays_o, scratch_grad_rays_d, grad_position, grad_rotation,
+                                    scratch_grad_rays_o, scratch_grad_rays_d, grad_position, grad_normal_pt,
                                     (cudaStream_t)stream);
 }
 

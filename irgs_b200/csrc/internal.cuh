@@ -142,7 +142,7 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s);
 int launch_incident_backward(const float *position, const float *normals, const float *azimuth, int64_t n_points,
                              int sample_num, float t_min, const float *g_rays_o, const float *g_rays_d, float *grad_position,
-                             float *grad_rotation, cudaStream_t s);
+                             float *grad_normal_pt, cudaStream_t s);
 int launch_incident_rays(const float *position, const float *normals, const float *azimuth, int64_t n_points, int sample_num,
                          float t_min, float *rays_o, float *rays_d, cudaStream_t s);
 int launch_unpack_grads(const float *fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,

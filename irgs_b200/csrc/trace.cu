@@ -705,14 +705,15 @@ __global__ void incident_rays_kernel(const float *__restrict__ position, const f
 // Chain rule from the per-ray gradients of the tracer back to the shading point: one warp per point.
 //   o = x + t_min d,  d = v / |v|,  v = R(n) zs   =>   dL/dx = sum_s g_o,   dL/dd = g_d + t_min g_o,
 //   dL/dv = (dL/dd - d (d . dL/dd)) / |v|,   dL/dR = sum_s dL/dv zs^T   (zero on the constant -identity branch).
-// dL/dn follows from dL/dR through rotation_between_z (9 numbers per point, done by the caller: irgs_b200/incident.py).
+// dL/dn follows from dL/dR through rotation_between_z (graphics_utils.py:133-165): with v1 = -n.y, v2 = n.x, c = max(n.z + 1, 1e-7),
+//   R = [[1 - v2^2/c, v1 v2/c, v2], [v1 v2/c, 1 - v1^2/c, -v1], [-v2, v1, 1 - (v1^2 + v2^2)/c]].
 __global__ void __launch_bounds__(128) incident_backward_kernel(const float *__restrict__ position,
                                                                 const float *__restrict__ normals,
                                                                 const float *__restrict__ azimuth, int64_t n_points, int S,
                                                                 float t_min, const float *__restrict__ g_rays_o,
                                                                 const float *__restrict__ g_rays_d,
                                                                 float *__restrict__ grad_position,
-                                                                float *__restrict__ grad_rotation) {
+                                                                float *__restrict__ grad_normal) {
     const int64_t pt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (pt >= n_points) return;
@@ -745,8 +746,14 @@ __global__ void __launch_bounds__(128) incident_backward_kernel(const float *__r
     if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) grad_position[3 * pt + j] = acc[j];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) grad_rotation[9 * pt + j] = acc[3 + j];
+        const float *G = acc + 3;   // dL/dR row-major
+        const float v1 = -ny, v2 = nx, c = fmaxf(nz + 1.0f, 1e-7f);
+        const float gv1 = (G[1] + G[3]) * v2 / c - (G[4] + G[8]) * 2.0f * v1 / c - G[5] + G[7];
+        const float gv2 = -(G[0] + G[8]) * 2.0f * v2 / c + (G[1] + G[3]) * v1 / c + G[2] - G[6];
+        const float gc = (G[0] * v2 * v2 - (G[1] + G[3]) * v1 * v2 + G[4] * v1 * v1 + G[8] * (v1 * v1 + v2 * v2)) / (c * c);
+        grad_normal[3 * pt] = gv2;
+        grad_normal[3 * pt + 1] = -gv1;
+        grad_normal[3 * pt + 2] = (nz + 1.0f > 1e-7f) ? gc : 0.0f;
     }
 }
 
@@ -866,10 +873,10 @@ int launch_incident_rays(const float *position, const float *normals, const floa
 
 int launch_incident_backward(const float *position, const float *normals, const float *azimuth, int64_t n_points,
                              int sample_num, float t_min, const float *g_rays_o, const float *g_rays_d, float *grad_position,
-                             float *grad_rotation, cudaStream_t s) {
+                             float *grad_normal, cudaStream_t s) {
     if (n_points <= 0) return 0;
     incident_backward_kernel<<<(unsigned)((n_points * 32 + 127) / 128), 128, 0, s>>>(
-        position, normals, azimuth, n_points, sample_num, t_min, g_rays_o, g_rays_d, grad_position, grad_rotation);
+        position, normals, azimuth, n_points, sample_num, t_min, g_rays_o, g_rays_d, grad_position, grad_normal);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;

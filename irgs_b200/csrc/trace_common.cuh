@@ -214,8 +214,10 @@ __device__ __forceinline__ IncidentSample incident_sample(float nx, float ny, fl
     const float rad = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(z, z)));
     float theta = __fmul_rn(2.399963229728653f, idx);
     if (has_azim) theta = __fadd_rn(azim, theta);
-    o.zy = __fmul_rn(cosf(theta), rad);
-    o.zx = __fmul_rn(sinf(theta), rad);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    o.zy = __fmul_rn(cs, rad);
+    o.zx = __fmul_rn(sn, rad);
     o.zz = z;
     o.rotated = __fadd_rn(nz, 1.0f) > 0.0f;
     if (o.rotated) {

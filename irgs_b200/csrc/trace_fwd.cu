@@ -45,6 +45,10 @@ constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #define IRGS_PQ 12
 #endif
 constexpr int PQ = IRGS_PQ;
+#ifndef IRGS_FETCH_MIN
+#define IRGS_FETCH_MIN 4
+#endif
+constexpr int FETCH_MIN = IRGS_FETCH_MIN;   // idle lanes a refill waits for (1: refill at once)
 #ifndef IRGS_LEAF_2STAGE
 #define IRGS_LEAF_2STAGE 0
 #endif
@@ -100,8 +104,11 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
+        // (a refill serves whatever lanes are idle: it waits until FETCH_MIN of them are, or until the walk is short of lanes)
         const unsigned need = __ballot_sync(FULL, phase == PH_FETCH);
-        if (need != 0u && !pool_empty) {
+        const bool refill = __popc(need) >= FETCH_MIN ||
+                            __popc(__ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE)) < MIN_ACTIVE;
+        if (need != 0u && !pool_empty && refill) {
             const int leader = __ffs(need) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));

@@ -33,7 +33,8 @@ def _desc(position, normals, azimuth, sample_num, t_min):
 
 
 def rotation_between_z(vec):
-    """utils/graphics_utils.py:133-165 restated in torch (differentiable): carries dL/dR [P,3,3] back to the normals."""
+    """utils/graphics_utils.py:133-165 restated in torch (differentiable); the tracer's own backward does this chain in its
+    kernel, this copy is for shading code and for the tests."""
     v1, v2 = -vec[..., 1], vec[..., 0]
     c = (vec[..., 2] + 1).clamp_min(1e-7)
     zero = torch.zeros_like(v1)
@@ -121,7 +122,7 @@ class _IncidentTrace(torch.autograd.Function):
         scratch_o = torch.empty(B, 3, device=dev)
         scratch_d = torch.empty(B, 3, device=dev)
         g_pos = torch.empty(P, 3, device=dev)
-        g_rot = torch.empty(P, 3, 3, device=dev)
+        g_nrm = torch.empty(P, 3, device=dev)
         deferred = tracer.accumulate_grads
         if deferred:
             fused, gfeat = tracer._grad_buffers(N, S)
@@ -135,12 +136,7 @@ class _IncidentTrace(torch.autograd.Function):
             impl.h, ctypes.byref(desc), S, K, deg, _ptr(means3D), _ptr(opacity), _ptr(ru), _ptr(rv), _ptr(normals),
             _ptr(features), _ptr(shs), _ptr(color), _ptr(normal), _ptr(feature), _ptr(depth), _ptr(alpha),
             _ptr(hit_count) if have_list else null, _ptr(hits) if have_list else null, ctx.cap, *[_ptr(t) for t in g],
-            _ptr(scratch_o), _ptr(scratch_d), _ptr(g_pos), _ptr(g_rot), _ptr(fused), _ptr(gfeat), alpha_min, T_min,
+            _ptr(scratch_o), _ptr(scratch_d), _ptr(g_pos), _ptr(g_nrm), _ptr(fused), _ptr(gfeat), alpha_min, T_min,
             int(back_culling), _stream(dev)))
-        g_nrm = None
-        if ctx.needs_input_grad[2]:
-            with torch.enable_grad():   # 9 numbers per point: dL/dR -> dL/dnormal through rotation_between_z
-                n = normals_pt.detach().requires_grad_(True)
-                (g_nrm,) = torch.autograd.grad(rotation_between_z(n), n, g_rot)
         surf = (None,) * 7 if deferred else tracer._unpack(fused, gfeat, opacity.shape, K)
         return (None, g_pos, g_nrm, None, None, None) + surf + (None, None, None)

@@ -336,7 +336,7 @@ def run_ours(args):
     traffic = None
     try:  # DRAM bytes of one forward launch from the committed ncu --set full capture (profiles/), same launch size
         tj = json.load(open(os.path.join(ROOT, "profiles", "fwd_kernel_traffic.json")))
-        if tj.get("rays_per_launch") == chunk:
+        if tj.get("rays_per_launch") == chunk and args.surfels == N_SURFELS and args.spp == SPP:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass

@@ -65,10 +65,11 @@ struct irgs_tracer {
     float *ploc_box = nullptr;          // [2][cap] PLOC cluster bounds, 8 floats each
     int *ploc_nn = nullptr, *ploc_counts = nullptr, *ploc_offs = nullptr, *ploc_totals = nullptr;
     int builder = 0;                    // 0: PLOC over the Morton order (default), 1: Karras LBVH
+    int tree_depth = 0;                 // depth of the PLOC tree of the last build (0: Karras tree, depth <= 62 by construction)
     int *radix_hist = nullptr;          // [256 * n_tiles]
     int64_t radix_tiles_cap = 0;
     float *scene = nullptr;             // [24]: 0-5 centroid bounds as ordered ints, 6-11 root bound (floats),
-                                        //       12-14 quantisation frame lo, 15-17 cell size
+                                        //       12-14 quantisation frame lo, 15-17 cell size, 18-23 bounds of the surfel boxes (ordered ints)
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
     int *inv_order = nullptr;           // [n] surfel id -> leaf position (written with the records)
     unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot

@@ -26,7 +26,9 @@ __global__ void scene_init_kernel(int *scene_i) {
     int t = threadIdx.x;
     if (t < 3) scene_i[t] = INT_MAX;
     else if (t < 6) scene_i[t] = INT_MIN;
-    else if (t < 16) scene_i[t] = 0;
+    else if (t < 18) scene_i[t] = 0;
+    else if (t < 21) scene_i[t] = INT_MAX;   // 18-23: bounds of the surfel boxes themselves (ordered ints)
+    else if (t < 24) scene_i[t] = INT_MIN;
 }
 
 __device__ __forceinline__ void scene_reduce(int *scene_i, bool valid, const float lo[3], const float hi[3]) {
@@ -37,9 +39,14 @@ __device__ __forceinline__ void scene_reduce(int *scene_i, bool valid, const flo
         int vmin = valid ? f2ord(c) : INT_MAX, vmax = valid ? f2ord(c) : INT_MIN;
         vmin = __reduce_min_sync(0xffffffffu, vmin);
         vmax = __reduce_max_sync(0xffffffffu, vmax);
+        int bmin = valid ? f2ord(lo[k]) : INT_MAX, bmax = valid ? f2ord(hi[k]) : INT_MIN;
+        bmin = __reduce_min_sync(0xffffffffu, bmin);
+        bmax = __reduce_max_sync(0xffffffffu, bmax);
         if ((threadIdx.x & 31) == 0) {
             if (vmin != INT_MAX) atomicMin(&scene_i[k], vmin);
             if (vmax != INT_MIN) atomicMax(&scene_i[3 + k], vmax);
+            if (bmin != INT_MAX) atomicMin(&scene_i[18 + k], bmin);
+            if (bmax != INT_MIN) atomicMax(&scene_i[21 + k], bmax);
         }
     }
 }
@@ -506,6 +513,20 @@ __global__ void __launch_bounds__(PLOC_SB) ploc_scatter_kernel(const int *__rest
     }
 }
 
+// Depth of the deepest leaf (the ray walk keeps one stack entry per level at most: STACK = 64 entries).
+__global__ void tree_depth_kernel(const int *__restrict__ leaf_parent, const int *__restrict__ node_parent, int n,
+                                  int *__restrict__ max_depth) {
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    int depth = 0;
+    if (leaf < n) {
+        int p = leaf_parent[leaf];
+        depth = 1;
+        while ((p = node_parent[p >> 1]) >= 0) ++depth;
+    }
+    depth = __reduce_max_sync(0xffffffffu, depth);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_depth, depth);
+}
+
 int ploc_build(irgs_tracer *h, cudaStream_t s) {
     const int n = (int)h->n;
     int *cid[2] = {h->ploc_cid, h->ploc_cid + h->cap};
@@ -531,6 +552,14 @@ int ploc_build(irgs_tracer *h, cudaStream_t s) {
         cur ^= 1;
     }
     if (free_hi != 0) { set_error("PLOC node count mismatch"); return 1; }
+    // clustering gives no depth guarantee (the Karras tree over 30 + 32 key bits does): measure it
+    IRGS_CHECK(cudaMemsetAsync(h->ploc_totals, 0, sizeof(int), s));
+    tree_depth_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->leaf_parent, h->node_parent, n, h->ploc_totals);
+    count_launch();
+    int depth = 0;
+    IRGS_CHECK(cudaMemcpyAsync(&depth, h->ploc_totals, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IRGS_CHECK(cudaStreamSynchronize(s));
+    h->tree_depth = depth;
     return 0;
 }
 
@@ -562,12 +591,14 @@ __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restr
     if (leaf >= n) return;
     // absolute pad: a few float ulps of the scene scale, so that neither the rounding of the fma slab test nor that
     // of the plane-hit arithmetic (trace_common.cuh leaf_test) can make the walk reject a surfel the hit test accepts;
-    // relative pad covers the proxy's 0.999993 in-radius
+    // relative pad covers the proxy's 0.999993 in-radius.  The scale is ISOTROPIC -- the largest extent / coordinate of
+    // the surfel boxes over all three axes: a flat scene (all surfels in one axis-aligned plane) is looked at from
+    // distances given by its other two axes, and the rounding of a ray's plane crossings scales with those.
     float scale = 1e-3f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float clo = ord2f(scene_i[k]), chi = ord2f(scene_i[3 + k]);
-        if (clo <= chi) scale = fmaxf(scale, fmaxf(chi - clo, fmaxf(fabsf(clo), fabsf(chi))));
+        float blo = ord2f(scene_i[18 + k]), bhi = ord2f(scene_i[21 + k]);
+        if (blo <= bhi) scale = fmaxf(scale, fmaxf(bhi - blo, fmaxf(fabsf(blo), fabsf(bhi))));
     }
     const float pad_abs = 8e-6f * scale;
     const float *bx = boxes + 6 * (size_t)order[leaf];
@@ -618,8 +649,11 @@ __global__ void refit_kernel(const float *__restrict__ boxes, const int *__restr
 __global__ void quant_frame_kernel(float *scene) {
     const int k = threadIdx.x;
     if (k < 3) {
-        const float lo = scene[6 + k], hi = scene[9 + k];
-        const float ext = (hi >= lo) ? (hi - lo) : 0.f;
+        // one cell size for all three axes (the largest root extent / 65520): the two-cell outward shift of every plane
+        // is then a pad in SPACE that does not vanish along an axis in which the scene happens to be thin
+        float ext = 0.f;
+        for (int j = 0; j < 3; ++j) ext = fmaxf(ext, (scene[9 + j] >= scene[6 + j]) ? (scene[9 + j] - scene[6 + j]) : 0.f);
+        const float lo = scene[6 + k];
         const float cell = fmaxf(ext / 65520.0f, 1e-30f);
         scene[12 + k] = lo - 4.0f * cell;
         scene[15 + k] = cell;
@@ -717,9 +751,11 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
         count_launch();
         if (radix_sort_pairs(h->codes, h->codes_alt, h->order, h->order_alt, n, 4, h->radix_hist, s)) return 1;
         int n_int = n > 1 ? n - 1 : 1;
+        h->tree_depth = 0;
         if (h->builder == 0 && n > 2) {
             if (ploc_build(h, s)) return 1;
-        } else {
+        }
+        if (h->builder != 0 || n <= 2 || h->tree_depth > 60) {   // a degenerate clustering falls back to the bounded-depth tree
             hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
             count_launch();
         }

@@ -278,10 +278,13 @@ __global__ void __launch_bounds__(TB) trace_backward_replay_kernel(const KParams
 //     cache lines per hit instead of 16 scattered requests.
 // ncu on the thread-per-ray replay (profiles/r01_bwd_replay_regions.txt): 7.96 of 32 lanes active, L1TEX 85 % busy
 // with the scattered reductions.
-constexpr int BROW = 76;   // floats per shared-memory row: 64 gradient floats + 6 ray-gradient terms, 76 % 32 == 12 (conflict-free float4 stores)
+#ifndef IRGS_BWD_BLOCKS
+#define IRGS_BWD_BLOCKS 4
+#endif
+constexpr int BROW = 68;   // floats per shared-memory row: 64 gradient floats + pad, 68 % 32 == 4 (conflict-free float4 stores)
 
 template <bool FEAT, bool BULK>
-__global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p) {
+__global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kernel(const KParams p) {
     __shared__ __align__(16) float s_rows[TB / 32][32 * BROW];
     const TraceArgs &a = p.a;
     const unsigned FULL = 0xffffffffu;
@@ -530,12 +533,14 @@ __global__ void __launch_bounds__(TB) trace_backward_flat_kernel(const KParams p
             // one bulk reduction (TMA unit, UBLKRED.ADD.F32) per hit adds the whole row to the fused buffer.  ncu on the
             // 16-byte vector reductions: the L1TEX data pipe spends one wavefront per LANE on a reduction however
             // well the addresses coalesce (1.65 M wavefronts per SM and launch = hits x 16), which bounded the kernel.
+#ifndef IRGS_DEBUG_SKIP_REDUCE   // timing experiment only: how much of the kernel is the reduction traffic
             if (act) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows + lane * BROW);
                 float *dst = a.grad_fused + (size_t)g * IRGS_GRAD_STRIDE;
                 asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                              :: "l"(dst), "r"(src), "r"((4 + nvec) * 16) : "memory");
             }
+#endif
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         } else {
             // sixteen consecutive lanes add one 256-byte row with 16-byte reductions

@@ -338,6 +338,37 @@ def test_ploc_and_karras_trees_give_bit_identical_results_and_ploc_visits_fewer_
     assert stats[0][0] < 0.85 * stats[1][0], stats                 # PLOC: clearly fewer node visits
 
 
+def test_degenerate_clustering_falls_back_to_the_bounded_depth_tree():
+    """300 concentric, coplanar, ever larger surfels.  (1) Locally-ordered clustering merges one pair per iteration and
+    would produce a chain 300 levels deep (the ray walk's stack holds 64): the build must notice and use the Karras
+    tree.  (2) The scene is flat in z while the rays come from 2-6 units away, with up to 174 hits per ray at depths a
+    few float ulps apart: the pads that keep the box walk consistent with the plane-hit arithmetic must follow the
+    scene's LARGEST extent, not the per-axis one (a per-axis pad lost one hit at a pass boundary on 10 % of these rays).
+    Results must equal the oracle's brute force."""
+    n = 300
+    g = torch.Generator().manual_seed(5)
+    means = torch.zeros(n, 3) + 1e-4 * torch.randn(n, 3, generator=g)
+    scale = 0.01 * 1.03 ** torch.arange(n, dtype=torch.float32)
+    nrm = torch.tensor([0.0, 0.0, 1.0]).expand(n, 3).contiguous()
+    ru = torch.tensor([1.0, 0.0, 0.0]).expand(n, 3) / scale[:, None]
+    rv = torch.tensor([0.0, 1.0, 0.0]).expand(n, 3) / scale[:, None]
+    inp = dict(means3D=means, opacity=torch.full((n, 1), 0.02), ru=ru.contiguous(), rv=rv.contiguous(), normals=nrm,
+               features=torch.zeros(n, 0), shs=torch.randn(n, 16, 3, generator=g) * 0.2)
+    o = torch.tensor([[0.3, 0.1, 2.0], [5.0, 0.0, 3.0], [-0.02, 0.01, 1.0]]).repeat(20, 1) + 0.05 * torch.randn(60, 3, generator=g)
+    d = -o / o.norm(dim=1, keepdim=True)
+    ref = oracle.trace_forward(_oracle_scene(inp), o, d, hit_cap=64)
+    assert ref["hit_count"].max() > 32
+    tr = _tracer(_gpu(inp))
+    gi = _gpu(inp)
+    with torch.no_grad():
+        res = tr.trace_with_hits(o.to(DEV), d.to(DEV), gi["means3D"], gi["opacity"], gi["ru"], gi["rv"], gi["normals"],
+                                 gi["features"], gi["shs"], synth.ALPHA_MIN, hit_cap=64)
+    safe = _safe(ref)
+    assert np.array_equal(res["hit_count"].cpu().numpy()[safe], ref["hit_count"][safe])
+    for name in ("color", "depth", "alpha"):
+        assert np.abs(res[name].cpu().numpy() - ref[name])[safe].max() <= 1e-4, name
+
+
 def test_proxy_build_and_surfel_build_give_identical_results(small_scene):
     sc, inp = small_scene
     g = _gpu(inp)

@@ -91,7 +91,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
+    cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->qnodes4); cudaFree(h->even); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
     cudaFree(h->ploc_cid); cudaFree(h->ploc_box); cudaFree(h->ploc_nn); cudaFree(h->ploc_counts); cudaFree(h->ploc_offs); cudaFree(h->ploc_totals);
     cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->inv_order); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);

@@ -697,6 +697,52 @@ __global__ void quantize_nodes_kernel(const Node *__restrict__ nodes, int n_int,
     qnodes[i].r = out[1];
 }
 
+// Step 7: 4-wide traversal nodes (QNode4 in internal.cuh).  Topology part (build only): depth parity of every binary node.
+__global__ void depth_parity_kernel(const int *__restrict__ node_parent, int n_int, int *__restrict__ even) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_int) return;
+    int depth = 0, p = node_parent[i];
+    while (p >= 0) { ++depth; p = node_parent[p >> 1]; }
+    even[i] = (depth & 1) ? 0 : 1;
+}
+
+__device__ __forceinline__ uint4 quant_child(const float *b, int ref, const float *scene) {
+    if (b[0] >= IRGS_EMPTY_FAR) return make_uint4(0u, 0u, 0u, (unsigned)IRGS_CHILD_NONE);
+    unsigned q[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        q[k] = quant_lo(b[k], scene[12 + k], scene[15 + k]);
+        q[3 + k] = quant_hi(b[3 + k], scene[12 + k], scene[15 + k]);
+    }
+    return make_uint4(q[0] | (q[1] << 16), q[2] | (q[3] << 16), q[4] | (q[5] << 16), (unsigned)ref);
+}
+
+// Bounds part (every build and refit): one thread per even-depth binary node gathers its (up to four) grandchildren.
+__global__ void quantize_wide_kernel(const Node *__restrict__ nodes, const int *__restrict__ even, int n_int,
+                                     const float *__restrict__ scene, QNode4 *__restrict__ wide) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_int || !even[i]) return;
+    const float *f = reinterpret_cast<const float *>(nodes + i);
+    const int4 d = nodes[i].d;
+    uint4 out[4];
+    int m = 0;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int c = side == 0 ? d.x : d.y;
+        if (c < 0 || f[6 * side] >= IRGS_EMPTY_FAR) {
+            out[m++] = quant_child(f + 6 * side, c, scene);       // a leaf (or an empty slot) stays one slot
+        } else {
+            const float *g = reinterpret_cast<const float *>(nodes + c);
+            const int4 dc = nodes[c].d;
+            out[m++] = quant_child(g, dc.x, scene);
+            out[m++] = quant_child(g + 6, dc.y, scene);
+        }
+    }
+    for (; m < 4; ++m) out[m] = make_uint4(0u, 0u, 0u, (unsigned)IRGS_CHILD_NONE);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wide[i].c[k] = out[k];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 template <typename T>
 static bool realloc_dev(T *&p, size_t count) {
@@ -708,7 +754,8 @@ static bool realloc_dev(T *&p, size_t count) {
 int lbvh_reserve(irgs_tracer *h, int64_t n) {
     if (n <= h->cap) return 0;
     int64_t c = n;
-    if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->qnodes, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
+    if (!realloc_dev(h->nodes, (size_t)c) || !realloc_dev(h->qnodes, (size_t)c) || !realloc_dev(h->qnodes4, (size_t)c) ||
+        !realloc_dev(h->even, (size_t)c) || !realloc_dev(h->boxes, (size_t)c * 6) || !realloc_dev(h->codes, (size_t)c) ||
         !realloc_dev(h->codes_alt, (size_t)c) || !realloc_dev(h->order, (size_t)c) || !realloc_dev(h->order_alt, (size_t)c) ||
         !realloc_dev(h->leaf_parent, (size_t)c) || !realloc_dev(h->node_parent, (size_t)c) ||
         !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c) || !realloc_dev(h->inv_order, (size_t)c) || !realloc_dev(h->ploc_cid, (size_t)c * 2) ||
@@ -759,6 +806,8 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
             hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
             count_launch();
         }
+        depth_parity_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->node_parent, n_int, h->even);
+        count_launch();
     }
     IRGS_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(int) * (size_t)n, s));
     refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, scene_i, h->nodes,
@@ -766,7 +815,8 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
     const int n_internal = n > 1 ? n - 1 : 1;
     quant_frame_kernel<<<1, 32, 0, s>>>(h->scene);
     quantize_nodes_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, n_internal, h->scene, h->qnodes);
-    count_launch(3);
+    quantize_wide_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, h->even, n_internal, h->scene, h->qnodes4);
+    count_launch(4);
     IRGS_CHECK(cudaGetLastError());
     h->built = true;
     return 0;

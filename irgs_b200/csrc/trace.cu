@@ -801,6 +801,7 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
     KParams p;
     p.a = a;
     p.nodes = h->qnodes;
+    p.nodes4 = h->qnodes4;
     p.qframe = h->scene + 12;
     p.recs = h->recs;
     p.inv_order = h->inv_order;

@@ -9,7 +9,7 @@ namespace irgs {
 
 constexpr int TB = 128;     // threads per block
 constexpr int KBUF = 16;    // k-buffer depth (MAX_BUFFER_SIZE, auxiliary.h:10)
-constexpr int STACK = 64;   // traversal stack entries (LBVH depth <= 30 code bits + 32 index bits)
+constexpr int STACK = 96;   // traversal stack entries: the 4-wide walk stacks up to 3 per level, 31 levels at most (binary depth <= 62)
 constexpr float T_EPS = 1.1920929e-07f;  // FLT_EPSILON tmin, gaussiantrace_forward.cu:38
 constexpr int NFMAX = IRGS_MAX_FEATURES;
 
@@ -25,6 +25,7 @@ __device__ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442
 struct KParams {
     TraceArgs a;
     const QNode *nodes;
+    const QNode4 *nodes4;  // forward walk
     const float *qframe;   // [6] quantisation frame: lo xyz, extent xyz
     const SurfelRec *recs;
     const int *inv_order;   // surfel id -> leaf position

@@ -5,9 +5,10 @@
 //
 // Every lane owns one ray and runs a small state machine
 //     FETCH -> TRAV -> COMP -> (TRAV for another pass | FETCH)          TRAV -> FULL -> TRAV
-//   TRAV  near-first stack walk of the LBVH in two alternating sub-phases.  NODE: two 16-byte loads fetch a 32-byte
-//         quantised node (both children's bounds, 16 bits per coordinate, conservative), two slab tests; children that are leaves are not tested on the spot but
-//         pushed on a small per-lane queue of pending leaves (shared memory), internal children are walked / stacked.
+//   TRAV  near-first stack walk of the BVH in two alternating sub-phases.  NODE: two 256-bit loads fetch a 64-byte
+//         4-wide quantised node (a binary node folded with its two children: up to four grandchildren, 16 bits per
+//         plane, conservative), four slab tests; children that are leaves are not tested on the spot but pushed on a
+//         small per-lane queue of pending leaves (shared memory), internal children are walked / stacked.
 //         LEAF: all lanes that have pending leaves fetch one 64-byte surfel record each and run the plane / alpha test
 //         together.  Postponing the leaves is what keeps both sub-phases wide: with node and leaf work interleaved per
 //         iteration, ncu showed the leaf code (27 % of all issued instructions) running at 3.4 of 32 lanes.
@@ -42,7 +43,7 @@ constexpr int SSTK = 32;           // traversal stack entries kept in shared mem
 #endif
 constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #ifndef IRGS_PQ
-#define IRGS_PQ 12
+#define IRGS_PQ 16
 #endif
 constexpr int PQ = IRGS_PQ;
 #ifndef IRGS_FETCH_MIN
@@ -133,31 +134,32 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         // ------------------------------------------------------------------ BVH walk, NODE sub-phase
         const int thr = pool_empty ? 1 : MIN_ACTIVE;
         unsigned walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
-        // (a node visit can queue two leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
-        while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 2)) {
+        // (a node visit can queue four leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
+        while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 4)) {
             if (phase == PH_TRAV && cur != CUR_NONE) {
-                uint4 wl, wr;
-                ldg256(&p.nodes[cur], wl, wr);
+                // one 4-wide node: two 256-bit loads from one 64-byte line, four slab tests
+                uint4 c[4];
+                ldg256(&p.nodes4[cur].c[0], c[0], c[1]);
+                ldg256(&p.nodes4[cur].c[2], c[2], c[3]);
                 if (STATS) ++st_nodes;
-                float tnL, tnR;
-                const bool hL = slab(r, wl, t_lo, t_hi, tnL);
-                const bool hR = slab(r, wr, t_lo, t_hi, tnR);
-                const int cl = (int)wl.w, cr = (int)wr.w;
-                const bool rightNear = hR && (!hL || tnR < tnL);
-                const int c_near = rightNear ? cr : cl, c_far = rightNear ? cl : cr;
-                const bool h_near = rightNear ? hR : hL, h_far = rightNear ? hL : hR;
                 int next = CUR_NONE;
-                if (h_near) {
-                    if (c_near < 0) { pend[pn * 32] = c_near; ++pn; }
-                    else next = c_near;
-                }
-                if (h_far) {
-                    if (c_far < 0) { pend[pn * 32] = c_far; ++pn; }
-                    else if (next == CUR_NONE) next = c_far;
-                    else {
-                        if (sp < SSTK) stk[sp * 32] = c_far;
-                        else if (sp < STACK) stack_spill[sp - SSTK] = c_far;
-                        if (sp < STACK) ++sp;
+                float t_next = INFINITY;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float tn;
+                    if (slab(r, c[k], t_lo, t_hi, tn)) {
+                        const int ref = (int)c[k].w;
+                        if (ref < 0) { pend[pn * 32] = ref; ++pn; }          // leaf: queued for the LEAF sub-phase
+                        else {
+                            // the nearest internal child is walked next, the others are stacked
+                            int push = ref;
+                            if (tn < t_next) { push = next; next = ref; t_next = tn; }
+                            if (push != CUR_NONE) {
+                                if (sp < SSTK) stk[sp * 32] = push;
+                                else if (sp < STACK) stack_spill[sp - SSTK] = push;
+                                if (sp < STACK) ++sp;
+                            }
+                        }
                     }
                 }
                 if (next == CUR_NONE && sp > 0) { --sp; next = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; }
@@ -495,7 +497,7 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p;
-    p.a = a; p.nodes = h->qnodes; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + h->slot; p.stats = h->stats;
+    p.a = a; p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + h->slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
     if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31)) {

@@ -172,6 +172,8 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
  * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.
+ * "slot": 0 (default) or 1 -- calls issued on two different streams at the same time must use different slots (each slot has
+ * its own persistent-kernel work counter and candidate scratch).
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
  * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);

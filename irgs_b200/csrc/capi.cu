@@ -402,7 +402,7 @@ static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, i
             a.g_rays_o = d_go; a.g_rays_d = d_gd; a.grad_fused = grad_fused; a.grad_features = grad_features;
             rc = launch_trace_backward(h, a, s);
         }
-        h->slot = 0;
+        h->slot = h->slot_default;
         if (rc) return 1;
         if (out_color_host) IRGS_CHECK(cudaMemcpyAsync(out_color_host + 3 * done, d_col, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
         if (out_normal_host) IRGS_CHECK(cudaMemcpyAsync(out_normal_host + 3 * done, d_nrm, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
@@ -451,6 +451,11 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
     if (!h || !name) return fail("null argument");
     if (strcmp(name, "sort_rays_min") == 0) {
         h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
+        return 0;
+    }
+    if (strcmp(name, "slot") == 0) {   // which of the two work-counter / scratch sets the following device-path calls use
+        h->slot_default = value == 1 ? 1 : 0;
+        h->slot = h->slot_default;
         return 0;
     }
     if (strcmp(name, "builder") == 0) {   // takes effect at the next build_bvh / build_from_surfels

@@ -86,6 +86,7 @@ struct irgs_tracer {
     int *inv_order = nullptr;           // [n] surfel id -> leaf position (written with the records)
     unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
     int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)
+    int slot_default = 0;                   // device path: set with irgs_set_option("slot"), one per concurrently used stream
     uint4 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t, id, alpha, -)
     int64_t cand_threads = 0;               // threads one slot has room for
     // ray-coherence sort scratch, per stream slot

@@ -141,6 +141,7 @@ class GaussianTracer:
         self.hit_cap = hit_cap
         self.last_hit_count = None
         self.accumulate_grads = False
+        self._side_streams = None
         self._fused = None
         self._gfeat = None
         self._n_proxy = None
@@ -295,6 +296,34 @@ class GaussianTracer:
                 self.transmittance_min, int(back_culling), _stream(dev)))
         return out
 
+    def run_chunks(self, n_items, per_chunk, body, streams=None):
+        """Chunk loop of the reference's renderer (gaussian_renderer/__init__.py:319-322) with consecutive chunks
+        alternating between two CUDA streams: `body(begin, end)` is called for every chunk inside the stream context of
+        its turn, with the tracer switched to that stream's slot (own work counter + candidate scratch), so that the
+        drain of one chunk's persistent kernels overlaps the next chunk (+5 % on the C3 step).  `body` may call
+        trace / trace_incident and run their backward.  Returns after everything has joined the current stream again.
+        Pass the same `streams` list on every call to reuse them."""
+        dev = self.impl.device
+        if streams is None:
+            if self._side_streams is None:
+                self._side_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+            streams = self._side_streams
+        if not 1 <= len(streams) <= 2:
+            raise ValueError("one or two streams")
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+        try:
+            for i, b in enumerate(range(0, n_items, per_chunk)):
+                k = i % len(streams)
+                self.set_option("slot", k)
+                with torch.cuda.stream(streams[k]):
+                    body(b, min(b + per_chunk, n_items))
+        finally:
+            self.set_option("slot", 0)
+            for st in streams:
+                cur.wait_stream(st)
+
     def set_option(self, name, value):
         """Tuning knobs of the native tracer (never change results), e.g. set_option("sort_rays_min", 0)."""
         _lib.check(self.impl.lib.irgs_set_option(self.impl.h, name.encode(), int(value)))
@@ -331,10 +360,15 @@ class GaussianTracer:
 
     def _grad_buffers(self, n, S):
         dev = self.impl.device
+        fresh = False
         if self._fused is None or self._fused.shape[0] != n:
             self._fused = torch.zeros(n, GRAD_STRIDE, device=dev, dtype=torch.float32)
+            fresh = True
         if self._gfeat is None or self._gfeat.shape != (n, S):
             self._gfeat = torch.zeros(n, S, device=dev, dtype=torch.float32)
+            fresh = True
+        if fresh:   # (once) the zero fill must be complete before a backward on ANOTHER stream may add to the buffers
+            torch.cuda.current_stream(dev).synchronize()
         return self._fused, self._gfeat
 
     def flush_grads(self, K=16, opacity_shape=None, all_reduce=True, group=None):

@@ -552,6 +552,40 @@ def test_deferred_gradient_accumulation_equals_sum_of_calls(small_scene):
 
 
 # ---------------------------------------------------------------------------------------------- parameter-level API
+def test_chunks_on_two_streams_equal_one_call(small_scene):
+    """run_chunks: consecutive chunks on two streams / two tracer slots give the outputs of one big call bit for bit and
+    the same accumulated gradients (float reductions: order noise only)."""
+    sc, inp = small_scene
+    o, d = _rays(inp, "secondary")
+    o, d = o.to(DEV), d.to(DEV)
+    R = o.shape[0]
+    gout = {k: v.to(DEV) for k, v in _gout(R, inp["features"].shape[1]).items()}
+    names = ("color", "normal", "feature", "depth", "alpha")
+    res = []
+    for chunked in (False, True):
+        tr = _tracer(_gpu(inp))
+        tr.accumulate_grads = True
+        leaf = {k: inp[k].to(DEV).clone().requires_grad_(True) for k in KEYS}
+        parts = []
+
+        def body(b, e):
+            outs = tr.trace(o[b:e], d[b:e], *[leaf[k] for k in KEYS], synth.ALPHA_MIN)
+            torch.autograd.backward(list(outs), [gout[n][b:e] for n in names])
+            parts.append([t.detach() for t in outs])     # (tensors of different streams: only combined after the join)
+        if chunked:
+            tr.run_chunks(R, 333, body)
+        else:
+            body(0, R)
+        torch.cuda.synchronize()
+        outs_all = [torch.cat([p[j] for p in parts]) for j in range(5)]
+        res.append((outs_all, tr.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape))))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for k in res[0][1]:
+        a, b = res[0][1][k], res[1][1][k]
+        assert (a - b).abs().max() <= 2e-4 * (a.abs().max() + 1e-30), k
+
+
 def test_trace_from_surfel_parameters_gradients_reach_scales_and_rotations(small_scene):
     """irgs_b200.surfels.SurfelScene: means / scales / rotations / opacities in, gradients back to all of them;
     checked against the float64 autograd twin fed through the same (torch) glue."""

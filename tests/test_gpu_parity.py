@@ -476,6 +476,43 @@ def test_api_shapes_and_edge_cases(small_scene):
     tr.trace(o2, d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], None, g["shs"], synth.ALPHA_MIN)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 17])
+@pytest.mark.parametrize("builder", [0, 1])
+def test_tiny_scenes_and_invisible_surfels(small_scene, n, builder):
+    """1 ... 17 surfels (degenerate wide nodes: root with one or two leaves, missing grandchildren) and scenes in which
+    a third of the surfels are invisible (opacity below alpha_min => empty bounds): forward and backward against the oracle."""
+    from irgs_b200.raytracer import GaussianTracer
+    sc, inp = small_scene
+    sub = {k: v[:n].clone().contiguous() for k, v in inp.items()}
+    if n >= 3:
+        sub["opacity"][::3] = 0.5 * synth.ALPHA_MIN
+    g = _gpu(sub)
+    tr = GaussianTracer(transmittance_min=synth.T_MIN)
+    tr.set_option("builder", builder)
+    tr.build_from_surfels(g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], synth.ALPHA_MIN)
+    gen = torch.Generator().manual_seed(n)
+    o = sub["means3D"].repeat(24, 1) + 0.3 * sub["normals"].repeat(24, 1) + 0.02 * torch.randn(24 * n, 3, generator=gen)
+    tgt = sub["means3D"].repeat(24, 1) + 0.01 * torch.randn(24 * n, 3, generator=gen)
+    d = torch.nn.functional.normalize(tgt - o, dim=-1)
+    S = _oracle_scene(sub)
+    ref = oracle.trace_forward(S, o, d)
+    safe = torch.from_numpy(_safe(ref))
+    gout = _gout(o.shape[0], S.S)
+    gout = {k: v * (safe[:, None] if v.dim() == 2 else safe) for k, v in gout.items()}
+    rb = oracle.trace_backward(S, o, d, ref, {k: v.numpy() for k, v in gout.items()})
+    fwd, grads = _cuda_fwd_bwd(tr, sub, o, d, gout)
+    sf = safe.numpy()
+    assert (ref["hit_count"] > 0).any()
+    assert np.array_equal(tr.last_hit_count.cpu().numpy()[sf], ref["hit_count"][sf])
+    for name in ("color", "normal", "feature", "depth", "alpha"):
+        assert np.abs(fwd[name] - ref[name])[sf].max() <= 1e-4, name
+    for k, rk in dict(means3D="means", opacity="opacity", ru="ru", rv="rv", normals="normals", shs="shs").items():
+        a, b = grads[k].reshape(rb[rk].shape), rb[rk]
+        assert np.abs(a - b).max() <= 2e-3 * (np.abs(b).max() + 1e-30) + 1e-7, k
+    if n >= 3:   # invisible surfels receive no gradient at all
+        assert not grads["shs"][::3].any() and not grads["means3D"][::3].any()
+
+
 def test_api_errors(small_scene):
     sc, inp = small_scene
     g = _gpu(inp)

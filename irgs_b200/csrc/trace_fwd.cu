@@ -142,24 +142,31 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 ldg256(&p.nodes4[cur].c[0], c[0], c[1]);
                 ldg256(&p.nodes4[cur].c[2], c[2], c[3]);
                 if (STATS) ++st_nodes;
-                int next = CUR_NONE;
-                float t_next = INFINITY;
+                // four slab tests; leaves are queued for the LEAF sub-phase, the nearest internal child is walked next and
+                // the other internal children are stacked (written with short predicated bodies: the lanes of a warp
+                // rarely agree on which children they hit)
+                float tk[4];
+                bool inner[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float tn;
-                    if (slab(r, c[k], t_lo, t_hi, tn)) {
-                        const int ref = (int)c[k].w;
-                        if (ref < 0) { pend[pn * 32] = ref; ++pn; }          // leaf: queued for the LEAF sub-phase
-                        else {
-                            // the nearest internal child is walked next, the others are stacked
-                            int push = ref;
-                            if (tn < t_next) { push = next; next = ref; t_next = tn; }
-                            if (push != CUR_NONE) {
-                                if (sp < SSTK) stk[sp * 32] = push;
-                                else if (sp < STACK) stack_spill[sp - SSTK] = push;
-                                if (sp < STACK) ++sp;
-                            }
-                        }
+                    const bool hit = slab(r, c[k], t_lo, t_hi, tn);
+                    const int ref = (int)c[k].w;
+                    if (hit && ref < 0) { pend[pn * 32] = ref; ++pn; }
+                    inner[k] = hit && ref >= 0;
+                    tk[k] = inner[k] ? tn : INFINITY;
+                }
+                const float tmin = fminf(fminf(tk[0], tk[1]), fminf(tk[2], tk[3]));
+                int next = CUR_NONE;
+                bool taken = false;   // exactly one child with the smallest entry distance is walked next
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool nearest = inner[k] && !taken && tk[k] == tmin;
+                    if (nearest) { next = (int)c[k].w; taken = true; }
+                    else if (inner[k]) {
+                        if (sp < SSTK) stk[sp * 32] = (int)c[k].w;
+                        else if (sp < STACK) stack_spill[sp - SSTK] = (int)c[k].w;
+                        if (sp < STACK) ++sp;
                     }
                 }
                 if (next == CUR_NONE && sp > 0) { --sp; next = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; }

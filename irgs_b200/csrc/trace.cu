@@ -1,23 +1,21 @@
-// Forward / backward surfel tracing kernels (sm_100a, compute-only BVH traversal: B200 has no RT cores).
+// Backward, re-trace, record packing, intersection test and incident-ray kernels of the surfel tracer (sm_100a, compute-only
+// BVH traversal: B200 has no RT cores).  The forward kernel is in trace_fwd.cu.
 //
-// Replaces the three OptiX programs of /root/reference/submodules/surfel_tracer/src/optix/:
-//   gaussiantrace_forward.cu:12-141   raygen (16-hit chunks, compositing) + any-hit (sorted k-buffer)
+// Replaces, of /root/reference/submodules/surfel_tracer/src/optix/:
 //   gaussiantrace_backward.cu:11-200  raygen (re-trace, analytic gradients, 74 scalar atomics per hit)
 //   gaussiantrace_intersection_test.cu:12-35
-// and auxiliary.h:52-143 (SH colour and its backward).
+// and auxiliary.h:91-143 (backward of the SH colour).
 //
-// Design (DESIGN.md has the long form):
-//   * persistent warps pull 32 consecutive rays at a time from a global counter; one thread owns one ray;
-//   * per pass, a near-first stack traversal collects the K=16 nearest candidates strictly after the last
-//     composited hit into a sorted k-buffer in shared memory ([slot][thread] layout: bank-conflict free), culling
-//     nodes whose entry distance exceeds the current K-th best depth; the hits are composited front to back with
-//     early termination at T < T_min, and only rays that exhaust a full buffer without terminating start another
-//     pass.  Unlike the reference, whose any-hit sees every proxy triangle within 100 units until 16 are buffered,
-//     traversal here shrinks its range as soon as the buffer is full;
-//   * the forward optionally saves the ordered surfel ids of the composited hits; the backward replays that list
-//     (no second traversal) and adds per-surfel gradients with 16-byte vector atomics into one fused buffer.
-//   * the depth of a hit is computed with the same explicit sequence of IEEE operations as oracle/surfel_oracle.c,
-//     so the hit order is bit-identical to the oracle's.
+// Kernels (DESIGN.md section 3 has the long form):
+//   * pack_records_kernel          the caller's five per-surfel arrays -> 64-byte records in leaf order + inverse order
+//   * trace_backward_flat_kernel   replay of the hit lists the forward saved, ONE HIT PER LANE: segmented warp scans for the
+//                                  sequential quantities, one TMA bulk reduction (256 B) per hit into the fused [N,64] buffer
+//   * trace_backward_replay_kernel the same replay, one ray per thread (kept for comparison, bwd_mode 1)
+//   * trace_backward_retrace_kernel the reference's scheme -- re-trace in ordered 16-hit passes (sorted k-buffer in shared
+//                                  memory, binary quantised nodes) -- for rays without a (complete) saved list
+//   * intersection_test_kernel, incident_rays_kernel, incident_backward_kernel, unpack_grads_kernel
+// The depth of a hit is computed with the same explicit sequence of IEEE operations as oracle/surfel_oracle.c, so the hit
+// order is bit-identical to the oracle's.
 #include "trace_common.cuh"
 
 namespace irgs {

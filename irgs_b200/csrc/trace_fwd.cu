@@ -1,5 +1,5 @@
-// Forward tracing kernel (sm_100a): persistent, dynamic ray fetch, co-operative 64-byte fetches staged through shared
-// memory, warp-cooperative sort + compositing.
+// Forward tracing kernel (sm_100a): persistent, dynamic ray fetch, 4-wide quantised BVH walk, warp-cooperative leaf tests,
+// sort and compositing.
 //
 // Replaces gaussiantrace_forward.cu:12-141 of the reference (raygen with 16-hit chunks + any-hit sorted insertion).
 //
@@ -9,26 +9,28 @@
 //         4-wide quantised node (a binary node folded with its two children: up to four grandchildren, 16 bits per
 //         plane, conservative), four slab tests; children that are leaves are not tested on the spot but pushed on a
 //         small per-lane queue of pending leaves (shared memory), internal children are walked / stacked.
-//         LEAF: all lanes that have pending leaves fetch one 64-byte surfel record each and run the plane / alpha test
-//         together.  Postponing the leaves is what keeps both sub-phases wide: with node and leaf work interleaved per
-//         iteration, ncu showed the leaf code (27 % of all issued instructions) running at 3.4 of 32 lanes.
+//         LEAF: the pending leaves of the whole warp are flattened into one list and tested 32 (ray, surfel) pairs at a
+//         time, one pair per lane whoever owns the ray (two 256-bit loads fetch the 64-byte record; the owner's ray
+//         comes through shuffles).  With node and leaf work interleaved per lane, ncu showed the leaf code (27 % of all
+//         issued instructions) running at 3.4 of 32 lanes; with every lane draining its own queue, 5.7.
 //         The traversal stack lives in shared memory ([entry][lane]: conflict free for any mix of depths).
 //         (A variant that fetched each 64-byte record with four lanes and staged it through a swizzled shared-memory
 //         tile measured 25 % slower than direct loads and was removed; profiles/r01_notes.md.)
-//         A surfel that passes the plane / alpha test is APPENDED (one 16-byte store: t, surfel id, alpha; unsorted)
-//         to the lane's candidate row in a global scratch buffer (L2 resident).
+//         A surfel that passes the plane / alpha test is APPENDED (one 16-byte store: t, surfel id, alpha, leaf
+//         position; unsorted) to its ray's candidate row in a global scratch buffer (L2 resident).
 //   FULL  the row holds KB candidates: the warp sorts it co-operatively.  If the buffered hits alone already push the
 //         transmittance below T_min at some entry, nothing behind that entry can ever be composited: the row is
 //         trimmed there and the walk continues with its range clipped to that depth.  Otherwise the pass's depth range
 //         is SPLIT: the nearest KB/2 candidates are kept, the range is clipped to the last of them and the rest of the
 //         ray is left to a following pass (no per-candidate eviction ever happens).
-//   COMP  the pass's walk is finished: the warp ranks the candidates through shuffles and permutes them into depth
-//         order (one per lane), evaluates the transmittance chain in the sequential order of the reference, shades
-//         one hit per lane (SH colour: twelve 16-byte loads, all hits in flight at once), warp-reduces the weighted
-//         sums in depth order and adds them to the (pre-zeroed) outputs.  The ordered surfel ids are written with one
-//         coalesced store (hit list for the backward replay).
-// A lane that finishes its ray pulls the next one from a global counter at once; the warp leaves the walk to serve
-// FULL / COMP lanes as soon as fewer than MIN_ACTIVE lanes are still walking.
+//   COMP  the pass's walk is finished.  The rows of as many finished rays as fit are packed into the 32 lanes (one
+//         candidate per lane, a ray's candidates in consecutive lanes); per ray the candidates are ranked through
+//         shuffles and permuted into depth order, the transmittance chain is evaluated in the sequential order of the
+//         reference, one hit per lane is shaded (SH colour: six 256-bit loads, all hits in flight at once), and one lane
+//         per (ray, output channel) adds the weighted terms in depth order to the (pre-zeroed) outputs.  The ordered
+//         surfel ids are written with one coalesced store (hit list for the backward replay).
+// A lane that finishes its ray pulls the next one from a global counter (refills wait for FETCH_MIN idle lanes); the warp
+// leaves the walk to serve the other phases as soon as fewer than MIN_ACTIVE lanes are still walking.
 #include "trace_common.cuh"
 
 namespace irgs {
@@ -45,7 +47,7 @@ constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #ifndef IRGS_PQ
 #define IRGS_PQ 16
 #endif
-constexpr int PQ = IRGS_PQ;
+constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
 #ifndef IRGS_FETCH_MIN
 #define IRGS_FETCH_MIN 4
 #endif
@@ -57,15 +59,9 @@ constexpr bool LEAF_2STAGE = IRGS_LEAF_2STAGE != 0;
 #ifndef IRGS_COMP_MIN
 #define IRGS_COMP_MIN 24
 #endif
-constexpr int COMP_MIN = IRGS_COMP_MIN;   // candidates that must be waiting before a packed compositing round is run               // pending-leaf queue entries per lane
+constexpr int COMP_MIN = IRGS_COMP_MIN;   // candidates that must be waiting before a packed compositing round is run
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 struct WarpSmem {
     float scratch[(8 + NFMAX) * 32];   // co-operative sort / accumulation scratch

@@ -325,7 +325,9 @@ def run_ours(args):
         oh, dh = rays_o.cpu().pin_memory(), rays_d.cpu().pin_memory()
         fused = torch.zeros(args.surfels, 64, device=device)
         fused_h = torch.empty(args.surfels, 64).pin_memory()
-        e2e_chunk = min(1 << 21, n_local)
+        # chunk of the host-buffer path: large enough to amortise the drain of the persistent kernels, small enough that the
+        # un-overlapped first copy stays a small part of the step (at least ~8 chunks per rank)
+        e2e_chunk = min(1 << 23, max(1 << 21, 1 << max(0, (n_local // 8).bit_length() - 1)), n_local)
         ge = make_gout(e2e_chunk, device)
 
         def e2e_step():

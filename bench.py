@@ -34,7 +34,7 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--chunk", type=int, default=1 << 22, help="rays per trace call")
+    p.add_argument("--chunk", type=int, default=1 << 24, help="rays per trace call (SURVEY 8d: 2^22 - 2^24)")
     p.add_argument("--surfels", type=int, default=N_SURFELS)
     p.add_argument("--img", type=int, default=IMG)
     p.add_argument("--spp", type=int, default=SPP)
@@ -189,7 +189,9 @@ def run_ours(args):
     sc, inp, tracer, rays_o, rays_d = build_workload(args, device, rank, world, factory)
     n_local = rays_o.shape[0]
     n_total = args.img * args.img * args.spp
-    chunk = min(args.chunk, n_local)
+    # rays per trace call: large calls amortise the drain of the persistent kernels; at least ~4 calls per rank so that the
+    # two streams have something to overlap
+    chunk = min(args.chunk, max(1 << 20, 1 << (max(1, (n_local + 3) // 4) - 1).bit_length()), n_local)
     gout = make_gout(chunk, device)
     leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
     tracer.accumulate_grads = True

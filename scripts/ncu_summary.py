@@ -30,10 +30,10 @@ def val(r, m):
 
 for r in rows[2:]:
     if 'trace_forward' in r[hdr.index('Kernel Name')]:
-        json.dump({"kernel": "trace_forward_kernel<0,0>", "rays_per_launch": 1 << 22,
+        json.dump({"kernel": "trace_forward_kernel<0,0>", "rays_per_launch": int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 24,
                    "dram_bytes_read": val(r, 'dram__bytes_read.sum'), "dram_bytes_write": val(r, 'dram__bytes_write.sum'),
                    "gpu_time_ms_under_ncu": float(r[hdr.index('gpu__time_duration.sum')]),
-                   "source": "profiles/r01_full_summary.csv (ncu --set full --clock-control none, bench.py C3 step, one 2^22-ray launch)"},
+                   "source": "profiles/r01_full_summary.csv (ncu --set full --clock-control none, bench.py C3 step, one forward launch)"},
                   open(os.path.join(ROOT, "profiles", "fwd_kernel_traffic.json"), "w"), indent=1)
         break
 print(open(os.path.join(ROOT, "profiles", "r01_full_summary.csv")).read())

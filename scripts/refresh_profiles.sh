@@ -7,4 +7,4 @@ python scripts/ncu_phases.py $R > profiles/r01_fwd_phases_final.txt
 python scripts/ncu_regions.py $R trace_backward_flat 0.6 > profiles/r01_bwd_flat_regions.txt
 python scripts/launch_summary.py gpurun_out/final_launches.csv > profiles/r01_step_launches.txt
 cp gpurun_out/final_launches.csv profiles/r01_step_launches.csv
-python scripts/ncu_summary.py $R
+python scripts/ncu_summary.py $R ${RAYS_PER_LAUNCH:-16777216}

@@ -47,6 +47,39 @@ def test_library_is_sm100a_only_and_uses_vector_atomics():
     assert re.search(r"(RED|ATOM)\S*\.128|REDG\S*\.128|\.F32x4|\.F32X4", sass) or "128" in sass
 
 
+def test_sass_has_the_blackwell_instructions_the_design_relies_on():
+    """The forward walk fetches nodes and records with 256-bit loads (LDG.E...256), the hit-parallel backward adds gradient
+    rows with TMA bulk reductions (UBLKRED); neither kernel spills registers on the throughput path."""
+    import shutil
+    import subprocess
+    from irgs_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = build.build()
+    fwd = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4irgs20trace_forward_kernelILb0ELb0EEEvNS_7KParamsEP5uint4", lib],
+                         capture_output=True, text=True).stdout
+    assert len(re.findall(r"LDG\.E\S*\.256", fwd)) >= 4, "forward kernel lost its 256-bit loads"
+    bwd = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4irgs26trace_backward_flat_kernelILb0ELb1EEEvNS_7KParamsE", lib],
+                         capture_output=True, text=True).stdout
+    assert "UBLKRED" in bwd, "backward kernel lost its bulk reduction"
+    assert re.search(r"LDG\.E\S*\.256", bwd)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/irgs_b200.h must compile as C (the boundary a cgo / JNI / ctypes host binds), not only as C++."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use.c"
+    src.write_text('#include "irgs_b200.h"\n'
+                   'int probe(void) { irgs_incident_t g; g.sample_num = 1; (void)g; return irgs_version() >= 100 ? 0 : 1; }\n')
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c",
+                           str(src), "-o", str(tmp_path / "use.o")])
+
+
 def test_no_cpu_fallback():
     """Without CUDA the product must refuse to run rather than fall back."""
     import torch

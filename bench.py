@@ -43,6 +43,7 @@ def parse():
                         "overlaps the next chunk)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
+    p.add_argument("--no-shade", action="store_true", help="skip the rendering-equation measurement (fused generation + shading epilogue)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     p.add_argument("--ref-rays", type=int, default=1 << 22, help="rays per step of the reference arm's bounded sample")
@@ -320,6 +321,53 @@ def run_ours(args):
                      "api": "GaussianTracer.trace_incident (irgs_trace_forward_incident / irgs_trace_backward_incident)",
                      "input_bytes_per_step": int(pts.shape[0] * 28), "grad_checksum": float(fg["shs"].abs().sum().item())}
 
+    # SURVEY 8f rank 1 + 3: the whole rendering equation of the stage-2 training step -- rays generated in the kernels,
+    # traced, shaded (environment lookup, GGX, means over the 256 samples) by the epilogue kernels, and back: the loss
+    # gradient arrives per PIXEL (diffuse / specular / light_direct), not per ray
+    shaded = None
+    if not args.no_shade and not args.no_fused:
+        from irgs_b200 import shading
+        pts, nrm, azim = build_workload.points
+        env = shading.EnvLight(resolution=(256, 512), activation="exp", device=device)   # arguments/__init__.py: envmap_resolution
+        gsh = torch.Generator(device).manual_seed(77)
+        env.base.data += 0.3 * torch.randn(env.base.shape, device=device, generator=gsh)
+        n_pts = pts.shape[0]
+        base_color = torch.rand(n_pts, 3, device=device, generator=gsh).requires_grad_(True)
+        rough = (0.1 + 0.8 * torch.rand(n_pts, 1, device=device, generator=gsh)).requires_grad_(True)
+        view = torch.nn.functional.normalize(torch.tensor(synth.CAMERA_CENTER, device=device, dtype=torch.float32)[None] - pts, dim=-1)
+        pts_l, nrm_l = pts.clone().requires_grad_(True), nrm.clone().requires_grad_(True)
+        pchunk = max(1, chunk // args.spp)
+        gpix = torch.randn(n_pts, 9, device=device, generator=gsh)
+        surf = (leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], None, leaf["shs"])
+
+        def shaded_step():
+            def body(b, e):
+                out = shading.rendering_equation(base_color[b:e], rough[b:e], nrm_l[b:e], pts_l[b:e], view[b:e], tracer, surf, env,
+                                                 args.spp, training=True, azimuth=azim[b:e], light_t_min=synth.LIGHT_T_MIN,
+                                                 alpha_min=synth.ALPHA_MIN)
+                torch.autograd.backward([out["diffuse"], out["specular"], out["light_direct"]],
+                                        [gpix[b:e, 0:3], gpix[b:e, 3:6], gpix[b:e, 6:9]])
+            chunks_on_streams(n_pts, pchunk, body)
+            genv = env.base.grad
+            for t in (pts_l, nrm_l, base_color, rough, env.base):
+                t.grad = None
+            return tracer.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape)), genv
+
+        for _ in range(min(args.warmup, 2)):
+            shaded_step()
+        sync_all()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(args.steps):
+            sg, genv = shaded_step()
+        h1.record()
+        sync_all()
+        hms = parallel.max_over_ranks(h0.elapsed_time(h1), device) / args.steps
+        shaded = {"value": n_total / (hms * 1e-3), "unit": "rays/s", "ms_per_step": hms,
+                  "api": "irgs_b200.shading.rendering_equation (trace_incident + irgs_shade_forward / irgs_shade_backward)",
+                  "envmap": "256x512 lat-long, exp activation", "grad_checksum": float(sg["shs"].abs().sum().item()),
+                  "env_grad_checksum": float(genv.abs().sum().item())}
+
     # end to end through the C ABI on HOST buffers: rays pinned on the host, copied in per chunk inside the timed region;
     # the step's result (fused per-surfel gradients after the all-reduce) is read back to the host
     e2e = None
@@ -383,7 +431,7 @@ def run_ours(args):
                    "parallelism": f"ray-sharded dp{world} (32-pixel blocks round-robin), surfels+BVH replicated, one all-reduce of N x 64 floats",
                    "l2": "inputs (3.9 GB of rays per step) exceed L2; no flush needed",
                    "shading_points": "all 640k bundles start on the surface (missed pixels re-assigned to hit pixels)"},
-        "e2e": e2e, "fused_generation": fused_gen, "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
+        "e2e": e2e, "fused_generation": fused_gen, "rendering_equation": shaded, "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
         "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_ray * chunk,

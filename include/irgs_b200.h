@@ -169,6 +169,44 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
                                  float *grad_normal_pt, float *grad_fused, float *grad_features, float alpha_min, float T_min,
                                  int back_culling, void *stream);
 
+/* ---- Shading epilogue around the incident-ray trace (SURVEY.md 8f rank 1 + rank 3) ----------------------------------
+ * Replaces the element-wise torch code of /root/reference/gaussian_renderer/__init__.py:334-415 (rendering_equation, the
+ * diffuse_sample_num > 0 / light_sample_num == 0 / non-relight path) together with :417-457 (GGX_specular) and the
+ * environment lookup scene/light.py:287-297,315 (EnvLight.__call__(mode='pure_env'): lat-long uv, nvdiffrast
+ * texture(filter 'linear', boundary 'wrap'), activation, clamp_min(0)).  One kernel per direction: a warp per shading
+ * point regenerates the S incident directions of `gen` (the same device function the tracing kernels use), reads the
+ * tracer's RAW colour / alpha of those rays and reduces over S. */
+typedef struct {
+    const float *base;       /* [H,W,3] pre-activation texels (EnvLight.base), device */
+    int32_t height, width;
+    int32_t activation;      /* 0 none, 1 exp, 2 sigmoid (EnvLight.activation_name) */
+    int32_t has_transform;   /* EnvLight.transform set? */
+    float transform[9];      /* row-major 3x3: lookup direction = d @ transform^T (light.py:299-300) */
+} irgs_envmap_t;
+
+/* trace_color [P*S,3], trace_alpha [P*S]: outputs of irgs_trace_forward_incident for the same `gen`.  saturate_alpha =
+ * 1 - transmittance_min applies GaussianModel.trace's normalisation of saturated rays (scene/gaussian_model.py:748-752:
+ * colour / alpha and alpha = 1 where alpha >= 1 - transmittance_min); a negative value skips it.  base_color [P,3],
+ * roughness [P], viewdirs [P,3] (any length).  gen->position is not used.
+ * out [P,16], means over the S samples: 0-2 diffuse, 3-5 specular, 6-8 light_direct, 9 visibility, 10-12 light,
+ * 13-15 light_indirect (the keys of rendering_equation's result dict, __init__.py:399-414). */
+int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
+                       const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
+                       float *out, void *stream);
+/* g_out [P,16] in the layout of `out`.  OVERWRITTEN: g_trace_color [P*S,3], g_trace_alpha [P*S] (the gradients to hand to
+ * irgs_trace_backward_incident as gout_color / gout_alpha) and g_point [P,16]: 0-2 dL/dbase_color, 3 dL/droughness,
+ * 4-6 dL/dnormal (n_d_i, the GGX normal AND the dependence of the sampled directions on the normal through
+ * rotation_between_z), 7-9 dL/dviewdirs.  Texel gradients are ADDED (atomically) into grad_env [H,W,3] (may be NULL). */
+int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
+                        const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
+                        const float *g_out, float *g_trace_color, float *g_trace_alpha, float *g_point, float *grad_env,
+                        void *stream);
+/* EnvLight.__call__(dirs, mode='pure_env') on its own (e.g. gaussian_renderer/__init__.py:244: the background radiance of
+ * the primary rays): dirs [n,3] -> out [n,3]; backward: g_dirs [n,3] overwritten (may be NULL), grad_env added to. */
+int irgs_env_lookup_forward(const irgs_envmap_t *env, const float *dirs, int64_t n_dirs, float *out, void *stream);
+int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const float *g_out, int64_t n_dirs, float *g_dirs,
+                             float *grad_env, void *stream);
+
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
  * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.

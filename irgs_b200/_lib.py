@@ -31,6 +31,10 @@ PROTOTYPES = {
     "irgs_trace_forward_incident": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_vp, _vp, _i32, _f32, _f32, _i32, _vp]),
     "irgs_trace_backward_incident": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_vp, _vp, _i32] + [_vp] * 5
                                      + [_vp] * 6 + [_f32, _f32, _i32, _vp]),
+    "irgs_shade_forward": (_i32, [_vp] * 7 + [_f32, _vp, _vp]),
+    "irgs_shade_backward": (_i32, [_vp] * 7 + [_f32] + [_vp] * 6),
+    "irgs_env_lookup_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "irgs_env_lookup_backward": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "irgs_unpack_grads": (_i32, [_vp, _i64, _i32] + [_vp] * 6 + [_vp]),
     "irgs_trace_forward_host": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 9 + [_vp] * 5 + [_f32, _f32, _i32, _i64]),
     "irgs_trace_fwd_bwd_host": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 9 + [_vp] * 5 + [_i64] + [_vp] * 3

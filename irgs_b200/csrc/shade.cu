@@ -1,0 +1,280 @@
+// Shading epilogue around the incident-ray trace (SURVEY.md 8f rank 1 + rank 3), sm_100a.
+//
+// The reference evaluates its rendering equation (gaussian_renderer/__init__.py:334-415) with some thirty element-wise
+// torch kernels over [P, S, 3] tensors: incident directions, environment lookup (nvdiffrast), visibility blend, GGX
+// term, two means over S.  Here ONE kernel per direction does all of it: a warp owns a shading point, regenerates the S
+// Fibonacci directions with the device function the tracing kernels use (incident_sample), reads 16 bytes per ray (traced
+// colour + alpha), looks the environment map up (lat-long bilinear, L2 resident), and reduces over S with shuffles.
+// The backward recomputes the same quantities, writes dL/d(colour, alpha) per ray for the tracer's backward, adds the
+// texel gradients with atomics, and chains dL/d(direction) through rotation_between_z to the shading normal.
+// Per-sample arithmetic: shade_math.cuh (shared with the host harness of the tests).
+//
+// Roofline: HBM streaming -- forward reads 16 B per ray, backward reads 16 B and writes 16 B per ray; everything per
+// point (56 B in, 64 B out) is amortised over S.  At S = 256 that is ~16.5 / ~32.5 bytes per ray.
+#include "internal.cuh"
+#include "shade_math.cuh"
+#include "trace_common.cuh"
+
+namespace irgs {
+
+struct ShadeArgs {
+    const float *normals, *azimuth;        // [P,3], [P] or null
+    int64_t n_points;
+    int S;
+    const float *base_color, *roughness, *viewdirs;   // [P,3], [P], [P,3]
+    const float *trace_color, *trace_alpha;           // [P*S,3], [P*S] raw tracer outputs
+    float saturate;                                   // 1 - transmittance_min, < 0: no normalisation
+    EnvMap env;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void load_point(const ShadeArgs &a, int64_t pt, float n[3], ShadePoint &p) {
+    float view[3], base[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        n[j] = __ldg(a.normals + 3 * pt + j);
+        view[j] = __ldg(a.viewdirs + 3 * pt + j);
+        base[j] = __ldg(a.base_color + 3 * pt + j);
+    }
+    shade_point_setup(n, view, __ldg(a.roughness + pt), base, p);
+}
+
+// out [P,16]: 0-2 diffuse, 3-5 specular, 6-8 light_direct, 9 visibility, 10-12 light, 13-15 light_indirect (means over S)
+__global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *__restrict__ out) {
+    const int64_t pt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= a.n_points) return;
+    float n[3];
+    ShadePoint p;
+    load_point(a, pt, n, p);
+    const float az = a.azimuth ? __ldg(a.azimuth + pt) : 0.f;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int s = lane; s < a.S; s += 32) {
+        const int64_t ray = pt * a.S + s;
+        const IncidentSample q = incident_sample(n[0], n[1], n[2], s, a.S, a.azimuth != nullptr, az);
+        const float d[3] = {__fdiv_rn(q.vx, q.len), __fdiv_rn(q.vy, q.len), __fdiv_rn(q.vz, q.len)};
+        const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
+                                __ldg(a.trace_color + 3 * ray + 2)};
+        ShadeSample o;
+        shade_sample_forward(p, a.env, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, o);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            acc[c] += p.fd[c] * o.transport[c];
+            acc[3 + c] += o.fs * o.transport[c];
+            acc[6 + c] += o.env[c];
+            acc[10 + c] += o.Li[c];
+            acc[13 + c] += o.local[c];
+        }
+        acc[9] += o.vis;
+    }
+    const float inv = 1.0f / (float)a.S;
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float v = warp_sum(acc[j]);
+        if (lane == j) mine = v * inv;
+    }
+    if (lane < 16) out[16 * pt + lane] = mine;    // one 64-byte row per point
+}
+
+// g_out [P,16] in the layout of the forward's rows.  Per ray: g_color [P*S,3], g_alpha [P*S] (overwritten).  Per point:
+// g_point [P,16]: 0-2 dL/dbase_color, 3 dL/droughness, 4-6 dL/dnormal, 7-9 dL/dviewdirs (overwritten).  Texel gradients
+// are ADDED into grad_env [H,W,3] (may be null).
+__global__ void __launch_bounds__(128) shade_backward_kernel(ShadeArgs a, const float *__restrict__ g_out,
+                                                             float *__restrict__ g_color, float *__restrict__ g_alpha,
+                                                             float *__restrict__ g_point, float *__restrict__ grad_env) {
+    const int64_t pt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= a.n_points) return;
+    float n[3];
+    ShadePoint p;
+    load_point(a, pt, n, p);
+    const float az = a.azimuth ? __ldg(a.azimuth + pt) : 0.f;
+    const float inv = 1.0f / (float)a.S;
+    float go = (lane < 16) ? __ldg(g_out + 16 * pt + lane) * inv : 0.f;     // the mean over S folded into the gradients
+    float gD[3], gS[3], gE[3], gLi[3], gLocal[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        gD[c] = __shfl_sync(0xffffffffu, go, c);
+        gS[c] = __shfl_sync(0xffffffffu, go, 3 + c);
+        gE[c] = __shfl_sync(0xffffffffu, go, 6 + c);
+        gLi[c] = __shfl_sync(0xffffffffu, go, 10 + c);
+        gLocal[c] = __shfl_sync(0xffffffffu, go, 13 + c);
+    }
+    const float gVis = __shfl_sync(0xffffffffu, go, 9);
+    ShadeAcc acc;
+    shade_acc_zero(acc);
+    float G[9];     // dL/dR of rotation_between_z, row-major
+#pragma unroll
+    for (int j = 0; j < 9; ++j) G[j] = 0.f;
+    for (int s = lane; s < a.S; s += 32) {
+        const int64_t ray = pt * a.S + s;
+        const IncidentSample q = incident_sample(n[0], n[1], n[2], s, a.S, a.azimuth != nullptr, az);
+        const float d[3] = {__fdiv_rn(q.vx, q.len), __fdiv_rn(q.vy, q.len), __fdiv_rn(q.vz, q.len)};
+        const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
+                                __ldg(a.trace_color + 3 * ray + 2)};
+        float g_c[3], g_a, gd[3];
+        shade_sample_backward(p, a.env, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, gD, gS, gE, gVis, gLi, gLocal,
+                              grad_env, acc, g_c, g_a, gd);
+        g_color[3 * ray] = g_c[0]; g_color[3 * ray + 1] = g_c[1]; g_color[3 * ray + 2] = g_c[2];
+        g_alpha[ray] = g_a;
+        if (q.rotated && q.len > 1e-12f) {   // d = v / |v|, v = R zs  (same chain as incident_backward_kernel, trace.cu)
+            const float dd = d[0] * gd[0] + d[1] * gd[1] + d[2] * gd[2];
+            const float gvx = (gd[0] - d[0] * dd) / q.len, gvy = (gd[1] - d[1] * dd) / q.len, gvz = (gd[2] - d[2] * dd) / q.len;
+            G[0] += gvx * q.zx; G[1] += gvx * q.zy; G[2] += gvx * q.zz;
+            G[3] += gvy * q.zx; G[4] += gvy * q.zy; G[5] += gvy * q.zz;
+            G[6] += gvz * q.zx; G[7] += gvz * q.zy; G[8] += gvz * q.zz;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        acc.g_base[j] = warp_sum(acc.g_base[j]);
+        acc.g_n[j] = warp_sum(acc.g_n[j]);
+        acc.g_N[j] = warp_sum(acc.g_N[j]);
+        acc.g_V[j] = warp_sum(acc.g_V[j]);
+    }
+    acc.g_nom1 = warp_sum(acc.g_nom1);
+    acc.g_a2 = warp_sum(acc.g_a2);
+    acc.g_k = warp_sum(acc.g_k);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) G[j] = warp_sum(G[j]);
+    if (lane == 0) {
+        float g_base[3], g_rough, g_normal[3], g_view[3];
+        shade_point_finish(p, acc, g_base, g_rough, g_normal, g_view);
+        // dL/dn through R(n): v1 = -n.y, v2 = n.x, c = max(n.z + 1, 1e-7)   (graphics_utils.py:133-165)
+        const float v1 = -n[1], v2 = n[0], c = fmaxf(n[2] + 1.0f, 1e-7f);
+        const float gv1 = (G[1] + G[3]) * v2 / c - (G[4] + G[8]) * 2.0f * v1 / c - G[5] + G[7];
+        const float gv2 = -(G[0] + G[8]) * 2.0f * v2 / c + (G[1] + G[3]) * v1 / c + G[2] - G[6];
+        const float gc = (G[0] * v2 * v2 - (G[1] + G[3]) * v1 * v2 + G[4] * v1 * v1 + G[8] * (v1 * v1 + v2 * v2)) / (c * c);
+        g_normal[0] += gv2;
+        g_normal[1] += -gv1;
+        g_normal[2] += (n[2] + 1.0f > 1e-7f) ? gc : 0.0f;
+        float *o = g_point + 16 * pt;
+        o[0] = g_base[0]; o[1] = g_base[1]; o[2] = g_base[2]; o[3] = g_rough;
+        o[4] = g_normal[0]; o[5] = g_normal[1]; o[6] = g_normal[2];
+        o[7] = g_view[0]; o[8] = g_view[1]; o[9] = g_view[2];
+        o[10] = o[11] = o[12] = o[13] = o[14] = o[15] = 0.f;
+    }
+}
+
+// ---- stand-alone environment lookup (EnvLight.__call__(dirs, mode='pure_env'), light.py:287-297,315): one thread per direction
+__global__ void env_lookup_forward_kernel(EnvMap env, const float *__restrict__ dirs, int64_t n, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvTap t;
+    float raw[3], val[3];
+    env_tap(env, __ldg(dirs + 3 * i), __ldg(dirs + 3 * i + 1), __ldg(dirs + 3 * i + 2), t);
+    env_fetch(env, t, raw, val);
+    out[3 * i] = val[0]; out[3 * i + 1] = val[1]; out[3 * i + 2] = val[2];
+}
+
+__global__ void env_lookup_backward_kernel(EnvMap env, const float *__restrict__ dirs, const float *__restrict__ g_out,
+                                           int64_t n, float *__restrict__ g_dirs, float *__restrict__ grad_env) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvTap t;
+    float raw[3], val[3], gd[3] = {0.f, 0.f, 0.f};
+    const float g[3] = {__ldg(g_out + 3 * i), __ldg(g_out + 3 * i + 1), __ldg(g_out + 3 * i + 2)};
+    env_tap(env, __ldg(dirs + 3 * i), __ldg(dirs + 3 * i + 1), __ldg(dirs + 3 * i + 2), t);
+    env_fetch(env, t, raw, val);
+    env_backward(env, t, raw, val, g, grad_env, gd);
+    if (g_dirs) { g_dirs[3 * i] = gd[0]; g_dirs[3 * i + 1] = gd[1]; g_dirs[3 * i + 2] = gd[2]; }
+}
+
+static int fail_msg(const char *msg) {
+    set_error(msg);
+    return 1;
+}
+
+static int make_env(const irgs_envmap_t *env, EnvMap &e) {
+    if (!env || !env->base) return fail_msg("null environment map");
+    if (env->height < 1 || env->width < 1) return fail_msg("environment map must be at least 1 x 1");
+    if (env->activation < 0 || env->activation > 2) return fail_msg("environment activation must be 0 (none), 1 (exp) or 2 (sigmoid)");
+    e.base = env->base; e.H = env->height; e.W = env->width; e.activation = env->activation;
+    e.has_transform = env->has_transform;
+    for (int j = 0; j < 9; ++j) e.T[j] = env->transform[j];
+    return 0;
+}
+
+static int make_args(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
+                     const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
+                     ShadeArgs &a) {
+    if (!gen) return fail_msg("null incident-ray descriptor");
+    if (gen->n_points < 0 || gen->sample_num < 1) return fail_msg("incident rays: n_points >= 0 and sample_num >= 1 required");
+    if (gen->n_points > 0 && (!gen->normals || !base_color || !roughness || !viewdirs || !trace_color || !trace_alpha))
+        return fail_msg("shade: null input array");
+    if (make_env(env, a.env)) return 1;
+    a.normals = gen->normals; a.azimuth = gen->azimuth; a.n_points = gen->n_points; a.S = gen->sample_num;
+    a.base_color = base_color; a.roughness = roughness; a.viewdirs = viewdirs;
+    a.trace_color = trace_color; a.trace_alpha = trace_alpha; a.saturate = saturate_alpha;
+    return 0;
+}
+
+}  // namespace irgs
+
+using namespace irgs;
+
+extern "C" {
+
+int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
+                       const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
+                       float *out, void *stream) {
+    ShadeArgs a;
+    if (make_args(gen, env, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
+    if (a.n_points == 0) return 0;
+    if (!out) return fail_msg("shade: null output array");
+    shade_forward_kernel<<<(unsigned)((a.n_points * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, out);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
+                        const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
+                        const float *g_out, float *g_trace_color, float *g_trace_alpha, float *g_point, float *grad_env,
+                        void *stream) {
+    ShadeArgs a;
+    if (make_args(gen, env, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
+    if (a.n_points == 0) return 0;
+    if (!g_out || !g_trace_color || !g_trace_alpha || !g_point) return fail_msg("shade backward: null array");
+    shade_backward_kernel<<<(unsigned)((a.n_points * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        a, g_out, g_trace_color, g_trace_alpha, g_point, grad_env);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int irgs_env_lookup_forward(const irgs_envmap_t *env, const float *dirs, int64_t n_dirs, float *out, void *stream) {
+    EnvMap e;
+    if (make_env(env, e)) return 1;
+    if (n_dirs < 0) return fail_msg("n_dirs < 0");
+    if (n_dirs == 0) return 0;
+    if (!dirs || !out) return fail_msg("env lookup: null array");
+    env_lookup_forward_kernel<<<(unsigned)((n_dirs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e, dirs, n_dirs, out);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const float *g_out, int64_t n_dirs, float *g_dirs,
+                             float *grad_env, void *stream) {
+    EnvMap e;
+    if (make_env(env, e)) return 1;
+    if (n_dirs < 0) return fail_msg("n_dirs < 0");
+    if (n_dirs == 0) return 0;
+    if (!dirs || !g_out) return fail_msg("env lookup backward: null array");
+    env_lookup_backward_kernel<<<(unsigned)((n_dirs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e, dirs, g_out, n_dirs, g_dirs,
+                                                                                                   grad_env);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

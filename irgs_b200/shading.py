@@ -1,0 +1,212 @@
+"""Shading epilogue around the incident-ray trace (SURVEY.md 8f rank 1 + rank 3): the reference's `rendering_equation`
+as two CUDA kernels (forward / backward) instead of some thirty element-wise torch kernels over [P, S, 3] tensors.
+
+Reference being mirrored (paths under /root/reference):
+  * gaussian_renderer/__init__.py:334-415  rendering_equation(base_color, roughness, normals, position, viewdirs, pc, pipe,
+        training=...) -> {"diffuse", "specular", "light_direct"} (training) + {"visibility", "light", "light_indirect"}
+        (evaluation); the `diffuse_sample_num > 0, light_sample_num == 0`, non-relight path (the stage-2 training path
+        and BASELINE config C3).  The mixed light-importance-sampling and relight paths (C4: nvdiffrast cube-map mips +
+        FG LUT) are not built and raise NotImplementedError, like the reference's own `else` branch.
+  * gaussian_renderer/__init__.py:417-457  GGX_specular
+  * scene/light.py:132-172,245-246,287-297,315  EnvLight (base, activation, transform, __call__(mode='pure_env'))
+  * scene/gaussian_model.py:748-752  GaussianModel.trace's normalisation of saturated rays (folded into the kernels)
+
+    env = EnvLight(resolution=(256, 512), activation="exp")                   # or any object with .base / .activation_name / .transform
+    out = rendering_equation(base_color, roughness, normals, position, viewdirs, tracer, surfels, env,
+                             sample_num=256, training=True)
+    out["diffuse"], out["specular"], out["light_direct"]                      # [P,3] each, differentiable
+
+`surfels` is the tuple (means3D, opacity, ru, rv, normals, features, shs) that `GaussianTracer.trace` takes.  Gradients
+reach base_color, roughness, normals (n_d_i, GGX and the sampled directions), position, viewdirs, the environment texels
+and -- through the tracer's backward -- the surfel parameters.  No CPU path: everything runs in libirgs_b200.so.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from .incident import _check, _desc
+from .raytracer import _ptr, _stream
+
+ACTIVATIONS = {"none": 0, "exp": 1, "sigmoid": 2}
+OUT_SLICES = {"diffuse": slice(0, 3), "specular": slice(3, 6), "light_direct": slice(6, 9), "visibility": slice(9, 10),
+              "light": slice(10, 13), "light_indirect": slice(13, 16)}
+
+
+class EnvDesc(ctypes.Structure):
+    """irgs_envmap_t of include/irgs_b200.h."""
+    _fields_ = [("base", ctypes.c_void_p), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("activation", ctypes.c_int32), ("has_transform", ctypes.c_int32), ("transform", ctypes.c_float * 9)]
+
+
+def _env_desc(base, activation, transform):
+    if base.dim() != 3 or base.shape[-1] != 3 or base.dtype != torch.float32 or not base.is_cuda:
+        raise ValueError("environment base must be a float32 CUDA tensor [H, W, 3]")
+    if activation not in ACTIVATIONS:
+        raise NotImplementedError(f"environment activation {activation!r} (light.py:160-168 knows exp / sigmoid / none)")
+    d = EnvDesc(base.data_ptr(), base.shape[0], base.shape[1], ACTIVATIONS[activation], int(transform is not None))
+    if transform is not None:
+        t = [float(x) for x in torch.as_tensor(transform, dtype=torch.float32).reshape(-1).tolist()]
+        if len(t) != 9:
+            raise ValueError("environment transform must be 3 x 3")
+        for j in range(9):
+            d.transform[j] = t[j]
+    return d
+
+
+def _env_fields(envmap):
+    """(base, activation name, transform) of a reference-style EnvLight object (duck-typed: scene/light.py:132-172)."""
+    return envmap.base, getattr(envmap, "activation_name", "exp"), getattr(envmap, "transform", None)
+
+
+class _EnvLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dirs, base, activation, transform):
+        dirs_c, base_c = dirs.reshape(-1, 3).contiguous(), base.contiguous()
+        out = torch.empty_like(dirs_c)
+        desc = _env_desc(base_c, activation, transform)
+        _lib.check(_lib.load().irgs_env_lookup_forward(ctypes.byref(desc), _ptr(dirs_c), dirs_c.shape[0], _ptr(out),
+                                                       _stream(dirs_c.device)))
+        ctx.save_for_backward(dirs_c, base_c)
+        ctx.cfg = (activation, transform, dirs.shape)
+        return out.view(dirs.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        dirs_c, base_c = ctx.saved_tensors
+        activation, transform, shape = ctx.cfg
+        g = g.reshape(-1, 3).contiguous()
+        g_dirs = torch.empty_like(dirs_c) if ctx.needs_input_grad[0] else None
+        g_env = torch.zeros_like(base_c) if ctx.needs_input_grad[1] else None
+        desc = _env_desc(base_c, activation, transform)
+        _lib.check(_lib.load().irgs_env_lookup_backward(ctypes.byref(desc), _ptr(dirs_c), _ptr(g), dirs_c.shape[0],
+                                                        _ptr(g_dirs), _ptr(g_env), _stream(dirs_c.device)))
+        return (g_dirs.view(shape) if g_dirs is not None else None), g_env, None, None
+
+
+class EnvLight(torch.nn.Module):
+    """The part of the reference's EnvLight (scene/light.py:132-172,245-246,287-297,315) that the tracing path uses: a
+    learnable lat-long map `base` [H, W, 3] stored pre-activation, `activation_name`, an optional `transform`, and
+    `__call__(dirs, mode='pure_env')`.  Cube-map mips (modes 'diffuse' / 'specular', nvdiffrast) are not built."""
+
+    def __init__(self, resolution=(256, 512), activation="exp", init_value=0.5, device="cuda"):
+        super().__init__()
+        if activation not in ACTIVATIONS:
+            raise NotImplementedError(activation)
+        base = torch.full((resolution[0], resolution[1], 3), float(init_value), dtype=torch.float32, device=device)
+        if activation == "sigmoid":
+            base = torch.log(base / (1 - base))
+        elif activation == "exp":
+            base = torch.log(base)
+        self.base = torch.nn.Parameter(base, requires_grad=True)
+        self.activation_name = activation
+        self.transform = None
+
+    def set_transform(self, transform):
+        self.transform = transform
+
+    def __call__(self, l, mode="pure_env", roughness=None):
+        if mode != "pure_env":
+            raise NotImplementedError("only mode='pure_env' is built (the cube-map modes need nvdiffrast's mip chain)")
+        return _EnvLookup.apply(l, self.base, self.activation_name, self.transform)
+
+
+def env_lookup(dirs, base, activation="exp", transform=None):
+    """EnvLight.__call__(dirs, mode='pure_env') as a function: dirs [...,3] -> radiance [...,3] (differentiable w.r.t.
+    dirs and base)."""
+    return _EnvLookup.apply(dirs, base, activation, transform)
+
+
+class _ShadeIncident(torch.autograd.Function):
+    """out [P,16] = means over the S incident samples (layout: OUT_SLICES)."""
+
+    @staticmethod
+    def forward(ctx, normals_pt, azimuth, sample_num, base_color, roughness, viewdirs, env_base, activation, transform,
+                trace_color, trace_alpha, saturate_alpha):
+        dev = normals_pt.device
+        P = normals_pt.shape[0]
+        out = torch.empty(P, 16, device=dev)
+        gen = _desc(normals_pt, normals_pt, azimuth, sample_num, 0.0)
+        env = _env_desc(env_base, activation, transform)
+        _lib.check(_lib.load().irgs_shade_forward(ctypes.byref(gen), ctypes.byref(env), _ptr(base_color), _ptr(roughness),
+                                                  _ptr(viewdirs), _ptr(trace_color), _ptr(trace_alpha), saturate_alpha,
+                                                  _ptr(out), _stream(dev)))
+        ctx.save_for_backward(normals_pt, azimuth if azimuth is not None else normals_pt[:0], base_color, roughness, viewdirs,
+                              env_base, trace_color, trace_alpha)
+        ctx.cfg = (sample_num, activation, transform, saturate_alpha, azimuth is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        normals_pt, azimuth, base_color, roughness, viewdirs, env_base, trace_color, trace_alpha = ctx.saved_tensors
+        sample_num, activation, transform, saturate_alpha, has_azim = ctx.cfg
+        dev = normals_pt.device
+        P = normals_pt.shape[0]
+        g_out = g_out.contiguous()
+        g_color = torch.empty_like(trace_color)
+        g_alpha = torch.empty_like(trace_alpha)
+        g_point = torch.empty(P, 16, device=dev)
+        g_env = torch.zeros_like(env_base) if ctx.needs_input_grad[6] else None
+        gen = _desc(normals_pt, normals_pt, azimuth if has_azim else None, sample_num, 0.0)
+        env = _env_desc(env_base, activation, transform)
+        _lib.check(_lib.load().irgs_shade_backward(ctypes.byref(gen), ctypes.byref(env), _ptr(base_color), _ptr(roughness),
+                                                   _ptr(viewdirs), _ptr(trace_color), _ptr(trace_alpha), saturate_alpha,
+                                                   _ptr(g_out), _ptr(g_color), _ptr(g_alpha), _ptr(g_point), _ptr(g_env),
+                                                   _stream(dev)))
+        return (g_point[:, 4:7], None, None, g_point[:, 0:3], g_point[:, 3], g_point[:, 7:10], g_env, None, None,
+                g_color, g_alpha, None)
+
+
+def shade_incident(normals, sample_num, base_color, roughness, viewdirs, env_base, trace_color, trace_alpha, azimuth=None,
+                   activation="exp", transform=None, transmittance_min=None):
+    """The rendering-equation epilogue on its own: given the tracer's RAW colour [P,S,3] / alpha [P,S] of the incident rays
+    that `GaussianTracer.trace_incident(position, normals, sample_num, ..., azimuth=azimuth)` traced, returns the dict
+    of rendering_equation (all six keys; [P,3] each, visibility [P,1]).  transmittance_min: apply GaussianModel.trace's
+    normalisation of saturated rays (None: the colour / alpha are used as they are)."""
+    dev = normals.device
+    f = lambda t: t.contiguous()                                                        # noqa: E731
+    normals, base_color, viewdirs = f(normals), f(base_color), f(viewdirs)
+    roughness = f(roughness).view(-1)
+    azimuth = f(azimuth).view(-1) if azimuth is not None else None
+    _check(normals, normals, azimuth, dev)
+    P, S = normals.shape[0], int(sample_num)
+    for name, t, shape in (("base_color", base_color, (P, 3)), ("roughness", roughness, (P,)), ("viewdirs", viewdirs, (P, 3)),
+                           ("trace_color", trace_color, (P, S, 3)), ("trace_alpha", trace_alpha, (P, S))):
+        if t.dtype != torch.float32 or t.device != dev:
+            raise TypeError(f"{name} must be a float32 tensor on {dev}")
+        if tuple(t.shape) != shape:
+            raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+    sat = -1.0 if transmittance_min is None else 1.0 - float(transmittance_min)
+    if P == 0:
+        out = torch.zeros(0, 16, device=dev)
+    else:
+        out = _ShadeIncident.apply(normals, azimuth, S, base_color, roughness, viewdirs, f(env_base), activation, transform,
+                                   f(trace_color).view(P * S, 3), f(trace_alpha).view(P * S), sat)
+    return {k: out[:, s] for k, s in OUT_SLICES.items()}
+
+
+def rendering_equation(base_color, roughness, normals, position, viewdirs, tracer, surfels, envmap, sample_num,
+                       training=False, azimuth=None, light_sample_num=0, light_t_min=0.05, alpha_min=1 / 255, deg=3,
+                       relight=False, wo_indirect=False, detach_indirect=False):
+    """gaussian_renderer/__init__.py:334-415.  `tracer` + `surfels` stand for the reference's `pc.trace`, `envmap` for
+    `pc.get_envmap`, sample_num / light_sample_num / light_t_min / wo_indirect / detach_indirect for the `pipe` fields of
+    the same names (arguments/__init__.py:92-101).  training=True draws the per-point random azimuth like
+    fibonacci_sphere_sampling(random_rotate=True) unless `azimuth` [P] is given."""
+    if relight or light_sample_num != 0 or sample_num <= 0:
+        raise NotImplementedError("only the diffuse_sample_num > 0, light_sample_num == 0, non-relight path is built")
+    P = base_color.shape[0]
+    if training and azimuth is None:
+        azimuth = torch.rand(P, device=normals.device) * (2 * math.pi)                   # graphics_utils.py:31
+    means3D, opacity, ru, rv, surf_normals, features, shs = surfels
+    color, _, _, _, alpha = tracer.trace_incident(position, normals, sample_num, means3D, opacity, ru, rv, surf_normals,
+                                                  features, shs, alpha_min, azimuth=azimuth, t_min=light_t_min, deg=deg)
+    if wo_indirect:
+        color = torch.zeros_like(color)                                                  # __init__.py:384-385
+    if detach_indirect:
+        color, alpha = color.detach(), alpha.detach()                                    # __init__.py:386-388
+    base, activation, transform = _env_fields(envmap)
+    out = shade_incident(normals, sample_num, base_color, roughness, viewdirs, base, color, alpha, azimuth=azimuth,
+                         activation=activation, transform=transform, transmittance_min=tracer.transmittance_min)
+    keys = ("diffuse", "specular", "light_direct") if training else tuple(OUT_SLICES)
+    return {k: out[k] for k in keys}

@@ -1,0 +1,137 @@
+"""CPU restatement of the reference's shading around the incident-ray trace -- TEST INFRASTRUCTURE ONLY (oracle/__init__.py).
+
+Differentiable torch code on the CPU (any dtype; the tests use float64 for gradient checks), each function citing the
+reference lines it follows (paths under /root/reference):
+
+  texture_linear_wrap   nvdiffrast.torch.texture(filter_mode='linear', boundary_mode='wrap')  -- the package (pinned by the
+                        reference's environment to nvdiffrast 0.3.x) is NOT in this image, so its published bilinear scheme
+                        (texture.cu: indexTextureLinear) is restated: texel centres at (i + 0.5) / size, wrap-around
+                        neighbours.  This one function is therefore "parity unpinned"; everything below it is pinned
+                        against golden vectors recorded from the UNMODIFIED reference functions with this lookup plugged
+                        in as `dr.texture` (tests/golden/ref_shading.npz, generator oracle/gen_golden_shading.py).
+  env_pure              scene/light.py:287-297,315   EnvLight.__call__(mode='pure_env')
+  normalise_trace       scene/gaussian_model.py:748-752   GaussianModel.trace post-processing of colour and alpha
+  ggx_specular          gaussian_renderer/__init__.py:417-457
+  rendering_equation    gaussian_renderer/__init__.py:334-415 (diffuse_sample_num > 0, light_sample_num == 0, relight=False)
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def texture_linear_wrap(tex, uv):
+    """tex [H, W, C], uv [..., 2] in texture units -> [..., C]."""
+    H, W = tex.shape[:2]
+    u, v = uv[..., 0], uv[..., 1]
+    u = u - torch.floor(u)
+    v = v - torch.floor(v)
+    u = u * W - 0.5
+    v = v * H - 0.5
+    iu0, iv0 = torch.floor(u).long(), torch.floor(v).long()
+    fu, fv = (u - iu0)[..., None], (v - iv0)[..., None]
+    iu1, iv1 = iu0 + 1, iv0 + 1
+    iu0 = torch.where(iu0 < 0, iu0 + W, iu0)
+    iv0 = torch.where(iv0 < 0, iv0 + H, iv0)
+    iu1 = torch.where(iu1 >= W, iu1 - W, iu1)
+    iv1 = torch.where(iv1 >= H, iv1 - H, iv1)
+    a00, a10, a01, a11 = tex[iv0, iu0], tex[iv0, iu1], tex[iv1, iu0], tex[iv1, iu1]
+    top = a00 + (a10 - a00) * fu
+    bot = a01 + (a11 - a01) * fu
+    return top + (bot - top) * fv
+
+
+ACTIVATIONS = {"exp": torch.exp, "sigmoid": torch.sigmoid, "none": lambda x: x}
+
+
+def env_pure(base, dirs, activation="exp", transform=None):
+    """light.py:287-297,315.  base [H,W,3] pre-activation, dirs [...,3] -> radiance [...,3]."""
+    l = dirs
+    if transform is not None:
+        l = l @ transform.T
+    uv = torch.cat([torch.atan2(l[..., :1], -l[..., 2:3]).nan_to_num() / (2.0 * math.pi) + 0.5,
+                    torch.acos(l[..., 1:2].clamp(-1.0 + 1e-6, 1.0 - 1e-6)) / math.pi], dim=-1).clamp(0, 1)
+    return ACTIVATIONS[activation](texture_linear_wrap(base, uv)).clamp_min(0.0)
+
+
+def normalise_trace(color, alpha, transmittance_min):
+    """gaussian_model.py:748-752.  color [...,3], alpha [...] raw tracer outputs."""
+    a_ = alpha[..., None]
+    sat = 1 - transmittance_min
+    color = torch.where(a_ < sat, color, color / a_)
+    alpha = torch.where(alpha < sat, alpha, torch.ones_like(alpha))
+    return color, alpha
+
+
+def ggx_specular(normal, pts2c, pts2l, roughness, fresnel):
+    """__init__.py:417-457 (out-of-place clamps: same values and gradients as the reference's clamp_)."""
+    L = F.normalize(pts2l, dim=-1)
+    V = F.normalize(pts2c, dim=-1)
+    H = F.normalize((L + V[:, None, :]) / 2.0, dim=-1)
+    N = F.normalize(normal, dim=-1)
+    NoV = torch.sum(V * N, dim=-1, keepdim=True)
+    N = N * NoV.sign()
+    NoL = torch.sum(N[:, None, :] * L, dim=-1, keepdim=True).clamp(1e-6, 1)
+    NoV = torch.sum(N * V, dim=-1, keepdim=True).clamp(1e-6, 1)
+    NoH = torch.sum(N[:, None, :] * H, dim=-1, keepdim=True).clamp(1e-6, 1)
+    VoH = torch.sum(V[:, None, :] * H, dim=-1, keepdim=True).clamp(1e-6, 1)
+    alpha = roughness * roughness
+    alpha2 = alpha * alpha
+    k = (alpha + 2 * roughness + 1.0) / 8.0
+    FMi = ((-5.55473) * VoH - 6.98316) * VoH
+    frac0 = fresnel + (1 - fresnel) * torch.pow(2.0, FMi)
+    frac = frac0 * alpha2[:, None, :]
+    nom0 = NoH * NoH * (alpha2[:, None, :] - 1) + 1
+    nom1 = NoV * (1 - k) + k
+    nom2 = NoL * (1 - k[:, None, :]) + k[:, None, :]
+    nom = (4 * math.pi * nom0 * nom0 * nom1[:, None, :] * nom2).clamp(1e-6, 4 * math.pi)
+    return frac / nom
+
+
+def rendering_equation(base_color, roughness, normals, viewdirs, incident_dirs, trace_color, trace_alpha, env_base,
+                       activation="exp", transform=None, transmittance_min=None):
+    """__init__.py:334-415 given the incident directions [P,S,3] and the tracer's RAW colour [P,S,3] / alpha [P,S] of those
+    rays (transmittance_min: GaussianModel.trace's normalisation, None to skip).  Returns the evaluation-mode dict (the
+    training-mode dict is its subset diffuse / specular / light_direct)."""
+    if transmittance_min is not None:
+        trace_color, trace_alpha = normalise_trace(trace_color, trace_alpha, transmittance_min)
+    global_incident_lights = env_pure(env_base, incident_dirs, activation, transform)
+    incident_visibility = 1 - trace_alpha[..., None]
+    local_incident_lights = trace_color
+    incident_lights = incident_visibility * global_incident_lights + local_incident_lights
+    incident_areas = 2 * math.pi                                   # graphics_utils.py:43
+    n_d_i = (normals[:, None] * incident_dirs).sum(-1, keepdim=True).clamp(min=0)
+    f_d = base_color[:, None] / math.pi
+    f_s = ggx_specular(normals, viewdirs, incident_dirs, roughness, fresnel=0.04)
+    transport = incident_lights * incident_areas * n_d_i
+    return {
+        "diffuse": (f_d * transport).mean(dim=-2),
+        "specular": (f_s * transport).mean(dim=-2),
+        "visibility": incident_visibility.mean(dim=1),
+        "light": incident_lights.mean(dim=1),
+        "light_indirect": local_incident_lights.mean(dim=1),
+        "light_direct": global_incident_lights.mean(dim=1),
+    }
+
+
+def fibonacci_dirs(normals, sample_num, azimuth=None):
+    """Differentiable torch restatement of utils/graphics_utils.py:19-47 + :133-165 (the numpy twin, pinned against the
+    reference's golden vectors, is oracle/incident.py)."""
+    P = normals.shape[0]
+    dt = normals.dtype
+    idx = torch.arange(sample_num, dtype=dt)[None]
+    z = (1 - 2 * idx / (2 * sample_num - 1)).clamp_min(math.sin(10 / 180 * math.pi))
+    rad = torch.sqrt(1 - z ** 2)
+    theta = math.pi * (3.0 - math.sqrt(5.0)) * idx
+    if azimuth is not None:
+        theta = azimuth.reshape(-1, 1).to(dt) + theta
+    zs = torch.stack([(torch.sin(theta) * rad).expand(P, sample_num), (torch.cos(theta) * rad).expand(P, sample_num),
+                      z.expand(P, sample_num)], -2)
+    v1, v2 = -normals[..., 1], normals[..., 0]
+    c = (normals[..., 2] + 1).clamp_min(1e-7)
+    R = torch.stack([1 + (-v2 * v2) / c, v1 * v2 / c, v2,
+                     v1 * v2 / c, 1 + (-v1 * v1) / c, -v1,
+                     -v2, v1, 1 + (-v2 * v2 - v1 * v1) / c], -1).reshape(P, 3, 3)
+    flip = -torch.eye(3, dtype=dt).expand(P, 3, 3)
+    R = torch.where((normals[..., 2] + 1 > 0)[:, None, None], R, flip)
+    return F.normalize(R @ zs, dim=-2).transpose(-1, -2)

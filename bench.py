@@ -57,15 +57,24 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
-    def start(self):
+    def start(self, wait_s=4.0):
+        """Starts nvidia-smi and waits for its first sample (it needs ~1 s to come up: a timed region shorter than that
+        would otherwise end before the first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < wait_s:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken from here on are the ones under load (the timed region starts now)."""
+        self.first = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -76,7 +85,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        lines = self.lines[self.first:] or self.lines
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -248,6 +258,8 @@ def run_ours(args):
     profiling = os.environ.get("IRGS_BENCH_PROFILE") == "1"   # ncu --profile-from-start off: only the timed region
     if profiling:
         torch.cuda.profiler.start()
+    if rank == 0:
+        clocks.mark()
     t0.record()
     for _ in range(args.steps):
         grads = step(True)
@@ -511,6 +523,7 @@ def run_reference(args):
         torch.cuda.synchronize()
         clocks = ClockSampler(0)
         clocks.start()
+        clocks.mark()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.steps):

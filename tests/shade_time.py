@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 14)
     ap.add_argument("--spp", type=int, default=256)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--profile", action="store_true",
+                    help="one forward + backward between cudaProfilerStart/Stop (for ncu --profile-from-start off), no timing")
     a = ap.parse_args()
     from irgs_b200 import shading
     from irgs_b200.incident import incident_dirs
@@ -65,6 +67,14 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / a.iters
 
+    if a.profile:
+        ours(True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        ours(True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     res = {"points": P, "spp": S, "rays": P * S}
     for name, fn in (("kernels", ours), ("torch_eager", eager)):
         f = timeit(fn, False)

@@ -79,7 +79,8 @@ def test_env_lookup_forward_backward_against_the_oracle():
         assert out.shape == (100, 200, 3)
         (out * w.to(DEV).view(100, 200, 3)).sum().backward()
         # float32 atan2 / acos against float64: a texel-boundary crossing can move single samples, so medians + tails
-        err = (out.detach().cpu().view(-1, 3).double() - ref.detach()).abs()
+        ref = ref.detach()
+        err = (out.detach().cpu().view(-1, 3).double() - ref).abs()
         assert err.median() <= 1e-6 and (err > 1e-3 * max(1.0, float(ref.abs().max()))).float().mean() < 2e-3
         _close(env.base.grad, bo.grad, f"texels {act}", tol=2e-3, cos_min=0.99999)
         gd, gr = dg.grad.cpu().double(), do.grad
@@ -158,6 +159,9 @@ def test_rendering_equation_end_to_end_against_the_unfused_composition(small_sce
         bf = torch.nan_to_num(b.double().flatten(), 0.0, 0.0, 0.0)     # the un-fused torch path back-propagates 0/0 at alpha == 0
         af = a.double().flatten()
         assert torch.isfinite(af).all(), k
+        if float(bf.norm()) == 0.0:                 # e.g. `features`: the rendering equation does not read the feature output
+            assert float(af.norm()) == 0.0, k
+            continue
         cos = float(af @ bf / (af.norm() * bf.norm() + 1e-300))
         # ulp-level direction differences move individual threshold decisions of the tracer: cosine is the criterion
         assert cos >= 0.9999, (k, cos)

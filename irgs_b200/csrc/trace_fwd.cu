@@ -60,6 +60,13 @@ constexpr bool LEAF_2STAGE = IRGS_LEAF_2STAGE != 0;
 #define IRGS_COMP_MIN 24
 #endif
 constexpr int COMP_MIN = IRGS_COMP_MIN;   // candidates that must be waiting before a packed compositing round is run
+#ifndef IRGS_DRAIN_MAX
+#define IRGS_DRAIN_MAX 8
+#endif
+constexpr int DRAIN_MAX = IRGS_DRAIN_MAX;   // drain: at most this many walking lanes per warp -> co-operative wide walk (0: off)
+constexpr int DRAIN_G = 4;                  // lanes (= node visits in flight) per walking ray in the wide walk
+static_assert(DRAIN_MAX * DRAIN_G <= 32, "one group of DRAIN_G lanes per walking ray");
+constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide walk accepts: sp + 3 G + 1 <= SSTK entries afterwards
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -131,7 +138,13 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         const int thr = pool_empty ? 1 : MIN_ACTIVE;
         unsigned walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
         // (a node visit can queue four leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
+        bool wide = false;
         while (__popc(walking) >= thr && walking != 0u && !__any_sync(FULL, pn > PQ - 4)) {
+            if (DRAIN_MAX > 0 && pool_empty && __popc(walking) <= DRAIN_MAX &&
+                !__any_sync(FULL, phase == PH_TRAV && cur != CUR_NONE && sp > DRAIN_SP_MAX)) {
+                wide = true;   // the drain of the launch: few long rays left in this warp, see below
+                break;
+            }
             if (phase == PH_TRAV && cur != CUR_NONE) {
                 // one 4-wide node: two 256-bit loads from one 64-byte line, four slab tests
                 uint4 c[4];
@@ -169,6 +182,80 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 cur = next;
             }
             walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
+        }
+
+        // ------------------------------------------------------------------ BVH walk, co-operative wide step (drain)
+        // At the end of a launch (work pool empty) a warp is left with a few long rays -- rays that run inside the surfel
+        // layer visit thousands of nodes -- and every visit is a dependent L2 access of ONE lane while the others idle:
+        // the launch cannot end before its slowest ray (2^14 rays took 0.93 ms, nearly all of it
+        // this tail).  Here the idle lanes help: every walking ray gets a group of DRAIN_G lanes which take its current
+        // node and the top DRAIN_G - 1 entries of its stack (shared memory), test their four children each against the
+        // owner's ray (constants through shuffles) and push the hits back onto the OWNER's stack / leaf queue at offsets
+        // from a prefix sum over the group.  Up to DRAIN_G node fetches of one ray are in flight at once.  The walk is no
+        // longer strictly near-first, which does not change results: a pass visits everything inside its depth window
+        // whatever the order, and rows are ordered by (t, id) before they are composited.
+        if (wide) {
+            __syncwarp();   // the owners' stack and queue columns are read and written by their helpers
+            const int grp = (int)lane / DRAIN_G, mi = (int)lane % DRAIN_G;
+            const int n_own = __popc(walking);
+            const int owner = grp < n_own ? (int)__fns(walking, 0, grp + 1) : (int)lane;
+            const int o_cur = __shfl_sync(FULL, cur, owner), o_sp = __shfl_sync(FULL, sp, owner);
+            const int o_pn = __shfl_sync(FULL, pn, owner);
+            // nodes this group takes: the current one + stack entries, as many as the leaf queue has room for (4 leaves each)
+            const int k_grp = min(min(DRAIN_G, 1 + o_sp), (PQ - o_pn) >> 2);
+            const bool work = grp < n_own && mi < k_grp;
+            RayCtx ro;
+            ro.ax = __shfl_sync(FULL, r.ax, owner); ro.ay = __shfl_sync(FULL, r.ay, owner); ro.az = __shfl_sync(FULL, r.az, owner);
+            ro.bx = __shfl_sync(FULL, r.bx, owner); ro.by = __shfl_sync(FULL, r.by, owner); ro.bz = __shfl_sync(FULL, r.bz, owner);
+            const float o_tlo = __shfl_sync(FULL, t_lo, owner), o_thi = __shfl_sync(FULL, t_hi, owner);
+            unsigned in_mask = 0u, lf_mask = 0u;
+            int ref[4] = {0, 0, 0, 0};
+            if (work) {
+                const int node = mi == 0 ? o_cur : ws.stack[(o_sp - mi) * 32 + owner];
+                uint4 c[4];
+                ldg256(&p.nodes4[node].c[0], c[0], c[1]);
+                ldg256(&p.nodes4[node].c[2], c[2], c[3]);
+                if (STATS) ++st_nodes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float tn;
+                    const bool hit = slab(ro, c[k], o_tlo, o_thi, tn);
+                    ref[k] = (int)c[k].w;
+                    if (hit && ref[k] >= 0) in_mask |= 1u << k;
+                    if (hit && ref[k] < 0) lf_mask |= 1u << k;
+                }
+            }
+            // inclusive prefix sums of the push counts over the DRAIN_G lanes of a group
+            int in_incl = __popc(in_mask), lf_incl = __popc(lf_mask);
+#pragma unroll
+            for (int o = 1; o < DRAIN_G; o <<= 1) {
+                const int vi = __shfl_up_sync(FULL, in_incl, o, DRAIN_G), vl = __shfl_up_sync(FULL, lf_incl, o, DRAIN_G);
+                if (mi >= o) { in_incl += vi; lf_incl += vl; }
+            }
+            __syncwarp();   // every helper has read its stack entry before anything is pushed
+            if (work) {
+                const int s0 = o_sp - (k_grp - 1) + in_incl - __popc(in_mask);   // the group popped k_grp - 1 entries
+                const int q0 = o_pn + lf_incl - __popc(lf_mask);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((in_mask >> k) & 1u) ws.stack[(s0 + __popc(in_mask & ((1u << k) - 1u))) * 32 + owner] = ref[k];
+                    if ((lf_mask >> k) & 1u) ws.pend[(q0 + __popc(lf_mask & ((1u << k) - 1u))) * 32 + owner] = ref[k];
+                }
+            }
+            // the owners take the totals of their group (held by its last lane) and pop the next node
+            const bool own = phase == PH_TRAV && cur != CUR_NONE;
+            const int my_grp_last = own ? __popc(walking & lt_mask) * DRAIN_G + DRAIN_G - 1 : (int)lane;
+            const int tot_in = __shfl_sync(FULL, in_incl, my_grp_last), tot_lf = __shfl_sync(FULL, lf_incl, my_grp_last);
+            __syncwarp();   // pushes are visible to the owners
+            if (own) {
+                const int k_own = min(min(DRAIN_G, 1 + sp), (PQ - pn) >> 2);
+                if (k_own >= 1) {
+                    sp = sp - (k_own - 1) + tot_in;
+                    pn += tot_lf;
+                    if (sp > 0) { --sp; cur = stk[sp * 32]; }
+                    else cur = CUR_NONE;
+                }
+            }
         }
 
         // ------------------------------------------------------------------ BVH walk, LEAF sub-phase

@@ -210,6 +210,8 @@ int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const 
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
  * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.
+ * "stride_rays_max": forward calls with at most this many rays (default and upper limit 2^19) start their rays in a stride
+ * order instead of the caller's order (latency of small calls; 0 disables).
  * "slot": 0 (default) or 1 -- calls issued on two different streams at the same time must use different slots (each slot has
  * its own persistent-kernel work counter and candidate scratch).
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.

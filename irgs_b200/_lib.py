@@ -57,8 +57,11 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.LIB
+    override = os.environ.get("IRGS_LIB")   # tuning experiments only: an alternative build of the same sources
+    if override:
+        path = override
     try:
-        if _build.needs_build():
+        if not override and _build.needs_build():
             _build.build()
     except Exception as e:  # nvcc missing on a box that only has the prebuilt .so is fine; a missing .so is not
         if not os.path.exists(path):

@@ -453,6 +453,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
         return 0;
     }
+    if (strcmp(name, "stride_rays_max") == 0) {
+        h->stride_rays_max = value < 0 ? 0 : value;
+        return 0;
+    }
     if (strcmp(name, "slot") == 0) {   // which of the two work-counter / scratch sets the following device-path calls use
         h->slot_default = value == 1 ? 1 : 0;
         h->slot = h->slot_default;

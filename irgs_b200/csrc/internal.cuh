@@ -94,6 +94,7 @@ struct irgs_tracer {
     int *rsort_vals[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int *rsort_hist[2] = {nullptr, nullptr};
     int64_t rsort_cap[2] = {0, 0};
+    int64_t stride_rays_max = 1 << 19;      // forward calls with at most this many rays start them in a stride order (0: never)
     int sort_rays_min = 0;                  // forward calls with at least this many rays are coherence-sorted (0: never;
                                             // measured on B200: the sort costs more than it saves, profiles/r01_notes.md)
     unsigned long long *stats = nullptr;    // [4]
@@ -144,6 +145,8 @@ struct TraceArgs {
     int gen_S;
     float gen_tmin;
     const int *ray_order;  // forward: optional processing order (coherence sort); results are still written per ray id
+    int64_t ray_mul;       // forward: 0, or an odd multiplier coprime to n_rays (n_rays <= 2^19): the i-th ray started is (i * ray_mul) % n_rays
+                           // (small launches: spreads the heavy rays of one pixel bundle over the warps, launch_trace_forward)
     // backward
     const float *gC, *gN, *gF, *gD, *gO;
     int64_t gout_period;  // 0: gout arrays have n_rays rows; >0: ray r reads row (gout_offset + r) % period

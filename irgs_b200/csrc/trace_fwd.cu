@@ -61,11 +61,12 @@ constexpr bool LEAF_2STAGE = IRGS_LEAF_2STAGE != 0;
 #endif
 constexpr int COMP_MIN = IRGS_COMP_MIN;   // candidates that must be waiting before a packed compositing round is run
 #ifndef IRGS_DRAIN_MAX
-#define IRGS_DRAIN_MAX 8
+#define IRGS_DRAIN_MAX 0   // measured (profiles/r01_sweeps.txt): 8 makes a 2^14-ray call 10 % faster, 2^18 rays unchanged, the C3 step 2.5 % slower
 #endif
 constexpr int DRAIN_MAX = IRGS_DRAIN_MAX;   // drain: at most this many walking lanes per warp -> co-operative wide walk (0: off)
 constexpr int DRAIN_G = 4;                  // lanes (= node visits in flight) per walking ray in the wide walk
 static_assert(DRAIN_MAX * DRAIN_G <= 32, "one group of DRAIN_G lanes per walking ray");
+static_assert(DRAIN_MAX >= 0, "0 compiles the wide walk out");
 constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide walk accepts: sp + 3 G + 1 <= SSTK entries afterwards
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 ray = (int64_t)base + __popc(need & lt_mask);
                 if (ray < a.n_rays) {
                     if (a.ray_order != nullptr) ray = __ldg(a.ray_order + ray);
+                    else if (a.ray_mul != 0) ray = (int64_t)(((unsigned)ray * (unsigned)a.ray_mul) % (unsigned)a.n_rays);   // < 2^32
                     load_ray(a, ray, r);
                     ray_setup(r, p.qframe);
                     T = 1.f;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         // from a prefix sum over the group.  Up to DRAIN_G node fetches of one ray are in flight at once.  The walk is no
         // longer strictly near-first, which does not change results: a pass visits everything inside its depth window
         // whatever the order, and rows are ordered by (t, id) before they are composited.
-        if (wide) {
+        while (wide) {
             __syncwarp();   // the owners' stack and queue columns are read and written by their helpers
             const int grp = (int)lane / DRAIN_G, mi = (int)lane % DRAIN_G;
             const int n_own = __popc(walking);
@@ -256,6 +258,10 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     else cur = CUR_NONE;
                 }
             }
+            // next wide step unless a leaf queue is about to fill up (LEAF sub-phase first) or the walks are done
+            walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
+            wide = walking != 0u && !__any_sync(FULL, pn > PQ - 4) &&
+                   !__any_sync(FULL, phase == PH_TRAV && cur != CUR_NONE && sp > DRAIN_SP_MAX);
         }
 
         // ------------------------------------------------------------------ BVH walk, LEAF sub-phase
@@ -594,6 +600,19 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
         int *order = nullptr;
         if (launch_ray_order(h, a.rays_o, a.rays_d, a.n_rays, &order, s)) return 1;
         p.a.ray_order = order;
+    }
+    // Small launches are latency bound: the call ends with its slowest warp, and the heavy rays (grazing samples that run
+    // inside the surfel layer: ~300 node visits, ~40 hits, several passes) come clustered -- the caller lays rays out
+    // bundle by bundle, so a grazing pixel puts many of them into the same warp, where their phases serialise.  Starting
+    // the rays in a stride order (the i-th ray started is (i * m) mod n, m odd and coprime to n) spreads them over the
+    // warps: 2^12 / 2^14 / 2^16 / 2^18 / 2^19 rays 0.84 / 0.92 / 1.01 / 1.14 / 1.41 ms -> 0.62 / 0.63 / 0.73 / 1.00 / 1.36 ms
+    // (scripts/stride_check.py); from 2^20 rays on throughput counts and the orders tie (2.19 ms), so large launches keep
+    // the caller's order.  Results are written per ray id either way.
+    if (p.a.ray_order == nullptr && a.n_rays >= 64 && a.n_rays <= h->stride_rays_max && a.n_rays <= ((int64_t)1 << 19)) {
+        int64_t m = 5063;   // odd, ~0.618 * 2^13: consecutive starts are ~20 pixel bundles apart; i * m < 2^32 for i < 2^19
+        auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
+        while (gcd(m, a.n_rays) != 1) m += 2;
+        p.a.ray_mul = m;
     }
     // rays that hit nothing are never written by the kernel
     const size_t R = (size_t)a.n_rays;

@@ -761,3 +761,23 @@ def test_full_size_properties():
     assert float((g2 - 2 * g1).abs().max()) <= 1e-3 * float(g1.abs().max())
     (gro,) = torch.autograd.grad(outs[3].sum(), ro)
     assert not gro[a["hit_count"][: 1 << 18] == 0].any()
+
+
+def test_start_order_of_small_launches_does_not_change_results(small_scene):
+    """Launches of up to 2^19 rays start their rays in a stride order (latency: the heavy rays of one pixel bundle are spread
+    over the warps); larger launches, and launches with the option switched off, keep the caller's order.  Outputs and hit
+    lists are bit-identical either way."""
+    sc, inp = small_scene
+    o, d = _rays(inp, "secondary")
+    g = _gpu(inp)
+    tr = _tracer(g, hit_cap=96)
+    args = (g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], g["features"], g["shs"], synth.ALPHA_MIN)
+    res = []
+    for limit in (1 << 19, 0, 100):      # on (default) / off / below this call's size: off
+        tr.set_option("stride_rays_max", limit)
+        res.append(tr.trace_with_hits(o.to(DEV), d.to(DEV), *args))
+    tr.set_option("stride_rays_max", 1 << 19)
+    assert o.shape[0] > 100 and float((res[0]["hit_count"] > 0).float().mean()) > 0.2
+    for other in res[1:]:
+        for k in res[0]:
+            assert torch.equal(res[0][k], other[k]), k

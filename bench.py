@@ -42,6 +42,7 @@ def parse():
                    help="consecutive chunks alternate between this many CUDA streams (2: the drain of one persistent kernel "
                         "overlaps the next chunk)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--e2e-chunk", type=int, default=0, help="rays per chunk of the host-buffer path (0: chosen from the shard size)")
     p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
     p.add_argument("--no-shade", action="store_true", help="skip the rendering-equation measurement (fused generation + shading epilogue)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -390,6 +391,8 @@ def run_ours(args):
         # chunk of the host-buffer path: large enough to amortise the drain of the persistent kernels, small enough that the
         # un-overlapped first copy stays a small part of the step (at least ~8 chunks per rank)
         e2e_chunk = min(1 << 23, max(1 << 21, 1 << max(0, (n_local // 8).bit_length() - 1)), n_local)
+        if args.e2e_chunk > 0:
+            e2e_chunk = min(args.e2e_chunk, n_local)
         ge = make_gout(e2e_chunk, device)
 
         def e2e_step():

@@ -106,6 +106,12 @@ struct irgs_tracer {
     cudaEvent_t hev[2] = {nullptr, nullptr};
     float *stage[2] = {nullptr, nullptr};
     int64_t stage_floats = 0;
+    // ring of ray buffers filled by a dedicated copy stream, so that host->device copies run ahead of the two compute streams
+    static constexpr int RING = 4;
+    cudaStream_t hcopy = nullptr;
+    float *ring[RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ring_full[RING] = {nullptr, nullptr, nullptr, nullptr}, ring_free[RING] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t ring_floats = 0;
 };
 
 namespace irgs {

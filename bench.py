@@ -364,6 +364,7 @@ def run_ours(args):
             genv = env.base.grad
             for t in (pts_l, nrm_l, base_color, rough, env.base):
                 t.grad = None
+            parallel.allreduce_sum_(genv)   # the environment map is replicated like the surfels: 1.5 MB more to reduce
             return tracer.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape)), genv
 
         for _ in range(min(args.warmup, 2)):

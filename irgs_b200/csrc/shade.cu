@@ -87,7 +87,11 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
 // g_out [P,16] in the layout of the forward's rows.  Per ray: g_color [P*S,3], g_alpha [P*S] (overwritten).  Per point:
 // g_point [P,16]: 0-2 dL/dbase_color, 3 dL/droughness, 4-6 dL/dnormal, 7-9 dL/dviewdirs (overwritten).  Texel gradients
 // are ADDED into grad_env [H,W,3] (may be null).
-__global__ void __launch_bounds__(128) shade_backward_kernel(ShadeArgs a, const float *__restrict__ g_out,
+#ifndef IRGS_SHADE_BWD_BLOCKS
+#define IRGS_SHADE_BWD_BLOCKS 4   // resident blocks per SM the register budget is set for.  Measured forward+backward per 2^22 rays:
+                                  // no cap (135 registers, 3 blocks) 0.668 ms | 4 (128 registers, no spills) 0.614 | 5 (96 registers, spills) 0.634
+#endif
+__global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_kernel(ShadeArgs a, const float *__restrict__ g_out,
                                                              float *__restrict__ g_color, float *__restrict__ g_alpha,
                                                              float *__restrict__ g_point, float *__restrict__ grad_env) {
     const int64_t pt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -188,6 +188,8 @@ def cpu_baseline(S, rays_o, rays_d, seconds):
 def run_ours(args):
     from irgs_b200 import _lib, parallel, synth
     from irgs_b200.raytracer import GaussianTracer, _ptr
+    # NCCL's own log lines (e.g. "NCCL version ..." when NCCL_DEBUG is set on the box) go to stderr: stdout carries the JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, local, world = parallel.init_from_env()
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)

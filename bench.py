@@ -41,6 +41,8 @@ def parse():
     p.add_argument("--streams", type=int, default=2, choices=[1, 2],
                    help="consecutive chunks alternate between this many CUDA streams (2: the drain of one persistent kernel "
                         "overlaps the next chunk)")
+    p.add_argument("--carveout", type=int, default=-1, help="experiments: shared-memory carve-out hint of the forward kernel in percent")
+    p.add_argument("--bwd-carveout", type=int, default=-1, help="experiments: the same for the backward replay kernel")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--e2e-chunk", type=int, default=0, help="rays per chunk of the host-buffer path (0: chosen from the shard size)")
     p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
@@ -198,6 +200,10 @@ def run_ours(args):
     def factory(sc, inp):
         tr = GaussianTracer(transmittance_min=synth.T_MIN, device=device)
         tr.build_from_surfels(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], synth.ALPHA_MIN)
+        if args.carveout >= 0:
+            tr.set_option("smem_carveout_pct", args.carveout)
+        if args.bwd_carveout >= 0:
+            tr.set_option("bwd_carveout_pct", args.bwd_carveout)
         return tr
 
     sc, inp, tracer, rays_o, rays_d = build_workload(args, device, rank, world, factory)

@@ -485,6 +485,14 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->sort_rays_min = value < 0 ? 0 : (value > INT32_MAX ? INT32_MAX : (int)value);
         return 0;
     }
+    if (strcmp(name, "bwd_carveout_pct") == 0) {
+        h->bwd_carveout_pct = value < 0 ? -1 : (value > 100 ? 100 : (int)value);
+        return 0;
+    }
+    if (strcmp(name, "smem_carveout_pct") == 0) {
+        h->carveout_pct = value < 0 ? -1 : (value > 100 ? 100 : (int)value);
+        return 0;
+    }
     if (strcmp(name, "stride_rays_max") == 0) {
         h->stride_rays_max = value < 0 ? 0 : value;
         return 0;

@@ -94,6 +94,8 @@ struct irgs_tracer {
     int *rsort_vals[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int *rsort_hist[2] = {nullptr, nullptr};
     int64_t rsort_cap[2] = {0, 0};
+    int bwd_carveout_pct = -1;              // backward replay kernel: carve-out hint in percent (-1: the driver's default)
+    int carveout_pct = -1;                  // forward kernel: shared-memory carve-out hint in percent (-1: what the resident blocks need)
     int64_t stride_rays_max = 1 << 19;      // forward calls with at most this many rays start them in a stride order (0: never)
     int sort_rays_min = 0;                  // forward calls with at least this many rays are coherence-sorted (0: never;
                                             // measured on B200: the sort costs more than it saves, profiles/r01_notes.md)

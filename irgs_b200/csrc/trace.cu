@@ -829,6 +829,13 @@ static int launch_persistent(irgs_tracer *h, Kern kern, const KParams &p, int64_
     return 0;
 }
 
+// Shared-memory carve-out hint for the replay kernel (irgs_set_option("bwd_carveout_pct"); -1 = the driver's default, which
+// measured best: see launch_fwd in trace_fwd.cu).
+template <typename Kern>
+static void set_carveout(Kern kern, int pct) {
+    if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+}
+
 int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p = make_params(h, a);
     const bool feat = a.S > 0;
@@ -842,8 +849,13 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
                 if (feat) trace_backward_flat_kernel<true, false><<<grid, TB, 0, s>>>(p);
                 else trace_backward_flat_kernel<false, false><<<grid, TB, 0, s>>>(p);
             } else {
-                if (feat) trace_backward_flat_kernel<true, true><<<grid, TB, 0, s>>>(p);
-                else trace_backward_flat_kernel<false, true><<<grid, TB, 0, s>>>(p);
+                if (feat) {
+                    set_carveout(trace_backward_flat_kernel<true, true>, h->bwd_carveout_pct);
+                    trace_backward_flat_kernel<true, true><<<grid, TB, 0, s>>>(p);
+                } else {
+                    set_carveout(trace_backward_flat_kernel<false, true>, h->bwd_carveout_pct);
+                    trace_backward_flat_kernel<false, true><<<grid, TB, 0, s>>>(p);
+                }
             }
         }
         count_launch();

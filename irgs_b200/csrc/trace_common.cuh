@@ -35,10 +35,35 @@ struct KParams {
 
 // 256-bit read-only loads (sm_100a: LDG.E.256): a 32-byte quantised node or half a surfel record in ONE request.  The
 // walk is bound by the L1TEX data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 73 % of peak), not by DRAM or L2.
+#ifndef IRGS_NODE_HINT
+#define IRGS_NODE_HINT 1   // 1: tree nodes are loaded with L1::evict_last (C3 step 617 -> 619 M rays/s), 0: no hint
+#endif
 __device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+#if IRGS_NODE_HINT
+    asm("ld.global.nc.L1::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(p));
+#else
     asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
         : "l"(p));
+#endif
+}
+// The same load for STREAMING data (surfel records, SH rows: read once per use, no reuse worth caching): no L1 allocation, so
+// that the small L1 (what the shared-memory carve-out leaves) keeps the top levels of the tree.  IRGS_STREAM_HINT=0: plain.
+#ifndef IRGS_STREAM_HINT
+#define IRGS_STREAM_HINT 1
+#endif
+__device__ __forceinline__ void ldg256_stream(const void *p, float4 &a, float4 &b) {
+#if IRGS_STREAM_HINT
+    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+#else
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+#endif
 }
 __device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -88,7 +113,7 @@ __device__ __forceinline__ void sh_color(const float *__restrict__ shs, int K, i
         for (int v = 0; v < 12; v += 2) {
             if (v < nvec) {
                 float4 q, q2;
-                if (wide) ldg256(p + v, q, q2);
+                if (wide) ldg256_stream(p + v, q, q2);
                 else { q = __ldg(p + v); q2 = __ldg(p + v + 1); }
                 acc[(4 * v) % 3] += Y[(4 * v) / 3] * q.x;
                 acc[(4 * v + 1) % 3] += Y[(4 * v + 1) / 3] * q.y;

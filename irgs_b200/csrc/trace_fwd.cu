@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 int leaf = 0;
                 if (has) {
                     leaf = ~ws.pend[(o_pn - 1 - (idx - o_start)) * 32 + owner];   // popped from the top
-                    ldg256(p.recs + leaf, q0, q1);
-                    if (!LEAF_2STAGE) ldg256(&p.recs[leaf].r2, q2, q3);
+                    ldg256_stream(p.recs + leaf, q0, q1);
+                    if (!LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, q2, q3);
                     if (STATS) ++st_leaf;
                 }
                 RayCtx ro;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 if (ok) {
                     // fetching the second half of the record only now saves L1TEX wavefronts but serialises two L2
                     // latencies: measured 2 % slower than issuing both loads up front (profiles/r01_sweeps.txt)
-                    if (LEAF_2STAGE) ldg256(&p.recs[leaf].r2, q2, q3);
+                    if (LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, q2, q3);
                     ok = leaf_stage2(q2, q3, px, py, pz, alpha_min, alpha);
                 }
                 const unsigned acc = __ballot_sync(FULL, ok);
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     else if (ch == 6) dst = a.depth + rr;
                     else if (ch == 7) dst = a.alpha + rr;
                     else dst = a.feature + rr * a.S + (ch - 8);
-                    float accv = *dst;
+                    float accv = *dst;   // (L2-only __ldcg / __stcg here measured 12 % SLOWER on the C3 step: profiles/r01_sweeps.txt)
                     for (int i = 0; i < nc; ++i) accv += s_c[ch * 32 + lo + i];
                     *dst = accv;
                 }

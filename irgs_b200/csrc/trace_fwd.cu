@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 // per-segment table, written by the first lane of each segment
                 if (act && k == 0) {
                     const int sidx = __popc(gmask & ((1u << owner) - 1u));
-                    ws.seg_lo[sidx] = seg_lo; ws.seg_nc[sidx] = term ? -n_comp : n_comp; ws.seg_T[sidx] = Tc;
+                    // bit 8: nothing of this ray has been composited yet (98 % of the rays that hit anything need one pass)
+                    ws.seg_lo[sidx] = seg_lo | (total_o == 0 ? 256 : 0); ws.seg_nc[sidx] = term ? -n_comp : n_comp; ws.seg_T[sidx] = Tc;
                     ws.seg_ray[sidx] = ray_o;
                 }
                 __syncwarp();
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 const int pairs = __popc(gmask) * n_ch;
                 for (int pr = (int)lane; pr < pairs; pr += 32) {
                     const int sidx = pr / n_ch, ch = pr - sidx * n_ch;
-                    const int lo = ws.seg_lo[sidx], nc = abs(ws.seg_nc[sidx]);
+                    const int slo = ws.seg_lo[sidx], lo = slo & 255, nc = abs(ws.seg_nc[sidx]);
                     const int64_t rr = ws.seg_ray[sidx];
                     float *dst;
                     if (ch < 3) dst = a.color + 3 * rr + ch;
@@ -538,7 +539,9 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     else if (ch == 6) dst = a.depth + rr;
                     else if (ch == 7) dst = a.alpha + rr;
                     else dst = a.feature + rr * a.S + (ch - 8);
-                    float accv = *dst;   // (L2-only __ldcg / __stcg here measured 12 % SLOWER on the C3 step: profiles/r01_sweeps.txt)
+                    // the outputs are pre-zeroed: a ray's first pass adds to 0 without reading them back (a dependent L2 access)
+                    // (L2-only __ldcg / __stcg here measured 12 % SLOWER on the C3 step: profiles/r01_sweeps.txt)
+                    float accv = (slo & 256) ? 0.f : *dst;
                     for (int i = 0; i < nc; ++i) accv += s_c[ch * 32 + lo + i];
                     *dst = accv;
                 }

@@ -6,6 +6,8 @@ Mirrors scene/gaussian_model.py:712-756 of the reference:
   * `SurfelScene.build / refit` :725-731 (get_boundings + build_bvh / update_bvh) -- here the bounds are derived
     analytically from the parameters by the native library, no 12N-vertex proxy mesh is materialised
   * `SurfelScene.trace` :733-765 incl. the normalisation by alpha where alpha >= 1 - T_min (:751-756)
+  * `SurfelScene.rendering_equation`: the reference's rendering_equation (gaussian_renderer/__init__.py:334-415) from the
+    same parameters -- incident rays generated in the kernels, traced, shaded by the epilogue kernels (irgs_b200/shading.py)
 Everything between the parameters and the tracer is plain differentiable torch, so gradients reach scales and
 rotations (quaternions) through autograd exactly as they do in IRGS.
 """
@@ -82,3 +84,18 @@ class SurfelScene:
             alpha = torch.where(sat, torch.ones_like(alpha), alpha)
         return dict(color=color, normal=normal, feature=feature, depth=depth, alpha=alpha, hit_count=hit_count,
                     normals=normals)
+
+    def rendering_equation(self, base_color, roughness, normals_pt, position, viewdirs, means, scales, rotations, opacities,
+                           shs, envmap, sample_num, training=False, azimuth=None, camera_center=None, deg=3,
+                           light_t_min=0.05, wo_indirect=False, detach_indirect=False):
+        """The reference's `rendering_equation(base_color, roughness, normals, position, viewdirs, pc, pipe, training)` with
+        `pc` spelled out as its parameters: dict(diffuse, specular, light_direct) when training, plus visibility, light and
+        light_indirect otherwise.  Differentiable w.r.t. the shading-point inputs, the environment texels and the surfel
+        parameters (scales and rotations included)."""
+        from . import shading
+        ru, rv, normals = surfel_frames(means, scales, rotations, camera_center)
+        return shading.rendering_equation(base_color, roughness, normals_pt, position, viewdirs, self.tracer,
+                                          (means, opacities, ru, rv, normals, None, shs), envmap, sample_num,
+                                          training=training, azimuth=azimuth, light_t_min=light_t_min,
+                                          alpha_min=self.alpha_min, deg=deg, wo_indirect=wo_indirect,
+                                          detach_indirect=detach_indirect)

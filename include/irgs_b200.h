@@ -184,23 +184,36 @@ typedef struct {
     float transform[9];      /* row-major 3x3: lookup direction = d @ transform^T (light.py:299-300) */
 } irgs_envmap_t;
 
+/* The light_sample_num > 0 branch (gaussian_renderer/__init__.py:340-357): Fibonacci samples mixed with directions drawn
+ * from the environment map (EnvLight.sample_light_directions, scene/light.py:181-205).  One shade call per kind of sample;
+ * every sample is weighted by 1 / clamp_min(p_diffuse / (2 pi) + p_light * light_pdf(dir), 1e-6) with light_pdf =
+ * EnvLight.light_pdf (light.py:207-223), and the means run over total_samples = diffuse + light samples, so that the
+ * [P,16] rows of the two calls ADD UP to rendering_equation's result.  Pass NULL for pure Fibonacci sampling. */
+typedef struct {
+    const float *dirs;       /* [P*S,3] explicit unit directions of this call's samples (the light samples), or NULL: generated */
+    const float *pdf;        /* [H,W] texel probabilities (EnvLight._pdf after update_pdf), or NULL: weight 2 pi */
+    float p_diffuse, p_light;   /* diffuse_sample_num / (diffuse + light), light_sample_num / (diffuse + light) */
+    int32_t total_samples;   /* diffuse + light samples: the divisor of the means */
+} irgs_shade_sampling_t;
+
 /* trace_color [P*S,3], trace_alpha [P*S]: outputs of irgs_trace_forward_incident for the same `gen`.  saturate_alpha =
  * 1 - transmittance_min applies GaussianModel.trace's normalisation of saturated rays (scene/gaussian_model.py:748-752:
  * colour / alpha and alpha = 1 where alpha >= 1 - transmittance_min); a negative value skips it.  base_color [P,3],
  * roughness [P], viewdirs [P,3] (any length).  gen->position is not used.
  * out [P,16], means over the S samples: 0-2 diffuse, 3-5 specular, 6-8 light_direct, 9 visibility, 10-12 light,
  * 13-15 light_indirect (the keys of rendering_equation's result dict, __init__.py:399-414). */
-int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
-                       const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
-                       float *out, void *stream);
+int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, const irgs_shade_sampling_t *sampling,
+                       const float *base_color, const float *roughness, const float *viewdirs, const float *trace_color,
+                       const float *trace_alpha, float saturate_alpha, float *out, void *stream);
 /* g_out [P,16] in the layout of `out`.  OVERWRITTEN: g_trace_color [P*S,3], g_trace_alpha [P*S] (the gradients to hand to
  * irgs_trace_backward_incident as gout_color / gout_alpha) and g_point [P,16]: 0-2 dL/dbase_color, 3 dL/droughness,
  * 4-6 dL/dnormal (n_d_i, the GGX normal AND the dependence of the sampled directions on the normal through
- * rotation_between_z), 7-9 dL/dviewdirs.  Texel gradients are ADDED (atomically) into grad_env [H,W,3] (may be NULL). */
-int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
-                        const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
-                        const float *g_out, float *g_trace_color, float *g_trace_alpha, float *g_point, float *grad_env,
-                        void *stream);
+ * rotation_between_z; explicit directions are constants), 7-9 dL/dviewdirs.  Texel gradients are ADDED (atomically) into
+ * grad_env [H,W,3] (may be NULL). */
+int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, const irgs_shade_sampling_t *sampling,
+                        const float *base_color, const float *roughness, const float *viewdirs, const float *trace_color,
+                        const float *trace_alpha, float saturate_alpha, const float *g_out, float *g_trace_color,
+                        float *g_trace_alpha, float *g_point, float *grad_env, void *stream);
 /* EnvLight.__call__(dirs, mode='pure_env') on its own (e.g. gaussian_renderer/__init__.py:244: the background radiance of
  * the primary rays): dirs [n,3] -> out [n,3]; backward: g_dirs [n,3] overwritten (may be NULL), grad_env added to. */
 int irgs_env_lookup_forward(const irgs_envmap_t *env, const float *dirs, int64_t n_dirs, float *out, void *stream);

@@ -31,8 +31,8 @@ PROTOTYPES = {
     "irgs_trace_forward_incident": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_vp, _vp, _i32, _f32, _f32, _i32, _vp]),
     "irgs_trace_backward_incident": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_vp, _vp, _i32] + [_vp] * 5
                                      + [_vp] * 6 + [_f32, _f32, _i32, _vp]),
-    "irgs_shade_forward": (_i32, [_vp] * 7 + [_f32, _vp, _vp]),
-    "irgs_shade_backward": (_i32, [_vp] * 7 + [_f32] + [_vp] * 6),
+    "irgs_shade_forward": (_i32, [_vp] * 8 + [_f32, _vp, _vp]),
+    "irgs_shade_backward": (_i32, [_vp] * 8 + [_f32] + [_vp] * 6),
     "irgs_env_lookup_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "irgs_env_lookup_backward": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "irgs_unpack_grads": (_i32, [_vp, _i64, _i32] + [_vp] * 6 + [_vp]),

@@ -25,7 +25,23 @@ struct ShadeArgs {
     const float *trace_color, *trace_alpha;           // [P*S,3], [P*S] raw tracer outputs
     float saturate;                                   // 1 - transmittance_min, < 0: no normalisation
     EnvMap env;
+    // light_sample_num > 0 (irgs_shade_sampling_t): explicit directions instead of generated ones, mixed-sampling weights
+    const float *dirs;                                // [P*S,3] or null (generated from normals / azimuth)
+    MisParams mis;
+    float inv_count;                                  // 1 / (samples the means run over)
 };
+
+// direction of sample s of point pt: generated (q is filled, q.rotated tells whether it depends on the normal) or read
+__device__ __forceinline__ void sample_dir(const ShadeArgs &a, const float n[3], int64_t ray, int s, float az, IncidentSample &q,
+                                           float d[3]) {
+    if (a.dirs != nullptr) {
+        d[0] = __ldg(a.dirs + 3 * ray); d[1] = __ldg(a.dirs + 3 * ray + 1); d[2] = __ldg(a.dirs + 3 * ray + 2);
+        q.rotated = false; q.len = 1.f; q.zx = q.zy = q.zz = q.vx = q.vy = q.vz = 0.f;
+        return;
+    }
+    q = incident_sample(n[0], n[1], n[2], s, a.S, a.azimuth != nullptr, az);
+    d[0] = __fdiv_rn(q.vx, q.len); d[1] = __fdiv_rn(q.vy, q.len); d[2] = __fdiv_rn(q.vz, q.len);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -58,12 +74,13 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
     for (int s = lane; s < a.S; s += 32) {
         const int64_t ray = pt * a.S + s;
-        const IncidentSample q = incident_sample(n[0], n[1], n[2], s, a.S, a.azimuth != nullptr, az);
-        const float d[3] = {__fdiv_rn(q.vx, q.len), __fdiv_rn(q.vy, q.len), __fdiv_rn(q.vz, q.len)};
+        IncidentSample q;
+        float d[3];
+        sample_dir(a, n, ray, s, az, q, d);
         const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
                                 __ldg(a.trace_color + 3 * ray + 2)};
         ShadeSample o;
-        shade_sample_forward(p, a.env, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, o);
+        shade_sample_forward(p, a.env, a.mis, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, o);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             acc[c] += p.fd[c] * o.transport[c];
@@ -74,7 +91,7 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
         }
         acc[9] += o.vis;
     }
-    const float inv = 1.0f / (float)a.S;
+    const float inv = a.inv_count;
     float mine = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -101,7 +118,7 @@ __global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_ker
     ShadePoint p;
     load_point(a, pt, n, p);
     const float az = a.azimuth ? __ldg(a.azimuth + pt) : 0.f;
-    const float inv = 1.0f / (float)a.S;
+    const float inv = a.inv_count;
     float go = (lane < 16) ? __ldg(g_out + 16 * pt + lane) * inv : 0.f;     // the mean over S folded into the gradients
     float gD[3], gS[3], gE[3], gLi[3], gLocal[3];
 #pragma unroll
@@ -120,12 +137,13 @@ __global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_ker
     for (int j = 0; j < 9; ++j) G[j] = 0.f;
     for (int s = lane; s < a.S; s += 32) {
         const int64_t ray = pt * a.S + s;
-        const IncidentSample q = incident_sample(n[0], n[1], n[2], s, a.S, a.azimuth != nullptr, az);
-        const float d[3] = {__fdiv_rn(q.vx, q.len), __fdiv_rn(q.vy, q.len), __fdiv_rn(q.vz, q.len)};
+        IncidentSample q;
+        float d[3];
+        sample_dir(a, n, ray, s, az, q, d);
         const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
                                 __ldg(a.trace_color + 3 * ray + 2)};
         float g_c[3], g_a, gd[3];
-        shade_sample_backward(p, a.env, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, gD, gS, gE, gVis, gLi, gLocal,
+        shade_sample_backward(p, a.env, a.mis, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, gD, gS, gE, gVis, gLi, gLocal,
                               grad_env, acc, g_c, g_a, gd);
         g_color[3 * ray] = g_c[0]; g_color[3 * ray + 1] = g_c[1]; g_color[3 * ray + 2] = g_c[2];
         g_alpha[ray] = g_a;
@@ -207,9 +225,9 @@ static int make_env(const irgs_envmap_t *env, EnvMap &e) {
     return 0;
 }
 
-static int make_args(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
-                     const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
-                     ShadeArgs &a) {
+static int make_args(const irgs_incident_t *gen, const irgs_envmap_t *env, const irgs_shade_sampling_t *smp,
+                     const float *base_color, const float *roughness, const float *viewdirs, const float *trace_color,
+                     const float *trace_alpha, float saturate_alpha, ShadeArgs &a) {
     if (!gen) return fail_msg("null incident-ray descriptor");
     if (gen->n_points < 0 || gen->sample_num < 1) return fail_msg("incident rays: n_points >= 0 and sample_num >= 1 required");
     if (gen->n_points > 0 && (!gen->normals || !base_color || !roughness || !viewdirs || !trace_color || !trace_alpha))
@@ -218,6 +236,15 @@ static int make_args(const irgs_incident_t *gen, const irgs_envmap_t *env, const
     a.normals = gen->normals; a.azimuth = gen->azimuth; a.n_points = gen->n_points; a.S = gen->sample_num;
     a.base_color = base_color; a.roughness = roughness; a.viewdirs = viewdirs;
     a.trace_color = trace_color; a.trace_alpha = trace_alpha; a.saturate = saturate_alpha;
+    a.dirs = nullptr; a.mis.pdf = nullptr; a.mis.p_diffuse = 1.f; a.mis.p_light = 0.f;
+    a.inv_count = 1.0f / (float)gen->sample_num;
+    if (smp != nullptr) {
+        if (smp->total_samples < gen->sample_num) return fail_msg("shade: total_samples must be >= the samples of this call");
+        if (smp->pdf != nullptr && !(smp->p_diffuse >= 0.f && smp->p_light >= 0.f))
+            return fail_msg("shade: sampling probabilities must be non-negative");
+        a.dirs = smp->dirs; a.mis.pdf = smp->pdf; a.mis.p_diffuse = smp->p_diffuse; a.mis.p_light = smp->p_light;
+        a.inv_count = 1.0f / (float)smp->total_samples;
+    }
     return 0;
 }
 
@@ -227,11 +254,11 @@ using namespace irgs;
 
 extern "C" {
 
-int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
-                       const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
-                       float *out, void *stream) {
+int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, const irgs_shade_sampling_t *sampling,
+                       const float *base_color, const float *roughness, const float *viewdirs, const float *trace_color,
+                       const float *trace_alpha, float saturate_alpha, float *out, void *stream) {
     ShadeArgs a;
-    if (make_args(gen, env, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
+    if (make_args(gen, env, sampling, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
     if (a.n_points == 0) return 0;
     if (!out) return fail_msg("shade: null output array");
     shade_forward_kernel<<<(unsigned)((a.n_points * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, out);
@@ -240,12 +267,12 @@ int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, con
     return 0;
 }
 
-int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, const float *base_color, const float *roughness,
-                        const float *viewdirs, const float *trace_color, const float *trace_alpha, float saturate_alpha,
-                        const float *g_out, float *g_trace_color, float *g_trace_alpha, float *g_point, float *grad_env,
-                        void *stream) {
+int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, const irgs_shade_sampling_t *sampling,
+                        const float *base_color, const float *roughness, const float *viewdirs, const float *trace_color,
+                        const float *trace_alpha, float saturate_alpha, const float *g_out, float *g_trace_color,
+                        float *g_trace_alpha, float *g_point, float *grad_env, void *stream) {
     ShadeArgs a;
-    if (make_args(gen, env, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
+    if (make_args(gen, env, sampling, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
     if (a.n_points == 0) return 0;
     if (!g_out || !g_trace_color || !g_trace_alpha || !g_point) return fail_msg("shade backward: null array");
     shade_backward_kernel<<<(unsigned)((a.n_points * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(

@@ -42,6 +42,7 @@ struct EnvTap {
     int i00, i10, i01, i11;   // texel indices (u0,v0) (u1,v0) (u0,v1) (u1,v1)
     float fu, fv;             // bilinear weights
     float lx, ly, lz;         // direction in the map's frame
+    float u, v;               // lat-long coordinates in [0, 1] (before the wrap of the bilinear lookup)
     bool u_open, v_open, y_open;   // the clamps that were NOT active (gradient passes)
 };
 
@@ -66,6 +67,7 @@ IRGS_HD void env_tap(const EnvMap &e, float dx, float dy, float dz, EnvTap &t) {
     t.v_open = (v >= 0.f) && (v <= 1.f);
     u = sh_clampf(u, 0.f, 1.f);
     v = sh_clampf(v, 0.f, 1.f);
+    t.u = u; t.v = v;
     // nvdiffrast indexTextureLinear, boundary mode 'wrap'
     u = u - floorf(u);
     v = v - floorf(v);
@@ -151,6 +153,43 @@ IRGS_HD void env_backward(const EnvMap &e, const EnvTap &t, const float raw[3], 
     } else {
         gd[0] += glx; gd[1] += gly; gd[2] += glz;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ light-importance sampling
+// The light_sample_num > 0 branch of rendering_equation (gaussian_renderer/__init__.py:340-357) mixes the Fibonacci samples
+// with directions drawn from the environment map (EnvLight.sample_light_directions, scene/light.py:181-205) and weights
+// every sample -- of either kind -- by 1 / clamp_min(p_diffuse / (2 pi) + p_light * light_pdf(dir), 1e-6), light_pdf being
+// EnvLight.light_pdf (light.py:207-223): the texel's probability times H W / (2 pi^2 sin(v pi)).
+struct MisParams {
+    const float *pdf;          // [H, W] texel probabilities (EnvLight._pdf) or null: pure Fibonacci sampling, area = 2 pi
+    float p_diffuse, p_light;
+};
+struct MisTerms { float area, mix, tex, weight, sinv; };
+
+IRGS_HD void mis_area(const EnvMap &e, const MisParams &m, const EnvTap &t, MisTerms &o) {
+    if (m.pdf == nullptr) { o.area = SH_TWO_PI; o.mix = 1.0f / SH_TWO_PI; o.tex = o.weight = 0.f; o.sinv = 1.f; return; }
+    int ui = (int)(t.u * (float)e.W), vi = (int)(t.v * (float)e.H);      // .long(): truncation, then clamp(0, size - 1)
+    ui = ui < 0 ? 0 : (ui > e.W - 1 ? e.W - 1 : ui);
+    vi = vi < 0 ? 0 : (vi > e.H - 1 ? e.H - 1 : vi);
+    o.tex = m.pdf[ui + vi * e.W];
+    o.sinv = sinf(t.v * SH_PI);
+    o.weight = (float)e.H * (float)e.W / (2.0f * SH_PI * SH_PI * fmaxf(o.sinv, 1e-6f));
+    o.mix = m.p_diffuse / SH_TWO_PI + o.tex * o.weight * m.p_light;
+    o.area = 1.0f / fmaxf(o.mix, 1e-6f);
+}
+
+// g_area = dL/d area of this sample; adds dL/d direction (through the 1 / sin(v pi) of the weight) to gd[3]
+IRGS_HD void mis_backward(const EnvMap &e, const MisParams &m, const EnvTap &t, const MisTerms &o, float g_area, float gd[3]) {
+    if (m.pdf == nullptr || g_area == 0.f) return;
+    if (!(o.mix >= 1e-6f)) return;                                       // clamp_min(1e-6)
+    const float g_mix = -g_area * o.area * o.area;
+    const float g_weight = g_mix * m.p_light * o.tex;
+    if (!(o.sinv >= 1e-6f) || !t.y_open) return;                         // clamp_min(1e-6) of the sine; clamp of l.y
+    const float g_sin = -g_weight * o.weight / o.sinv;
+    const float g_v = g_sin * cosf(t.v * SH_PI) * SH_PI;
+    const float gly = -g_v / (sqrtf(fmaxf(1.0f - t.ly * t.ly, 1e-30f)) * SH_PI);   // v = acos(l.y) / pi
+    if (e.has_transform) { gd[0] += e.T[3] * gly; gd[1] += e.T[4] * gly; gd[2] += e.T[5] * gly; }
+    else gd[1] += gly;
 }
 
 // ------------------------------------------------------------------------------------------------ shading point
@@ -323,16 +362,18 @@ struct ShadeSample {
     float Li[3];         // incident_lights
     float ndi;
     float fs;
-    float transport[3];  // Li * area * n_d_i, area = 2 pi (graphics_utils.py:43)
+    float transport[3];  // Li * area * n_d_i, area = 2 pi (graphics_utils.py:43) or the mixed-sampling weight (mis_area)
 };
 
-IRGS_HD void shade_sample_forward(const ShadePoint &p, const EnvMap &e, const float d[3], const float c_raw[3], float a_raw,
-                                  float sat, ShadeSample &o) {
+IRGS_HD void shade_sample_forward(const ShadePoint &p, const EnvMap &e, const MisParams &m, const float d[3],
+                                  const float c_raw[3], float a_raw, float sat, ShadeSample &o) {
     EnvTap t;
     float raw[3], a;
     bool saturated;
+    MisTerms mt;
     env_tap(e, d[0], d[1], d[2], t);
     env_fetch(e, t, raw, o.env);
+    mis_area(e, m, t, mt);
     trace_normalise(c_raw, a_raw, sat, o.local, a, saturated);
     o.vis = 1.0f - a;
     GgxTerms g;
@@ -342,7 +383,7 @@ IRGS_HD void shade_sample_forward(const ShadePoint &p, const EnvMap &e, const fl
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         o.Li[c] = o.vis * o.env[c] + o.local[c];
-        o.transport[c] = o.Li[c] * SH_TWO_PI * o.ndi;
+        o.transport[c] = o.Li[c] * mt.area * o.ndi;
     }
 }
 
@@ -350,31 +391,35 @@ IRGS_HD void shade_sample_forward(const ShadePoint &p, const EnvMap &e, const fl
 // gVis, gLi, gLocal likewise for the evaluation-mode outputs (visibility, light, light_indirect), zero in training.
 // Outputs: g_c_raw[3], g_a_raw (gradients of the RAW traced colour / alpha of this ray), gd[3] (dL/d direction, overwritten);
 // texel gradients are added into grad_base; point-level terms into acc.
-IRGS_HD void shade_sample_backward(const ShadePoint &p, const EnvMap &e, const float d[3], const float c_raw[3], float a_raw,
-                                   float sat, const float gD[3], const float gS[3], const float gE[3], float gVis,
+IRGS_HD void shade_sample_backward(const ShadePoint &p, const EnvMap &e, const MisParams &m, const float d[3],
+                                   const float c_raw[3], float a_raw, float sat, const float gD[3], const float gS[3],
+                                   const float gE[3], float gVis,
                                    const float gLi[3], const float gLocal[3], float *grad_base, ShadeAcc &acc,
                                    float g_c_raw[3], float &g_a_raw, float gd[3]) {
     EnvTap t;
     float raw[3], env[3], local[3], a;
     bool saturated;
+    MisTerms mt;
     env_tap(e, d[0], d[1], d[2], t);
     env_fetch(e, t, raw, env);
+    mis_area(e, m, t, mt);
     trace_normalise(c_raw, a_raw, sat, local, a, saturated);
     const float vis = 1.0f - a;
     GgxTerms g;
     ggx_forward(p, d, g);
     const float ndi_raw = p.n[0] * d[0] + p.n[1] * d[1] + p.n[2] * d[2];
     const float ndi = fmaxf(ndi_raw, 0.f);
-    float g_fs = 0.f, g_ndi = 0.f, g_vis = gVis, g_env[3], g_local[3];
+    float g_fs = 0.f, g_ndi = 0.f, g_area = 0.f, g_vis = gVis, g_env[3], g_local[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float Li = vis * env[c] + local[c];
-        const float transport = Li * SH_TWO_PI * ndi;
+        const float transport = Li * mt.area * ndi;
         const float g_tr = p.fd[c] * gD[c] + g.fs * gS[c];
         acc.g_base[c] += transport * gD[c];
         g_fs += transport * gS[c];
-        const float g_Li = g_tr * SH_TWO_PI * ndi + gLi[c];
-        g_ndi += g_tr * Li * SH_TWO_PI;
+        const float g_Li = g_tr * mt.area * ndi + gLi[c];
+        g_ndi += g_tr * Li * mt.area;
+        g_area += g_tr * Li * ndi;
         g_env[c] = g_Li * vis + gE[c];
         g_vis += g_Li * env[c];
         g_local[c] = g_Li + gLocal[c];
@@ -386,6 +431,7 @@ IRGS_HD void shade_sample_backward(const ShadePoint &p, const EnvMap &e, const f
     }
     ggx_backward(p, g, g_fs, acc, gd);
     env_backward(e, t, raw, env, g_env, grad_base, gd);
+    mis_backward(e, m, t, mt, g_area, gd);
     // through GaussianModel.trace's normalisation
     const float g_a = -g_vis;
     if (saturated) {

@@ -4,11 +4,13 @@ as two CUDA kernels (forward / backward) instead of some thirty element-wise tor
 Reference being mirrored (paths under /root/reference):
   * gaussian_renderer/__init__.py:334-415  rendering_equation(base_color, roughness, normals, position, viewdirs, pc, pipe,
         training=...) -> {"diffuse", "specular", "light_direct"} (training) + {"visibility", "light", "light_indirect"}
-        (evaluation); the `diffuse_sample_num > 0, light_sample_num == 0`, non-relight path (the stage-2 training path
-        and BASELINE config C3).  The mixed light-importance-sampling and relight paths (C4: nvdiffrast cube-map mips +
-        FG LUT) are not built and raise NotImplementedError, like the reference's own `else` branch.
+        (evaluation); the non-relight path with `diffuse_sample_num > 0`: pure Fibonacci sampling (`light_sample_num == 0`,
+        the stage-2 training path and BASELINE config C3) and the mix with light-importance samples (`light_sample_num > 0`,
+        :340-357, what render.py uses after `env_map.update_pdf()`).  The relight path (nvdiffrast cube-map mips + FG LUT)
+        is not built and raises NotImplementedError.
   * gaussian_renderer/__init__.py:417-457  GGX_specular
-  * scene/light.py:132-172,245-246,287-297,315  EnvLight (base, activation, transform, __call__(mode='pure_env'))
+  * scene/light.py:132-172,245-246,287-297,315  EnvLight (base, activation, transform, __call__(mode='pure_env'));
+        :174-223 update_pdf, sample_light_directions, light_pdf
   * scene/gaussian_model.py:748-752  GaussianModel.trace's normalisation of saturated rays (folded into the kernels)
 
     env = EnvLight(resolution=(256, 512), activation="exp")                   # or any object with .base / .activation_name / .transform
@@ -53,6 +55,19 @@ def _env_desc(base, activation, transform):
         for j in range(9):
             d.transform[j] = t[j]
     return d
+
+
+class SamplingDesc(ctypes.Structure):
+    """irgs_shade_sampling_t of include/irgs_b200.h."""
+    _fields_ = [("dirs", ctypes.c_void_p), ("pdf", ctypes.c_void_p), ("p_diffuse", ctypes.c_float), ("p_light", ctypes.c_float),
+                ("total_samples", ctypes.c_int32)]
+
+
+def _sampling_desc(dirs, pdf, p_diffuse, p_light, total):
+    if dirs is None and pdf is None:
+        return None
+    return SamplingDesc(dirs.data_ptr() if dirs is not None else None, pdf.data_ptr() if pdf is not None else None,
+                        float(p_diffuse), float(p_light), int(total))
 
 
 def _env_fields(envmap):
@@ -106,6 +121,48 @@ class EnvLight(torch.nn.Module):
     def set_transform(self, transform):
         self.transform = transform
 
+    @torch.no_grad()
+    def update_pdf(self):
+        """light.py:174-179: texel sampling probabilities `_pdf` [H,W] from the current map (max over channels x sin(theta))."""
+        H, W = self.base.shape[:2]
+        y = ((torch.arange(H, dtype=torch.float32, device=self.base.device) + 0.5) / H)[:, None]
+        act = {"exp": torch.exp, "sigmoid": torch.sigmoid, "none": lambda x: x}[self.activation_name]
+        pdf = act(self.base).clamp_min(0.0).max(dim=-1)[0] * torch.sin(y * math.pi)
+        self._pdf = (pdf / pdf.sum()).contiguous()
+
+    @torch.no_grad()
+    def sample_light_directions(self, B, sample_num, training=False):
+        """light.py:181-205: B x sample_num directions drawn texel-wise from `_pdf` (jittered inside the texel when
+        training) and their solid-angle densities -> ([B, sample_num, 3], [B, sample_num, 1])."""
+        H, W = self._pdf.shape
+        idx = torch.multinomial(self._pdf.reshape(-1), B * sample_num, replacement=True)
+        gx = ((idx % W + 0.5) / W) * 2 - 1
+        gy = (idx // W + 0.5) / H
+        if training:
+            gx = gx + (torch.rand_like(gx) - 0.5) / W * 2
+            gy = gy + (torch.rand_like(gy) - 0.5) / H
+        st, ct = torch.sin(gy * math.pi), torch.cos(gy * math.pi)
+        sp, cp = torch.sin(gx * math.pi), torch.cos(gx * math.pi)
+        direction = torch.stack((st * sp, ct, -st * cp), dim=-1)
+        if self.transform is not None:
+            direction = direction @ torch.as_tensor(self.transform, dtype=torch.float32, device=direction.device)
+        direction = direction.reshape(B, sample_num, 3).contiguous()
+        return direction, self.light_pdf(direction)
+
+    @torch.no_grad()
+    def light_pdf(self, direction):
+        """light.py:207-223 (the shading kernels evaluate the same expression per sample; this copy serves callers that
+        want the densities themselves)."""
+        H, W = self._pdf.shape
+        flat = direction.reshape(-1, 3)
+        if self.transform is not None:
+            flat = flat @ torch.as_tensor(self.transform, dtype=torch.float32, device=flat.device).T
+        u = torch.atan2(flat[..., 0], -flat[..., 2]).nan_to_num() / (2.0 * math.pi) + 0.5
+        v = torch.acos(flat[..., 1].clamp(-1.0 + 1e-6, 1.0 - 1e-6)) / math.pi
+        idx = (u * W).clamp(0, W - 1).long() + (v * H).clamp(0, H - 1).long() * W
+        weight = H * W / (2.0 * math.pi ** 2 * torch.sin(v * math.pi).clamp_min(1e-6))
+        return (self._pdf.reshape(-1)[idx] * weight).reshape(*direction.shape[:-1], 1)
+
     def __call__(self, l, mode="pure_env", roughness=None):
         if mode != "pure_env":
             raise NotImplementedError("only mode='pure_env' is built (the cube-map modes need nvdiffrast's mip chain)")
@@ -123,24 +180,30 @@ class _ShadeIncident(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, normals_pt, azimuth, sample_num, base_color, roughness, viewdirs, env_base, activation, transform,
-                trace_color, trace_alpha, saturate_alpha):
+                trace_color, trace_alpha, saturate_alpha, dirs, pdf, p_diffuse, p_light, total_samples):
         dev = normals_pt.device
         P = normals_pt.shape[0]
         out = torch.empty(P, 16, device=dev)
         gen = _desc(normals_pt, normals_pt, azimuth, sample_num, 0.0)
         env = _env_desc(env_base, activation, transform)
-        _lib.check(_lib.load().irgs_shade_forward(ctypes.byref(gen), ctypes.byref(env), _ptr(base_color), _ptr(roughness),
-                                                  _ptr(viewdirs), _ptr(trace_color), _ptr(trace_alpha), saturate_alpha,
-                                                  _ptr(out), _stream(dev)))
-        ctx.save_for_backward(normals_pt, azimuth if azimuth is not None else normals_pt[:0], base_color, roughness, viewdirs,
-                              env_base, trace_color, trace_alpha)
-        ctx.cfg = (sample_num, activation, transform, saturate_alpha, azimuth is not None)
+        smp = _sampling_desc(dirs, pdf, p_diffuse, p_light, total_samples)
+        _lib.check(_lib.load().irgs_shade_forward(ctypes.byref(gen), ctypes.byref(env), ctypes.byref(smp) if smp else None,
+                                                  _ptr(base_color), _ptr(roughness), _ptr(viewdirs), _ptr(trace_color),
+                                                  _ptr(trace_alpha), saturate_alpha, _ptr(out), _stream(dev)))
+        none = normals_pt[:0]
+        ctx.save_for_backward(normals_pt, azimuth if azimuth is not None else none, base_color, roughness, viewdirs,
+                              env_base, trace_color, trace_alpha, dirs if dirs is not None else none,
+                              pdf if pdf is not None else none)
+        ctx.cfg = (sample_num, activation, transform, saturate_alpha, azimuth is not None, dirs is not None, pdf is not None,
+                   p_diffuse, p_light, total_samples)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        normals_pt, azimuth, base_color, roughness, viewdirs, env_base, trace_color, trace_alpha = ctx.saved_tensors
-        sample_num, activation, transform, saturate_alpha, has_azim = ctx.cfg
+        (normals_pt, azimuth, base_color, roughness, viewdirs, env_base, trace_color, trace_alpha, dirs,
+         pdf) = ctx.saved_tensors
+        (sample_num, activation, transform, saturate_alpha, has_azim, has_dirs, has_pdf, p_diffuse, p_light,
+         total_samples) = ctx.cfg
         dev = normals_pt.device
         P = normals_pt.shape[0]
         g_out = g_out.contiguous()
@@ -150,20 +213,26 @@ class _ShadeIncident(torch.autograd.Function):
         g_env = torch.zeros_like(env_base) if ctx.needs_input_grad[6] else None
         gen = _desc(normals_pt, normals_pt, azimuth if has_azim else None, sample_num, 0.0)
         env = _env_desc(env_base, activation, transform)
-        _lib.check(_lib.load().irgs_shade_backward(ctypes.byref(gen), ctypes.byref(env), _ptr(base_color), _ptr(roughness),
-                                                   _ptr(viewdirs), _ptr(trace_color), _ptr(trace_alpha), saturate_alpha,
-                                                   _ptr(g_out), _ptr(g_color), _ptr(g_alpha), _ptr(g_point), _ptr(g_env),
-                                                   _stream(dev)))
+        smp = _sampling_desc(dirs if has_dirs else None, pdf if has_pdf else None, p_diffuse, p_light, total_samples)
+        _lib.check(_lib.load().irgs_shade_backward(ctypes.byref(gen), ctypes.byref(env), ctypes.byref(smp) if smp else None,
+                                                   _ptr(base_color), _ptr(roughness), _ptr(viewdirs), _ptr(trace_color),
+                                                   _ptr(trace_alpha), saturate_alpha, _ptr(g_out), _ptr(g_color),
+                                                   _ptr(g_alpha), _ptr(g_point), _ptr(g_env), _stream(dev)))
         return (g_point[:, 4:7], None, None, g_point[:, 0:3], g_point[:, 3], g_point[:, 7:10], g_env, None, None,
-                g_color, g_alpha, None)
+                g_color, g_alpha, None, None, None, None, None, None)
 
 
 def shade_incident(normals, sample_num, base_color, roughness, viewdirs, env_base, trace_color, trace_alpha, azimuth=None,
-                   activation="exp", transform=None, transmittance_min=None):
+                   activation="exp", transform=None, transmittance_min=None, dirs=None, pdf=None, p_diffuse=1.0, p_light=0.0,
+                   total_samples=None):
     """The rendering-equation epilogue on its own: given the tracer's RAW colour [P,S,3] / alpha [P,S] of the incident rays
     that `GaussianTracer.trace_incident(position, normals, sample_num, ..., azimuth=azimuth)` traced, returns the dict
     of rendering_equation (all six keys; [P,3] each, visibility [P,1]).  transmittance_min: apply GaussianModel.trace's
-    normalisation of saturated rays (None: the colour / alpha are used as they are)."""
+    normalisation of saturated rays (None: the colour / alpha are used as they are).
+    Mixed sampling (light_sample_num > 0): `dirs` [P,S,3] = explicit directions of these samples (the light samples; None:
+    the generated Fibonacci ones), `pdf` [H,W] = the map's texel probabilities (EnvLight._pdf), p_diffuse / p_light = the
+    two sample fractions, total_samples = diffuse + light samples (the divisor of the means): the results of the two
+    calls, one per kind of sample, add up to rendering_equation's."""
     dev = normals.device
     f = lambda t: t.contiguous()                                                        # noqa: E731
     normals, base_color, viewdirs = f(normals), f(base_color), f(viewdirs)
@@ -178,11 +247,21 @@ def shade_incident(normals, sample_num, base_color, roughness, viewdirs, env_bas
         if tuple(t.shape) != shape:
             raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
     sat = -1.0 if transmittance_min is None else 1.0 - float(transmittance_min)
+    if dirs is not None:
+        dirs = f(dirs.detach())
+        if dirs.dtype != torch.float32 or dirs.device != dev or tuple(dirs.shape) != (P, S, 3):
+            raise ValueError(f"dirs must be a float32 tensor of shape {(P, S, 3)} on {dev}")
+    if pdf is not None:
+        pdf = f(pdf.detach())
+        if pdf.dtype != torch.float32 or pdf.device != dev or tuple(pdf.shape) != tuple(env_base.shape[:2]):
+            raise ValueError("pdf must be a float32 tensor with the environment map's [H, W]")
+    total = S if total_samples is None else int(total_samples)
     if P == 0:
         out = torch.zeros(0, 16, device=dev)
     else:
         out = _ShadeIncident.apply(normals, azimuth, S, base_color, roughness, viewdirs, f(env_base), activation, transform,
-                                   f(trace_color).view(P * S, 3), f(trace_alpha).view(P * S), sat)
+                                   f(trace_color).view(P * S, 3), f(trace_alpha).view(P * S), sat, dirs, pdf, float(p_diffuse),
+                                   float(p_light), total)
     return {k: out[:, s] for k, s in OUT_SLICES.items()}
 
 
@@ -192,21 +271,48 @@ def rendering_equation(base_color, roughness, normals, position, viewdirs, trace
     """gaussian_renderer/__init__.py:334-415.  `tracer` + `surfels` stand for the reference's `pc.trace`, `envmap` for
     `pc.get_envmap`, sample_num / light_sample_num / light_t_min / wo_indirect / detach_indirect for the `pipe` fields of
     the same names (arguments/__init__.py:92-101).  training=True draws the per-point random azimuth like
-    fibonacci_sphere_sampling(random_rotate=True) unless `azimuth` [P] is given."""
-    if relight or light_sample_num != 0 or sample_num <= 0:
-        raise NotImplementedError("only the diffuse_sample_num > 0, light_sample_num == 0, non-relight path is built")
+    fibonacci_sphere_sampling(random_rotate=True) unless `azimuth` [P] is given.  light_sample_num > 0 additionally draws
+    that many directions per point from `envmap` (its `_pdf` / `sample_light_directions`, like the reference)."""
+    if relight or sample_num <= 0 or light_sample_num < 0:
+        raise NotImplementedError("only the non-relight path with diffuse_sample_num > 0 is built")
     P = base_color.shape[0]
+    keys = ("diffuse", "specular", "light_direct") if training else tuple(OUT_SLICES)
+    if P == 0:
+        return {k: base_color.new_zeros(0, 1 if k == "visibility" else 3) for k in keys}
     if training and azimuth is None:
         azimuth = torch.rand(P, device=normals.device) * (2 * math.pi)                   # graphics_utils.py:31
     means3D, opacity, ru, rv, surf_normals, features, shs = surfels
+    base, activation, transform = _env_fields(envmap)
+
+    def indirect(color, alpha):
+        if wo_indirect:
+            color = torch.zeros_like(color)                                              # __init__.py:384-385
+        if detach_indirect:
+            color, alpha = color.detach(), alpha.detach()                                # __init__.py:386-388
+        return color, alpha
+
     color, _, _, _, alpha = tracer.trace_incident(position, normals, sample_num, means3D, opacity, ru, rv, surf_normals,
                                                   features, shs, alpha_min, azimuth=azimuth, t_min=light_t_min, deg=deg)
-    if wo_indirect:
-        color = torch.zeros_like(color)                                                  # __init__.py:384-385
-    if detach_indirect:
-        color, alpha = color.detach(), alpha.detach()                                    # __init__.py:386-388
-    base, activation, transform = _env_fields(envmap)
-    out = shade_incident(normals, sample_num, base_color, roughness, viewdirs, base, color, alpha, azimuth=azimuth,
-                         activation=activation, transform=transform, transmittance_min=tracer.transmittance_min)
-    keys = ("diffuse", "specular", "light_direct") if training else tuple(OUT_SLICES)
-    return {k: out[k] for k in keys}
+    color, alpha = indirect(color, alpha)
+    if light_sample_num == 0:
+        out = shade_incident(normals, sample_num, base_color, roughness, viewdirs, base, color, alpha, azimuth=azimuth,
+                             activation=activation, transform=transform, transmittance_min=tracer.transmittance_min)
+        return {k: out[k] for k in keys}
+    # __init__.py:340-357: Fibonacci samples + directions drawn from the environment map, every sample weighted by the
+    # mixed density (evaluated per sample inside the shading kernels); one shading call per kind of sample, results add up
+    pdf = getattr(envmap, "_pdf", None)
+    if pdf is None:
+        raise RuntimeError("light_sample_num > 0 needs the texel probabilities: call envmap.update_pdf() first (render.py:89)")
+    total = sample_num + light_sample_num
+    mix = dict(pdf=pdf, p_diffuse=sample_num / total, p_light=light_sample_num / total, total_samples=total)
+    light_dirs, _ = envmap.sample_light_directions(P, light_sample_num, training)
+    light_dirs = light_dirs.detach().contiguous()
+    out_d = shade_incident(normals, sample_num, base_color, roughness, viewdirs, base, color, alpha, azimuth=azimuth,
+                           activation=activation, transform=transform, transmittance_min=tracer.transmittance_min, **mix)
+    color_l, _, _, _, alpha_l = tracer.trace(position[:, None] + light_dirs * light_t_min, light_dirs, means3D, opacity, ru,
+                                             rv, surf_normals, features, shs, alpha_min, deg=deg)
+    color_l, alpha_l = indirect(color_l, alpha_l)
+    out_l = shade_incident(normals, light_sample_num, base_color, roughness, viewdirs, base, color_l, alpha_l,
+                           activation=activation, transform=transform, transmittance_min=tracer.transmittance_min,
+                           dirs=light_dirs, **mix)
+    return {k: out_d[k] + out_l[k] for k in keys}

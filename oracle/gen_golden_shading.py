@@ -1,7 +1,8 @@
 """Records golden vectors of the reference's shading around the incident-ray trace by EXECUTING THE UNMODIFIED SOURCE of
 
     gaussian_renderer/__init__.py : sample_incident_rays, rendering_equation, GGX_specular
-    scene/light.py                : inverse_sigmoid, EnvLight            (EnvLight.__call__(mode='pure_env'))
+    scene/light.py                : inverse_sigmoid, pixel_grid, EnvLight   (EnvLight.__call__(mode='pure_env'), update_pdf,
+                                    sample_light_directions, light_pdf -- the light_sample_num > 0 branch)
     utils/graphics_utils.py       : fibonacci_sphere_sampling, rotation_between_z
 
 on the CPU of the build container.  The functions are cut out of the reference files with `ast` (the modules themselves
@@ -60,7 +61,7 @@ def load_reference():
     ns = {"torch": torch, "F": F, "np": np, "math": math, "dr": _Dr,
           "fibonacci_sphere_sampling": gu.fibonacci_sphere_sampling, "rotation_between_z": gu.rotation_between_z}
     exec(cut(f"{REF}/gaussian_renderer/__init__.py", ["sample_incident_rays", "rendering_equation", "GGX_specular"]), ns)
-    exec(cut(f"{REF}/scene/light.py", ["inverse_sigmoid", "EnvLight"]), ns)
+    exec(cut(f"{REF}/scene/light.py", ["inverse_sigmoid", "pixel_grid", "EnvLight"]), ns)
     return types.SimpleNamespace(**ns)
 
 
@@ -80,7 +81,7 @@ class _PC:
         return {"color": color, "alpha": alpha}
 
 
-def make_case(ref, seed, P, S, training, activation, res, with_transform):
+def make_case(ref, seed, P, S, training, activation, res, with_transform, n_light=0):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=g)          # noqa: E731
     n = torch.randn(P, 3, generator=g)
@@ -93,7 +94,8 @@ def make_case(ref, seed, P, S, training, activation, res, with_transform):
     inp = {
         "base_color": r(P, 3), "roughness": 0.05 + 0.9 * r(P, 1), "normals": n, "viewdirs": view,
         "position": torch.randn(P, 3, generator=g),
-        "color_raw": r(P, S, 3) * (r(P, S, 1) < 0.6), "alpha_raw": (r(P, S) * 1.15).clamp(0, 0.999) * (r(P, S) < 0.7),
+        "color_raw": r(P, S + n_light, 3) * (r(P, S + n_light, 1) < 0.6),
+        "alpha_raw": (r(P, S + n_light) * 1.15).clamp(0, 0.999) * (r(P, S + n_light) < 0.7),
     }
     inp["alpha_raw"][:, 0] = 0.985                       # saturated rays (>= 1 - T_MIN): normalised by pc.trace
     inp["color_raw"][:, 0] = r(P, 3)
@@ -109,13 +111,23 @@ def make_case(ref, seed, P, S, training, activation, res, with_transform):
         env.set_transform(transform)
     leaves = {k: v.clone().requires_grad_(True) for k, v in inp.items() if k != "position"}
     pc = _PC(env, leaves["color_raw"], leaves["alpha_raw"])
-    pipe = types.SimpleNamespace(diffuse_sample_num=S, light_sample_num=0, light_t_min=0.05, wo_indirect=False,
+    pipe = types.SimpleNamespace(diffuse_sample_num=S, light_sample_num=n_light, light_t_min=0.05, wo_indirect=False,
                                  detach_indirect=False)
     torch.manual_seed(seed + 1)
+    light_log = []
+    if n_light > 0:
+        env.update_pdf()                                  # render.py:89 does this before rendering with light samples
+        sample = env.sample_light_directions
+
+        def logged(*a, **k):
+            out = sample(*a, **k)
+            light_log.append(tuple(t.detach().clone() for t in out))
+            return out
+        env.sample_light_directions = logged
     ggi._rand_log.clear()
     out = ref.rendering_equation(leaves["base_color"], leaves["roughness"], leaves["normals"], inp["position"],
                                  leaves["viewdirs"], pc, pipe, training=training)
-    azimuth = (ggi._rand_log[-1] * 2 * np.pi).reshape(-1) if training else None
+    azimuth = (ggi._rand_log[0] * 2 * np.pi).reshape(-1) if training else None      # the first rand call: the Fibonacci rotation
     keys = sorted(out)
     w = {k: torch.randn(out[k].shape, generator=g) for k in keys}
     sum((out[k] * w[k]).sum() for k in keys).backward()
@@ -124,6 +136,10 @@ def make_case(ref, seed, P, S, training, activation, res, with_transform):
     rec["activation"] = np.array(activation)
     rec["training"] = np.array(training)
     rec["S"] = np.array(S)
+    rec["n_light"] = np.array(n_light)
+    if n_light > 0:
+        rec["in_light_dirs"], rec["light_pdfs"] = light_log[0][0].numpy(), light_log[0][1].numpy()
+        rec["in_pdf"] = env._pdf.numpy()
     if transform is not None:
         rec["in_transform"] = transform.numpy()
     if azimuth is not None:
@@ -145,6 +161,8 @@ def main():
         "train64": make_case(ref, 12, 33, 64, True, "exp", (32, 64), False),
         "train40_sigmoid_xf": make_case(ref, 13, 24, 40, True, "sigmoid", (8, 16), True),
         "eval33_none": make_case(ref, 14, 16, 33, False, "none", (16, 16), False),
+        "eval24_light12": make_case(ref, 15, 24, 24, False, "exp", (16, 32), False, n_light=12),
+        "train32_light16_xf": make_case(ref, 16, 20, 32, True, "exp", (8, 16), True, n_light=16),
     }
     flat = {f"{c}/{k}": v for c, rec in cases.items() for k, v in rec.items()}
     path = os.path.join(ROOT, "tests", "golden", "ref_shading.npz")

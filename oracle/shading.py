@@ -12,7 +12,10 @@ reference lines it follows (paths under /root/reference):
   env_pure              scene/light.py:287-297,315   EnvLight.__call__(mode='pure_env')
   normalise_trace       scene/gaussian_model.py:748-752   GaussianModel.trace post-processing of colour and alpha
   ggx_specular          gaussian_renderer/__init__.py:417-457
-  rendering_equation    gaussian_renderer/__init__.py:334-415 (diffuse_sample_num > 0, light_sample_num == 0, relight=False)
+  rendering_equation    gaussian_renderer/__init__.py:334-415 (diffuse_sample_num > 0, relight=False; with light_sample_num > 0
+                        through mis_areas)
+  update_pdf, light_dirs_from_texels, light_pdf, mis_areas    scene/light.py:174-223 + __init__.py:340-357 (light-importance
+                        sampling mixed with the Fibonacci samples)
 """
 import math
 
@@ -88,10 +91,59 @@ def ggx_specular(normal, pts2c, pts2l, roughness, fresnel):
     return frac / nom
 
 
+def update_pdf(base, activation="exp"):
+    """light.py:174-179 EnvLight.update_pdf: per-texel sampling probability [H,W] (no gradient)."""
+    with torch.no_grad():
+        H, W = base.shape[:2]
+        Y = ((torch.arange(0, H, dtype=torch.float32, device=base.device) + 0.5) / H)[:, None].expand(H, W)   # pixel_grid(...)[..., 1]
+        pdf = torch.max(ACTIVATIONS[activation](base).clamp_min(0.0), dim=-1)[0] * torch.sin(Y * math.pi)
+        return pdf / torch.sum(pdf)
+
+
+def light_dirs_from_texels(idx, H, W, jitter_x=None, jitter_y=None, transform=None):
+    """light.py:186-202 EnvLight.sample_light_directions after the multinomial draw: texel index -> direction.
+    jitter_* = the training mode's `rand - 0.5` terms (None: texel centres)."""
+    gx = ((idx % W + 0.5) / W) * 2 - 1
+    gy = (idx // W + 0.5) / H
+    if jitter_x is not None:
+        gx = gx + jitter_x / W * 2
+        gy = gy + jitter_y / H
+    sintheta, costheta = torch.sin(gy * math.pi), torch.cos(gy * math.pi)
+    sinphi, cosphi = torch.sin(gx * math.pi), torch.cos(gx * math.pi)
+    d = torch.stack((sintheta * sinphi, costheta, -sintheta * cosphi), dim=-1)
+    if transform is not None:
+        d = d @ transform
+    return d
+
+
+def light_pdf(pdf, direction, transform=None):
+    """light.py:207-223 EnvLight.light_pdf: solid-angle density of the texel sampling at `direction` [...,3] -> [...,1]."""
+    H, W = pdf.shape[:2]
+    flat = direction.reshape(-1, 3)
+    if transform is not None:
+        flat = flat @ transform.T
+    u = torch.atan2(flat[..., 0], -flat[..., 2]).nan_to_num() / (2.0 * math.pi) + 0.5
+    v = torch.acos(flat[..., 1].clamp(-1.0 + 1e-6, 1.0 - 1e-6)) / math.pi
+    u_idx = (u * W).clamp(0, W - 1).long()
+    v_idx = (v * H).clamp(0, H - 1).long()
+    weight = H * W / (2.0 * math.pi ** 2 * torch.sin(v * math.pi).clamp_min(1e-6))
+    return (pdf.reshape(-1)[u_idx + v_idx * W] * weight).reshape(*direction.shape[:-1], 1)
+
+
+def mis_areas(incident_dirs, pdf, n_diffuse, n_light, transform=None):
+    """__init__.py:340-357: per-sample `incident_areas` [P,S,1] of the mixed diffuse / light-importance sampling, S = n_diffuse +
+    n_light (the same expression for both kinds of samples: 1/(2 pi) * p_diffuse + light_pdf(dir) * p_light)."""
+    p_d = n_diffuse / (n_diffuse + n_light)
+    p_l = n_light / (n_diffuse + n_light)
+    mix = 1 / (2 * math.pi) * p_d + light_pdf(pdf, incident_dirs, transform) * p_l
+    return 1 / mix.clamp_min(1e-6)
+
+
 def rendering_equation(base_color, roughness, normals, viewdirs, incident_dirs, trace_color, trace_alpha, env_base,
-                       activation="exp", transform=None, transmittance_min=None):
+                       activation="exp", transform=None, transmittance_min=None, incident_areas=None):
     """__init__.py:334-415 given the incident directions [P,S,3] and the tracer's RAW colour [P,S,3] / alpha [P,S] of those
-    rays (transmittance_min: GaussianModel.trace's normalisation, None to skip).  Returns the evaluation-mode dict (the
+    rays (transmittance_min: GaussianModel.trace's normalisation, None to skip).  incident_areas: [P,S,1] from mis_areas
+    for the light_sample_num > 0 branch (None: the 2 pi of pure Fibonacci sampling).  Returns the evaluation-mode dict (the
     training-mode dict is its subset diffuse / specular / light_direct)."""
     if transmittance_min is not None:
         trace_color, trace_alpha = normalise_trace(trace_color, trace_alpha, transmittance_min)
@@ -99,7 +151,8 @@ def rendering_equation(base_color, roughness, normals, viewdirs, incident_dirs, 
     incident_visibility = 1 - trace_alpha[..., None]
     local_incident_lights = trace_color
     incident_lights = incident_visibility * global_incident_lights + local_incident_lights
-    incident_areas = 2 * math.pi                                   # graphics_utils.py:43
+    if incident_areas is None:
+        incident_areas = 2 * math.pi                               # graphics_utils.py:43
     n_d_i = (normals[:, None] * incident_dirs).sum(-1, keepdim=True).clamp(min=0)
     f_d = base_color[:, None] / math.pi
     f_s = ggx_specular(normals, viewdirs, incident_dirs, roughness, fresnel=0.04)

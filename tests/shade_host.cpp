@@ -22,8 +22,10 @@ extern "C" {
 // out [P,16] in the layout of irgs_shade_forward
 void shade_host_forward(int64_t P, int S, const float *normals, const float *viewdirs, const float *roughness,
                         const float *base_color, const float *dirs, const float *c_raw, const float *a_raw, float sat,
-                        const float *env_base, int H, int W, int activation, const float *transform, float *out) {
+                        const float *env_base, int H, int W, int activation, const float *transform, const float *pdf,
+                        float p_diffuse, float p_light, int total_samples, float *out) {
     const EnvMap e = make_env(env_base, H, W, activation, transform);
+    const MisParams m = {pdf, p_diffuse, p_light};
     for (int64_t pt = 0; pt < P; ++pt) {
         ShadePoint p;
         shade_point_setup(normals + 3 * pt, viewdirs + 3 * pt, roughness[pt], base_color + 3 * pt, p);
@@ -31,7 +33,7 @@ void shade_host_forward(int64_t P, int S, const float *normals, const float *vie
         for (int s = 0; s < S; ++s) {
             const int64_t ray = pt * S + s;
             ShadeSample o;
-            shade_sample_forward(p, e, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, o);
+            shade_sample_forward(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, o);
             for (int c = 0; c < 3; ++c) {
                 acc[c] += p.fd[c] * o.transport[c];
                 acc[3 + c] += o.fs * o.transport[c];
@@ -41,20 +43,22 @@ void shade_host_forward(int64_t P, int S, const float *normals, const float *vie
             }
             acc[9] += o.vis;
         }
-        for (int j = 0; j < 16; ++j) out[16 * pt + j] = acc[j] / (float)S;
+        for (int j = 0; j < 16; ++j) out[16 * pt + j] = acc[j] / (float)total_samples;
     }
 }
 
 // g_point [P,16]: 0-2 base_color, 3 roughness, 4-6 normal (DIRECT dependence only), 7-9 viewdirs; g_dirs [P*S,3]
 void shade_host_backward(int64_t P, int S, const float *normals, const float *viewdirs, const float *roughness,
                          const float *base_color, const float *dirs, const float *c_raw, const float *a_raw, float sat,
-                         const float *env_base, int H, int W, int activation, const float *transform, const float *g_out,
+                         const float *env_base, int H, int W, int activation, const float *transform, const float *pdf,
+                         float p_diffuse, float p_light, int total_samples, const float *g_out,
                          float *g_c_raw, float *g_a_raw, float *g_dirs, float *g_point, float *grad_env) {
     const EnvMap e = make_env(env_base, H, W, activation, transform);
+    const MisParams m = {pdf, p_diffuse, p_light};
     for (int64_t pt = 0; pt < P; ++pt) {
         ShadePoint p;
         shade_point_setup(normals + 3 * pt, viewdirs + 3 * pt, roughness[pt], base_color + 3 * pt, p);
-        const float inv = 1.0f / (float)S;
+        const float inv = 1.0f / (float)total_samples;
         const float *go = g_out + 16 * pt;
         float gD[3], gS[3], gE[3], gLi[3], gLocal[3];
         for (int c = 0; c < 3; ++c) {
@@ -66,7 +70,7 @@ void shade_host_backward(int64_t P, int S, const float *normals, const float *vi
         shade_acc_zero(acc);
         for (int s = 0; s < S; ++s) {
             const int64_t ray = pt * S + s;
-            shade_sample_backward(p, e, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, gD, gS, gE, gVis, gLi, gLocal,
+            shade_sample_backward(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, gD, gS, gE, gVis, gLi, gLocal,
                                   grad_env, acc, g_c_raw + 3 * ray, g_a_raw[ray], g_dirs + 3 * ray);
         }
         float *o = g_point + 16 * pt;

@@ -15,7 +15,7 @@ from irgs_b200 import synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_shading.npz")
-CASES = ("eval24", "train64", "train40_sigmoid_xf", "eval33_none")
+CASES = ("eval24", "train64", "train40_sigmoid_xf", "eval33_none", "eval24_light12", "train32_light16_xf")
 T_MIN = 0.03
 
 
@@ -42,10 +42,20 @@ def test_shade_kernels_match_reference_golden(name):
                                                             "alpha_raw", "env_base")}
     az = t("in_azimuth") if "in_azimuth" in case else None
     tr = t("in_transform") if "in_transform" in case else None
-    S = int(case["S"])
-    out = shading.shade_incident(leaves["normals"], S, leaves["base_color"], leaves["roughness"], leaves["viewdirs"],
-                                 leaves["env_base"], leaves["color_raw"], leaves["alpha_raw"], azimuth=az,
-                                 activation=str(case["activation"]), transform=tr, transmittance_min=T_MIN)
+    S, Sl = int(case["S"]), int(case["n_light"]) if "n_light" in case else 0
+    common = dict(activation=str(case["activation"]), transform=tr, transmittance_min=T_MIN)
+    if Sl == 0:
+        out = shading.shade_incident(leaves["normals"], S, leaves["base_color"], leaves["roughness"], leaves["viewdirs"],
+                                     leaves["env_base"], leaves["color_raw"], leaves["alpha_raw"], azimuth=az, **common)
+    else:   # light_sample_num > 0: one call per kind of sample, the rows add up
+        mix = dict(pdf=t("in_pdf"), p_diffuse=S / (S + Sl), p_light=Sl / (S + Sl), total_samples=S + Sl)
+        od = shading.shade_incident(leaves["normals"], S, leaves["base_color"], leaves["roughness"], leaves["viewdirs"],
+                                    leaves["env_base"], leaves["color_raw"][:, :S], leaves["alpha_raw"][:, :S], azimuth=az,
+                                    **common, **mix)
+        ol = shading.shade_incident(leaves["normals"], Sl, leaves["base_color"], leaves["roughness"], leaves["viewdirs"],
+                                    leaves["env_base"], leaves["color_raw"][:, S:], leaves["alpha_raw"][:, S:],
+                                    dirs=t("in_light_dirs"), **common, **mix)
+        out = {k: od[k] + ol[k] for k in od}
     keys = [k for k in shading.OUT_SLICES if f"out_{k}" in case]
     assert len(keys) == (3 if bool(case["training"]) else 6)
     for k in keys:
@@ -192,8 +202,6 @@ def test_flags_empty_input_and_errors(small_scene):
     e = shading.rendering_equation(bc[:0], ro[:0], nrm[:0], pos[:0], view[:0], tr, surf, env, S, training=True)
     assert e["diffuse"].shape == (0, 3) and set(e) == {"diffuse", "specular", "light_direct"}
     with pytest.raises(NotImplementedError):
-        shading.rendering_equation(*args, light_sample_num=8)
-    with pytest.raises(NotImplementedError):
         shading.rendering_equation(*args, relight=True)
     with pytest.raises(ValueError):
         shading.shade_incident(nrm, S, bc, ro, view, env.base, torch.zeros(P, S + 1, 3, device=DEV), torch.zeros(P, S, device=DEV))
@@ -281,3 +289,77 @@ def test_rendering_equation_from_surfel_parameters(small_scene):
         b = torch.nan_to_num(res[1][1][k].double().flatten(), 0.0, 0.0, 0.0)
         assert torch.isfinite(a).all() and float(b.norm()) > 0, k
         assert float(a @ b / (a.norm() * b.norm() + 1e-300)) >= 0.9999, k
+
+
+def test_light_sampling_matches_the_oracle_and_the_unfused_composition(small_scene):
+    """light_sample_num > 0 (gaussian_renderer/__init__.py:340-357): EnvLight.update_pdf / light_pdf / sample_light_directions
+    against the oracle's restatement of scene/light.py:174-223, and rendering_equation with light samples against the
+    un-fused composition (tracer on materialised rays + the oracle's torch code) on the very same light directions."""
+    from irgs_b200 import shading
+    from irgs_b200.raytracer import GaussianTracer
+    sc, inp = small_scene
+    gen = torch.Generator().manual_seed(31)
+    env = shading.EnvLight(resolution=(16, 32), device=DEV)
+    env.base.data += (0.8 * torch.randn(16, 32, 3, generator=gen)).to(DEV)
+    env.update_pdf()
+    pdf_ref = osh.update_pdf(env.base.detach().cpu(), "exp")
+    assert float((env._pdf.cpu() - pdf_ref).abs().max()) <= 1e-6 * float(pdf_ref.max())
+    for training in (False, True):
+        d, p = env.sample_light_directions(4096, 8, training)
+        assert d.shape == (4096, 8, 3) and p.shape == (4096, 8, 1)
+        assert float((d.norm(dim=-1) - 1).abs().max()) <= 1e-5
+        pr = osh.light_pdf(pdf_ref, d.cpu())
+        assert float(((p.cpu() - pr).abs() / pr.clamp_min(1e-6)).median()) <= 1e-5
+        # texel frequencies follow the probabilities (32 768 draws over 512 texels)
+        l = d.reshape(-1, 3).cpu()
+        u = torch.atan2(l[:, 0], -l[:, 2]) / (2 * math.pi) + 0.5
+        v = torch.acos(l[:, 1].clamp(-1, 1)) / math.pi
+        idx = (u * 32).clamp(0, 31).long() + (v * 16).clamp(0, 15).long() * 32
+        freq = torch.bincount(idx, minlength=512).float() / idx.numel()
+        assert float((freq - pdf_ref.reshape(-1)).abs().max()) <= 6 * math.sqrt(float(pdf_ref.max()) / idx.numel())
+    # end to end with fixed light directions
+    g = {k: v.to(DEV) for k, v in inp.items()}
+    tr = GaussianTracer(transmittance_min=synth.T_MIN)
+    tr.build_from_surfels(g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], synth.ALPHA_MIN)
+    P, S, Sl = 64, 24, 16
+    idx = torch.randint(0, inp["means3D"].shape[0], (P,), generator=gen)
+    nrm = inp["normals"][idx].contiguous().to(DEV)
+    pos = (inp["means3D"][idx] + 0.01 * inp["normals"][idx]).contiguous().to(DEV)
+    view = torch.nn.functional.normalize(torch.tensor(synth.CAMERA_CENTER, dtype=torch.float32, device=DEV)[None] - pos, dim=-1)
+    azim = (torch.rand(P, generator=gen) * 2 * math.pi).to(DEV)
+    light_dirs, _ = env.sample_light_directions(P, Sl, True)
+    env.sample_light_directions = lambda B, n, training=False: (light_dirs, None)
+    keys_s = ("means3D", "opacity", "ru", "rv", "normals", "features", "shs")
+    w = [torch.randn(P, 3, generator=gen).to(DEV) for _ in range(3)]
+    res = []
+    for fused in (True, False):
+        leaf = {k: g[k].clone().requires_grad_(True) for k in keys_s}
+        pt = {"base_color": torch.rand(P, 3, generator=torch.Generator().manual_seed(5)).to(DEV).requires_grad_(True),
+              "roughness": (0.1 + 0.8 * torch.rand(P, 1, generator=torch.Generator().manual_seed(6))).to(DEV).requires_grad_(True),
+              "normals_pt": nrm.clone().requires_grad_(True), "position": pos.clone().requires_grad_(True)}
+        env.base.grad = None
+        surf = tuple(leaf[k] for k in keys_s)
+        if fused:
+            out = shading.rendering_equation(pt["base_color"], pt["roughness"], pt["normals_pt"], pt["position"], view, tr, surf,
+                                             env, S, training=True, azimuth=azim, light_sample_num=Sl, light_t_min=0.05,
+                                             alpha_min=synth.ALPHA_MIN)
+        else:
+            d = torch.cat([_torch_dirs(pt["normals_pt"], S, azim), light_dirs], dim=1)
+            color, _, _, _, alpha = tr.trace(pt["position"][:, None] + d * 0.05, d, *surf, synth.ALPHA_MIN)
+            areas = osh.mis_areas(d, env._pdf, S, Sl)
+            out = osh.rendering_equation(pt["base_color"], pt["roughness"], pt["normals_pt"], view, d, color, alpha, env.base,
+                                         "exp", None, synth.T_MIN, incident_areas=areas)
+        sum((out[k] * wi).sum() for k, wi in zip(("diffuse", "specular", "light_direct"), w)).backward()
+        res.append(({k: out[k].detach() for k in ("diffuse", "specular", "light_direct")},
+                    {**{k: v.grad for k, v in pt.items()}, **{k: leaf[k].grad for k in keys_s if k != "features"},
+                     "env_base": env.base.grad.clone()}))
+    for k in res[0][0]:
+        assert float((res[0][0][k] - res[1][0][k]).abs().max()) <= 1e-4 * max(1.0, float(res[1][0][k].abs().max())), k
+    for k in res[0][1]:
+        a = res[0][1][k].double().flatten()
+        b = torch.nan_to_num(res[1][1][k].double().flatten(), 0.0, 0.0, 0.0)
+        assert torch.isfinite(a).all() and float(b.norm()) > 0, k
+        assert float(a @ b / (a.norm() * b.norm() + 1e-300)) >= 0.9999, k
+    with pytest.raises(RuntimeError):
+        shading.rendering_equation(pt["base_color"], pt["roughness"], nrm, pos, view, tr, surf,
+                                   shading.EnvLight(resolution=(8, 16), device=DEV), S, light_sample_num=4)

@@ -17,7 +17,7 @@ from oracle import shading as osh
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden", "ref_shading.npz")
-CASES = ("eval24", "train64", "train40_sigmoid_xf", "eval33_none")
+CASES = ("eval24", "train64", "train40_sigmoid_xf", "eval33_none", "eval24_light12", "train32_light16_xf")
 OUT_KEYS = ("diffuse", "specular", "light_direct", "visibility", "light", "light_indirect")
 OUT_SLICES = {"diffuse": slice(0, 3), "specular": slice(3, 6), "light_direct": slice(6, 9), "visibility": slice(9, 10),
               "light": slice(10, 13), "light_indirect": slice(13, 16)}
@@ -35,15 +35,23 @@ def _oracle(case, dtype, dirs_leaf=False):
     leaves = {k: t("in_" + k).requires_grad_(True) for k in ("base_color", "roughness", "normals", "viewdirs", "color_raw",
                                                             "alpha_raw", "env_base")}
     transform = t("in_transform") if "in_transform" in case else None
+    n_light = int(case["n_light"]) if "n_light" in case else 0
     if dirs_leaf:
         dirs = t("rays_d").requires_grad_(True)
         leaves["dirs"] = dirs
     else:
         az = torch.from_numpy(case["in_azimuth"]).to(dtype) if "in_azimuth" in case else None
         dirs = osh.fibonacci_dirs(leaves["normals"], int(case["S"]), az)
+        if n_light > 0:
+            dirs = torch.cat([dirs, t("in_light_dirs")], dim=1)
+    areas = None
+    if n_light > 0:   # the light_sample_num > 0 branch: mixed-sampling weights from the (gradient-free) texel probabilities
+        pdf = osh.update_pdf(leaves["env_base"].detach().float(), str(case["activation"]))
+        assert np.abs(pdf.numpy() - case["in_pdf"]).max() <= 1e-6 * case["in_pdf"].max()
+        areas = osh.mis_areas(dirs, t("in_pdf"), int(case["S"]), n_light, transform)
     out = osh.rendering_equation(leaves["base_color"], leaves["roughness"], leaves["normals"], leaves["viewdirs"], dirs,
                                  leaves["color_raw"], leaves["alpha_raw"], leaves["env_base"], str(case["activation"]),
-                                 transform, T_MIN)
+                                 transform, T_MIN, incident_areas=areas)
     return leaves, out, dirs
 
 
@@ -82,14 +90,17 @@ def _p(a):
 
 def _host_args(case):
     f = lambda k: np.ascontiguousarray(case[k], np.float32)    # noqa: E731
-    P, S = case["in_normals"].shape[0], int(case["S"])
+    n_light = int(case["n_light"]) if "n_light" in case else 0
+    P, S = case["in_normals"].shape[0], int(case["S"]) + n_light         # the harness takes all samples as explicit directions
     env = f("in_env_base")
     tr = f("in_transform") if "in_transform" in case else None
+    pdf = f("in_pdf") if n_light > 0 else None
     arrs = dict(normals=f("in_normals"), view=f("in_viewdirs"), rough=f("in_roughness").reshape(-1), base=f("in_base_color"),
-                dirs=f("rays_d"), c=f("in_color_raw"), a=f("in_alpha_raw"), env=env, tr=tr)
+                dirs=f("rays_d"), c=f("in_color_raw"), a=f("in_alpha_raw"), env=env, tr=tr, pdf=pdf)
     head = [ctypes.c_int64(P), ctypes.c_int(S)] + [_p(arrs[k]) for k in ("normals", "view", "rough", "base", "dirs", "c", "a")] + \
            [ctypes.c_float(1 - T_MIN), _p(env), ctypes.c_int(env.shape[0]), ctypes.c_int(env.shape[1]),
-            ctypes.c_int(ACT[str(case["activation"])]), _p(tr)]
+            ctypes.c_int(ACT[str(case["activation"])]), _p(tr), _p(pdf), ctypes.c_float(int(case["S"]) / S),
+            ctypes.c_float(n_light / S), ctypes.c_int(S)]
     return P, S, arrs, head
 
 
@@ -132,13 +143,17 @@ def test_kernel_arithmetic_matches_reference_golden_on_the_host(host, name):
     # dL/d direction and the direct normal term: float64 autograd of the oracle with the directions as a leaf
     leaves, out64, _ = _oracle(case, torch.float64, dirs_leaf=True)
     sum((out64[k] * torch.from_numpy(case[f"w_{k}"]).double()).sum() for k in keys).backward()
-    close(g_d, leaves["dirs"].grad.numpy(), "dirs")
-    close(g_pt[:, 4:7], leaves["normals"].grad.numpy(), "normal (direct)")
+    # (only the Fibonacci samples: the light samples are constants of the pipeline, and in evaluation mode they sit exactly on
+    # texel centres, where the bilinear lookup has a kink and float32 / float64 pick different one-sided derivatives)
+    Sd_ = int(case["S"])
+    close(g_d.reshape(P, S, 3)[:, :Sd_], leaves["dirs"].grad.numpy().reshape(P, S, 3)[:, :Sd_], "dirs")
+    close(g_pt[:, 4:7], leaves["normals"].grad.numpy(), "normal (direct)", tol=5e-4)   # float32 sums against float64
     # and the full normal gradient = direct + chain through the oracle's differentiable sampling == the reference's
     n = torch.from_numpy(case["in_normals"]).double().requires_grad_(True)
     az = torch.from_numpy(case["in_azimuth"]).double() if "in_azimuth" in case else None
-    d = osh.fibonacci_dirs(n, S, az)
-    (d * torch.from_numpy(g_d.reshape(P, S, 3)).double()).sum().backward()
+    Sd = int(case["S"])                                   # only the Fibonacci samples depend on the normal
+    d = osh.fibonacci_dirs(n, Sd, az)
+    (d * torch.from_numpy(g_d.reshape(P, S, 3)[:, :Sd]).double()).sum().backward()
     close(g_pt[:, 4:7] + n.grad.numpy(), case["grad_normals"], "normal (total)", tol=5e-4)
 
 

@@ -195,7 +195,7 @@ def test_flags_empty_input_and_errors(small_scene):
     assert float(wo["light_indirect"].detach().abs().max()) == 0.0 and torch.equal(wo["visibility"], full["visibility"])
     assert torch.equal(wo["light_direct"], full["light_direct"])
     # a constant environment of radiance 0.5 (the initial value): light_direct is exactly that
-    assert float((full["light_direct"] - 0.5).abs().max()) <= 1e-6
+    assert float((full["light_direct"].detach() - 0.5).abs().max()) <= 1e-6
     det = shading.rendering_equation(bc.clone().requires_grad_(True), ro, nrm, pos.clone().requires_grad_(True), view, tr,
                                      tuple(t.clone().requires_grad_(True) for t in surf), env, S, detach_indirect=True)
     assert torch.equal(det["diffuse"], full["diffuse"])

@@ -32,9 +32,10 @@ struct ShadeArgs {
 };
 
 // direction of sample s of point pt: generated (q is filled, q.rotated tells whether it depends on the normal) or read
+template <bool MIX>
 __device__ __forceinline__ void sample_dir(const ShadeArgs &a, const float n[3], int64_t ray, int s, float az, IncidentSample &q,
                                            float d[3]) {
-    if (a.dirs != nullptr) {
+    if (MIX && a.dirs != nullptr) {
         d[0] = __ldg(a.dirs + 3 * ray); d[1] = __ldg(a.dirs + 3 * ray + 1); d[2] = __ldg(a.dirs + 3 * ray + 2);
         q.rotated = false; q.len = 1.f; q.zx = q.zy = q.zz = q.vx = q.vy = q.vz = 0.f;
         return;
@@ -61,6 +62,7 @@ __device__ __forceinline__ void load_point(const ShadeArgs &a, int64_t pt, float
 }
 
 // out [P,16]: 0-2 diffuse, 3-5 specular, 6-8 light_direct, 9 visibility, 10-12 light, 13-15 light_indirect (means over S)
+template <bool MIX>   // MIX: light_sample_num > 0 (explicit directions and / or mixed-sampling weights)
 __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *__restrict__ out) {
     const int64_t pt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,11 +78,11 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
         const int64_t ray = pt * a.S + s;
         IncidentSample q;
         float d[3];
-        sample_dir(a, n, ray, s, az, q, d);
+        sample_dir<MIX>(a, n, ray, s, az, q, d);
         const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
                                 __ldg(a.trace_color + 3 * ray + 2)};
         ShadeSample o;
-        shade_sample_forward(p, a.env, a.mis, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, o);
+        shade_sample_forward<MIX>(p, a.env, a.mis, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, o);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             acc[c] += p.fd[c] * o.transport[c];
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
 #define IRGS_SHADE_BWD_BLOCKS 4   // resident blocks per SM the register budget is set for.  Measured forward+backward per 2^22 rays:
                                   // no cap (135 registers, 3 blocks) 0.668 ms | 4 (128 registers, no spills) 0.614 | 5 (96 registers, spills) 0.634
 #endif
+template <bool MIX>
 __global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_kernel(ShadeArgs a, const float *__restrict__ g_out,
                                                              float *__restrict__ g_color, float *__restrict__ g_alpha,
                                                              float *__restrict__ g_point, float *__restrict__ grad_env) {
@@ -139,11 +142,11 @@ __global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_ker
         const int64_t ray = pt * a.S + s;
         IncidentSample q;
         float d[3];
-        sample_dir(a, n, ray, s, az, q, d);
+        sample_dir<MIX>(a, n, ray, s, az, q, d);
         const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
                                 __ldg(a.trace_color + 3 * ray + 2)};
         float g_c[3], g_a, gd[3];
-        shade_sample_backward(p, a.env, a.mis, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, gD, gS, gE, gVis, gLi, gLocal,
+        shade_sample_backward<MIX>(p, a.env, a.mis, d, c_raw, __ldg(a.trace_alpha + ray), a.saturate, gD, gS, gE, gVis, gLi, gLocal,
                               grad_env, acc, g_c, g_a, gd);
         g_color[3 * ray] = g_c[0]; g_color[3 * ray + 1] = g_c[1]; g_color[3 * ray + 2] = g_c[2];
         g_alpha[ray] = g_a;
@@ -261,7 +264,9 @@ int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, con
     if (make_args(gen, env, sampling, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
     if (a.n_points == 0) return 0;
     if (!out) return fail_msg("shade: null output array");
-    shade_forward_kernel<<<(unsigned)((a.n_points * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, out);
+    const unsigned grid = (unsigned)((a.n_points * 32 + 127) / 128);
+    if (sampling != nullptr) shade_forward_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, out);
+    else shade_forward_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a, out);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;
@@ -275,8 +280,11 @@ int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, co
     if (make_args(gen, env, sampling, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
     if (a.n_points == 0) return 0;
     if (!g_out || !g_trace_color || !g_trace_alpha || !g_point) return fail_msg("shade backward: null array");
-    shade_backward_kernel<<<(unsigned)((a.n_points * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        a, g_out, g_trace_color, g_trace_alpha, g_point, grad_env);
+    const unsigned grid = (unsigned)((a.n_points * 32 + 127) / 128);
+    if (sampling != nullptr)
+        shade_backward_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_trace_color, g_trace_alpha, g_point, grad_env);
+    else
+        shade_backward_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_trace_color, g_trace_alpha, g_point, grad_env);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;

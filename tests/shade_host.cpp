@@ -33,7 +33,8 @@ void shade_host_forward(int64_t P, int S, const float *normals, const float *vie
         for (int s = 0; s < S; ++s) {
             const int64_t ray = pt * S + s;
             ShadeSample o;
-            shade_sample_forward(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, o);
+            if (pdf) shade_sample_forward<true>(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, o);
+            else shade_sample_forward<false>(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, o);
             for (int c = 0; c < 3; ++c) {
                 acc[c] += p.fd[c] * o.transport[c];
                 acc[3 + c] += o.fs * o.transport[c];
@@ -70,8 +71,12 @@ void shade_host_backward(int64_t P, int S, const float *normals, const float *vi
         shade_acc_zero(acc);
         for (int s = 0; s < S; ++s) {
             const int64_t ray = pt * S + s;
-            shade_sample_backward(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, gD, gS, gE, gVis, gLi, gLocal,
-                                  grad_env, acc, g_c_raw + 3 * ray, g_a_raw[ray], g_dirs + 3 * ray);
+            if (pdf)
+                shade_sample_backward<true>(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, gD, gS, gE, gVis, gLi,
+                                            gLocal, grad_env, acc, g_c_raw + 3 * ray, g_a_raw[ray], g_dirs + 3 * ray);
+            else
+                shade_sample_backward<false>(p, e, m, dirs + 3 * ray, c_raw + 3 * ray, a_raw[ray], sat, gD, gS, gE, gVis, gLi,
+                                             gLocal, grad_env, acc, g_c_raw + 3 * ray, g_a_raw[ray], g_dirs + 3 * ray);
         }
         float *o = g_point + 16 * pt;
         std::memset(o, 0, 16 * sizeof(float));

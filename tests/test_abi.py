@@ -60,6 +60,9 @@ def test_sass_has_the_blackwell_instructions_the_design_relies_on():
     fwd = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4irgs20trace_forward_kernelILb0ELb0EEEvNS_7KParamsEP5uint4", lib],
                          capture_output=True, text=True).stdout
     assert len(re.findall(r"LDG\.E\S*\.256", fwd)) >= 4, "forward kernel lost its 256-bit loads"
+    # L1 policy of the walk: streaming data (records, SH rows) must not allocate in L1, tree nodes evict last
+    assert len(re.findall(r"LDG\.E\.NA\S*\.256", fwd)) >= 8, "records / SH rows must be loaded with L1::no_allocate"
+    assert len(re.findall(r"LDG\.E\.EL\S*\.256", fwd)) >= 2, "tree nodes must be loaded with L1::evict_last"
     bwd = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4irgs26trace_backward_flat_kernelILb0ELb1EEEvNS_7KParamsE", lib],
                          capture_output=True, text=True).stdout
     assert "UBLKRED" in bwd, "backward kernel lost its bulk reduction"

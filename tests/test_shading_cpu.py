@@ -177,3 +177,36 @@ def test_env_lookup_on_the_host_matches_the_oracle_at_the_seams(host):
             # atan2 / acos differ by an ulp between libm and torch: compare with a tolerance scaled by the texel contrast
             err = np.abs(out - ref)
             assert np.median(err) <= 1e-6 and (err > 1e-3 * max(1.0, np.abs(ref).max())).mean() < 2e-3, (act, res, err.max())
+
+
+@pytest.mark.parametrize("name", ["eval24_light12", "train32_light16_xf"])
+def test_oracle_light_sampling_matches_the_reference(name):
+    """scene/light.py:174-223 restated (oracle/shading.py) against what the unmodified EnvLight produced while the golden
+    vectors were recorded: texel probabilities, the densities of the drawn directions, and -- in evaluation mode, where the
+    draws sit on texel centres -- the directions themselves from the texel indices."""
+    case = load_case(name)
+    base = torch.from_numpy(case["in_env_base"])
+    tr = torch.from_numpy(case["in_transform"]) if "in_transform" in case else None
+    pdf = osh.update_pdf(base, str(case["activation"]))
+    assert np.abs(pdf.numpy() - case["in_pdf"]).max() <= 1e-6 * case["in_pdf"].max()
+    assert abs(float(pdf.sum()) - 1.0) <= 1e-5
+    dirs = torch.from_numpy(case["in_light_dirs"])
+    dens = osh.light_pdf(torch.from_numpy(case["in_pdf"]), dirs, tr).numpy()
+    assert np.abs(dens - case["light_pdfs"]).max() <= 1e-5 * np.abs(case["light_pdfs"]).max()
+    # the texel every direction came from, and back
+    H, W = pdf.shape
+    l = dirs.reshape(-1, 3) if tr is None else dirs.reshape(-1, 3) @ tr.T
+    u = torch.atan2(l[:, 0], -l[:, 2]) / (2 * np.pi) + 0.5
+    v = torch.acos(l[:, 1].clamp(-1, 1)) / np.pi
+    idx = (u * W).clamp(0, W - 1).long() + (v * H).clamp(0, H - 1).long() * W
+    assert float(torch.from_numpy(case["in_pdf"]).reshape(-1)[idx].min()) > 0        # only texels with probability are drawn
+    back = osh.light_dirs_from_texels(idx, H, W, transform=tr).reshape(dirs.shape)
+    if not bool(case["training"]):
+        assert float((back - dirs).abs().max()) <= 2e-6                              # texel centres
+    else:                                                                            # jittered inside the texel
+        assert float((back - dirs).norm(dim=-1).max()) <= 1.5 * np.pi / min(H, W)
+    # mixed-sampling weights of all samples: finite, positive, bounded by the clamp
+    S, Sl = int(case["S"]), int(case["n_light"])
+    areas = osh.mis_areas(torch.from_numpy(case["rays_d"]), torch.from_numpy(case["in_pdf"]), S, Sl, tr)
+    assert areas.shape == (dirs.shape[0], S + Sl, 1) and bool(torch.isfinite(areas).all())
+    assert float(areas.min()) > 0 and float(areas.max()) <= 2 * np.pi * (S + Sl) / S + 1e-3

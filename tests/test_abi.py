@@ -100,3 +100,35 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src, f
+
+
+def test_argument_validation_needs_no_gpu():
+    """Error behaviour of the boundary: invalid arguments are rejected on the host, before any CUDA call, with a non-zero
+    status and a message from irgs_last_error() (the Python layer maps that to RuntimeError)."""
+    from irgs_b200 import _lib
+    from irgs_b200.incident import IncidentDesc
+    from irgs_b200.shading import EnvDesc, SamplingDesc
+    lib = _lib.load()
+    err = lambda: lib.irgs_last_error().decode()                              # noqa: E731
+    dummy = ctypes.create_string_buffer(256)
+    ptr = ctypes.cast(dummy, ctypes.c_void_p)
+    gen = IncidentDesc(ptr, ptr, None, 4, 8, 0.05)
+    env = EnvDesc(ptr, 4, 8, 1, 0)
+    args = (ptr, ptr, ptr, ptr, ptr, ctypes.c_float(0.97), ptr, None)
+    assert lib.irgs_shade_forward(None, ctypes.byref(env), None, *args) != 0 and "incident" in err()
+    assert lib.irgs_shade_forward(ctypes.byref(gen), None, None, *args) != 0 and "environment" in err()
+    assert lib.irgs_shade_forward(ctypes.byref(IncidentDesc(ptr, ptr, None, 4, 0, 0.05)), ctypes.byref(env), None, *args) != 0
+    assert lib.irgs_shade_forward(ctypes.byref(gen), ctypes.byref(EnvDesc(ptr, 4, 8, 7, 0)), None, *args) != 0 and "activation" in err()
+    assert lib.irgs_shade_forward(ctypes.byref(gen), ctypes.byref(EnvDesc(ptr, 0, 8, 1, 0)), None, *args) != 0
+    few = SamplingDesc(None, ptr, 0.5, 0.5, 4)                                 # total_samples < the samples of the call
+    assert lib.irgs_shade_forward(ctypes.byref(gen), ctypes.byref(env), ctypes.byref(few), *args) != 0 and "total_samples" in err()
+    assert lib.irgs_env_lookup_forward(ctypes.byref(env), ptr, -1, ptr, None) != 0
+    assert lib.irgs_env_lookup_forward(None, ptr, 4, ptr, None) != 0
+    # an empty batch is not an error and launches nothing
+    assert lib.irgs_shade_forward(ctypes.byref(IncidentDesc(None, None, None, 0, 8, 0.05)), ctypes.byref(env), None, *args) == 0
+    assert lib.irgs_env_lookup_forward(ctypes.byref(env), None, 0, None, None) == 0
+    # tracer entry points without a handle
+    assert lib.irgs_trace_forward(None, 4, 0, 16, 3, ptr, ptr, *([None] * 14), 0, ctypes.c_float(0.0), ctypes.c_float(0.0), 0, None) != 0
+    assert "handle" in err()
+    assert lib.irgs_trace_forward(None, 4, 0, 16, 3, *([None] * 16), 0, ctypes.c_float(0.0), ctypes.c_float(0.0), 0, None) != 0
+    assert lib.irgs_set_option(None, b"slot", 0) != 0

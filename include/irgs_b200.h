@@ -231,6 +231,10 @@ int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const 
  * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 
+/* The multiplier m of that stride order for a call of n_rays rays (the i-th ray started is (i * m) mod n_rays), 0 when the
+ * caller's order is kept (fewer than 64 or more than 2^19 rays).  Pure host function, exposed for tests. */
+int64_t irgs_stride_multiplier(int64_t n_rays);
+
 /* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with
  * irgs_set_stats(h, 1): sums over rays of node visits, surfel tests, composited hits, traversal passes. */
 int irgs_set_stats(irgs_tracer_t *h, int enable);

@@ -476,6 +476,8 @@ int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int 
                            grad_fused, grad_features, alpha_min, T_min, back_culling, chunk_rays);
 }
 
+int64_t irgs_stride_multiplier(int64_t n_rays) { return stride_multiplier(n_rays); }
+
 int64_t irgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void irgs_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
 

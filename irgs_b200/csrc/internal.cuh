@@ -163,6 +163,7 @@ struct TraceArgs {
 };
 int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
+int64_t stride_multiplier(int64_t n_rays);
 int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s);
 int launch_incident_backward(const float *position, const float *normals, const float *azimuth, int64_t n_points,

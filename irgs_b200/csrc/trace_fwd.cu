@@ -610,6 +610,17 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
     return 0;
 }
 
+// Multiplier of the stride start order of small launches: the i-th ray started is (i * m) mod n.  m is odd, coprime to n
+// (a bijection on [0, n)) and small enough that i * m < 2^32 for every i < n <= 2^19 (the kernel multiplies in 32 bits);
+// ~0.618 * 2^13, so that consecutive starts are ~20 pixel bundles apart.  0: keep the caller's order.
+int64_t stride_multiplier(int64_t n_rays) {
+    if (n_rays < 64 || n_rays > ((int64_t)1 << 19)) return 0;
+    int64_t m = 5063;
+    auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
+    while (gcd(m, n_rays) != 1) m += 2;
+    return m < 8192 ? m : 0;
+}
+
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     KParams p;
     p.a = a; p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + h->slot; p.stats = h->stats;
@@ -627,12 +638,7 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     // warps: 2^12 / 2^14 / 2^16 / 2^18 / 2^19 rays 0.84 / 0.92 / 1.01 / 1.14 / 1.41 ms -> 0.62 / 0.63 / 0.73 / 1.00 / 1.36 ms
     // (scripts/stride_check.py); from 2^20 rays on throughput counts and the orders tie (2.19 ms), so large launches keep
     // the caller's order.  Results are written per ray id either way.
-    if (p.a.ray_order == nullptr && a.n_rays >= 64 && a.n_rays <= h->stride_rays_max && a.n_rays <= ((int64_t)1 << 19)) {
-        int64_t m = 5063;   // odd, ~0.618 * 2^13: consecutive starts are ~20 pixel bundles apart; i * m < 2^32 for i < 2^19
-        auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
-        while (gcd(m, a.n_rays) != 1) m += 2;
-        p.a.ray_mul = m;
-    }
+    if (p.a.ray_order == nullptr && a.n_rays <= h->stride_rays_max) p.a.ray_mul = stride_multiplier(a.n_rays);
     // rays that hit nothing are never written by the kernel
     const size_t R = (size_t)a.n_rays;
     IRGS_CHECK(cudaMemsetAsync(a.color, 0, sizeof(float) * 3 * R, s));

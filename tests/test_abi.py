@@ -132,3 +132,22 @@ def test_argument_validation_needs_no_gpu():
     assert "handle" in err()
     assert lib.irgs_trace_forward(None, 4, 0, 16, 3, *([None] * 16), 0, ctypes.c_float(0.0), ctypes.c_float(0.0), 0, None) != 0
     assert lib.irgs_set_option(None, b"slot", 0) != 0
+
+
+def test_stride_start_order_is_a_bijection_in_32_bits():
+    """Small launches start their rays in the order (i * m) mod n (trace_fwd.cu launch_trace_forward); the kernel multiplies in
+    32 bits.  For a spread of n: m is odd, coprime to n, i * m never overflows, and the map is a permutation of [0, n)."""
+    import math
+    import numpy as np
+    from irgs_b200 import _lib
+    lib = _lib.load()
+    assert lib.irgs_stride_multiplier(63) == 0 and lib.irgs_stride_multiplier((1 << 19) + 1) == 0
+    sizes = [64, 65, 100, 255, 256, 4096, 5063, 5063 * 3, 61 * 83 * 7, 65536, 99991, 1 << 18, (1 << 18) + 3, 3 * 5 * 7 * 11 * 13 * 17,
+             2 * 3 * 5 * 7 * 11 * 13 * 17, 510510 - 1, (1 << 19) - 1, 1 << 19]
+    for n in sizes:
+        m = lib.irgs_stride_multiplier(n)
+        assert m > 0 and m % 2 == 1 and m < 8192 and math.gcd(m, n) == 1, (n, m)
+        assert (n - 1) * m < 2 ** 32
+        i = np.arange(n, dtype=np.uint32)
+        perm = (i * np.uint32(m)) % np.uint32(n)                    # the kernel's arithmetic
+        assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32)), n

@@ -112,7 +112,7 @@ IRGS_HD void env_fetch(const EnvMap &e, const EnvTap &t, float raw[3], float env
 
 // Backward of env_fetch + env_tap: g_env = dL/denv[3].  Adds the texel gradients into grad_base (may be null) and returns
 // dL/d(direction) in gd[3] (added).
-IRGS_HD void env_backward(const EnvMap &e, const EnvTap &t, const float raw[3], const float env[3], const float g_env[3],
+IRGS_HD void env_backward(const EnvMap &e, const EnvTap &t, const float raw[3], const float /*env*/[3], const float g_env[3],
                           float *grad_base, float gd[3]) {
     float g_u = 0.f, g_v = 0.f;
 #pragma unroll

@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--e2e-chunk", type=int, default=0, help="rays per chunk of the host-buffer path (0: chosen from the shard size)")
     p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
     p.add_argument("--no-shade", action="store_true", help="skip the rendering-equation measurement (fused generation + shading epilogue)")
+    p.add_argument("--no-other", action="store_true", help="skip the other BASELINE.json configurations (C2, C4, C5) and the small-call timings")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     p.add_argument("--ref-rays", type=int, default=1 << 22, help="rays per step of the reference arm's bounded sample")
@@ -185,6 +186,211 @@ def cpu_baseline(S, rays_o, rays_d, seconds):
     return {"value": n / dt, "unit": "rays/s", "cores": oracle.num_threads(), "kind": "port",
             "sample": f"first {n} rays of rank 0's shard, forward+backward, {dt:.1f} s"}
 
+
+
+# ------------------------------------------------------------------------------------------------ other configurations
+def _median_ms(fn, reps, sync):
+    """Median over `reps` of the CUDA-event time of fn() on the current stream."""
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        sync()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def measure_small_calls(tracer, inp, rays_o, rays_d, device):
+    """The call sizes the unmodified IRGS issues (trace_num_rays = 2^18, arguments/__init__.py:154; evaluation chunks of 2^20,
+    gaussian_renderer/__init__.py:314-315) through GaussianTracer.trace + autograd, one call at a time on one stream."""
+    from irgs_b200 import synth
+    out = {}
+    leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
+    was = tracer.accumulate_grads
+    tracer.accumulate_grads = False
+    for lg in (18, 20):
+        n = min(1 << lg, rays_o.shape[0])
+        o, d = rays_o[:n], rays_d[:n]
+        g = make_gout(n, device)
+
+        def fwd():
+            with torch.no_grad():
+                tracer.trace(o, d, inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"],
+                             synth.ALPHA_MIN)
+
+        def fwd_bwd():
+            outs = tracer.trace(o, d, leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], None,
+                                leaf["shs"], synth.ALPHA_MIN)
+            torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]], [g[0], g[1], g[3], g[4]])
+            for v in leaf.values():
+                v.grad = None
+
+        for f in (fwd, fwd_bwd):
+            for _ in range(3):
+                f()
+        torch.cuda.synchronize()
+        f_ms, fb_ms = _median_ms(fwd, 15, torch.cuda.synchronize), _median_ms(fwd_bwd, 15, torch.cuda.synchronize)
+        out[f"2^{lg}"] = {"rays": n, "fwd_ms": f_ms, "fwd_bwd_ms": fb_ms, "fwd_bwd_rays_per_s": n / (fb_ms * 1e-3)}
+    tracer.accumulate_grads = was
+    return out
+
+
+def measure_c2(tracer, inp, args, device):
+    """C2: 300k surfels, 800 x 800 primary rays, forward + backward, one call (this rank alone; N > 1 runs replicas)."""
+    from irgs_b200 import synth
+    o, d = synth.primary_rays(args.img, args.img, device=device)
+    n = o.shape[0]
+    g = make_gout(n, device)
+    leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
+    was = tracer.accumulate_grads
+    tracer.accumulate_grads = False
+
+    def fwd_bwd():
+        outs = tracer.trace(o, d, leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], None, leaf["shs"],
+                            synth.ALPHA_MIN)
+        torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]], [g[0], g[1], g[3], g[4]])
+        for v in leaf.values():
+            v.grad = None
+
+    for _ in range(3):
+        fwd_bwd()
+    torch.cuda.synchronize()
+    ms = _median_ms(fwd_bwd, 9, torch.cuda.synchronize)
+    tracer.accumulate_grads = was
+    return {"workload": f"C2: {args.surfels} surfels, {args.img}x{args.img} primary rays, fwd+bwd, one call per GPU",
+            "rays": n, "ms": ms, "value": n / (ms * 1e-3), "unit": "rays/s"}
+
+
+def measure_c4(tracer, inp, args, device, rank, world, chunk, steps, sync_all):
+    """C4, the relighting evaluation shape: per pixel 512 Fibonacci (evaluation mode: no random rotation) + 256 directions
+    drawn from the environment map (EnvLight.sample_light_directions), S = 4 feature channels (base colour + roughness, the
+    relight branch's `features`, gaussian_renderer/__init__.py:363-364), forward only, pixels sharded over the ranks."""
+    from irgs_b200 import parallel, shading, synth
+    pts, nrm, _ = build_workload.points                       # this rank's shading points
+    n_pts = pts.shape[0]
+    n_diff, n_light = 2 * args.spp, args.spp                  # 512 + 256 at the default spp
+    gen = torch.Generator(device).manual_seed(31)
+    feats = torch.rand(inp["means3D"].shape[0], 4, device=device, generator=gen)
+    env = shading.EnvLight(resolution=(256, 512), activation="exp", device=device)
+    env.base.data += 0.5 * torch.randn(env.base.shape, device=device, generator=gen)
+    env.update_pdf()
+    torch.manual_seed(41 + rank)
+    pchunk_d = max(1, chunk // n_diff)
+    pchunk_l = max(1, chunk // n_light)
+    surf = (inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], feats, inp["shs"])
+    acc = torch.zeros(2, device=device, dtype=torch.float64)
+
+    def step():
+        def diffuse(b, e):
+            o = tracer.trace_incident(pts[b:e], nrm[b:e], n_diff, *surf, synth.ALPHA_MIN, t_min=synth.LIGHT_T_MIN)
+            acc[0] += o[4].sum(dtype=torch.float64)
+
+        def light(b, e):
+            dirs, _ = env.sample_light_directions(e - b, n_light, False)
+            o = tracer.trace(pts[b:e, None] + dirs * synth.LIGHT_T_MIN, dirs, *surf, synth.ALPHA_MIN)
+            acc[1] += o[2].sum(dtype=torch.float64)
+        with torch.no_grad():
+            tracer.run_chunks(n_pts, pchunk_d, diffuse)
+            tracer.run_chunks(n_pts, pchunk_l, light)
+
+    step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device) / steps
+    n_total = args.img * args.img * (n_diff + n_light)
+    return {"workload": f"C4: {args.surfels} surfels, {args.img}x{args.img}x({n_diff}+{n_light}) rays, S=4 features, forward only, "
+                        f"ray-sharded over {world} GPU(s); diffuse rays generated in-kernel (trace_incident), light rays drawn "
+                        "from a 256x512 environment map inside the timed region and traced through GaussianTracer.trace",
+            "rays_per_step": n_total, "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "rays/s", "steps": steps,
+            "alpha_checksum": float(acc[0].item()), "feature_checksum": float(acc[1].item())}
+
+
+def measure_c5(args, device, rank, world, steps, sync_all):
+    """C5: 1M-surfel stress scene; EVERY step perturbs the geometry (an optimiser update), refits the acceleration structure
+    (GaussianTracer.update_from_surfels: topology frozen, like optixAccelBuild UPDATE, train.py:150-154), traces forward +
+    backward over this rank's share of 800 x 800 x 256 secondary rays and sums the [N,64] gradient buffer over the ranks with
+    the one all-reduce (256 MB at N = 1M)."""
+    from irgs_b200 import parallel, synth
+    from irgs_b200.raytracer import GaussianTracer
+    n_surf = 1000000
+    sc = synth.make_scene(n_surf, device=device)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    tracer = GaussianTracer(transmittance_min=synth.T_MIN, device=device)
+    tracer.build_from_surfels(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], synth.ALPHA_MIN)
+    o, d = synth.primary_rays(args.img, args.img, device=device)
+    with torch.no_grad():
+        outs = tracer.trace(o, d, inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"],
+                            synth.ALPHA_MIN)
+    pts, nrm = synth.shading_points_from_primary(o, d, outs[3], outs[4], outs[1])
+    pix = parallel.shard_interleaved(args.img * args.img, rank, world, block=32)
+    gen = torch.Generator().manual_seed(synth.RAY_SEED)
+    azim = (torch.rand(args.img * args.img, generator=gen)[pix] * 2 * np.pi).to(device)
+    pix = pix.to(device)
+    pts, nrm = pts[pix].contiguous(), nrm[pix].contiguous()
+    n_pts = pts.shape[0]
+    n_local = n_pts * args.spp
+    chunk = min(1 << 24, max(1 << 20, 1 << (max(1, (n_local + 3) // 4) - 1).bit_length()), n_local)
+    pchunk = max(1, chunk // args.spp)
+    gout = make_gout(pchunk * args.spp, device)
+    gout = [g.view(pchunk, args.spp, *g.shape[1:]) if g.numel() else g for g in gout]
+    means = inp["means3D"].clone()
+    leaf = {k: inp[k].clone().requires_grad_(True) for k in ("opacity", "ru", "rv", "normals", "shs")}
+    g2 = torch.Generator(device).manual_seed(17)
+    noise = 2e-4 * torch.randn(means.shape, device=device, generator=g2)     # the same update on every rank (same seed)
+    tracer.accumulate_grads = True
+    ev = {"refit": [], "allreduce": []}
+
+    def step(record):
+        means.add_(noise)
+        noise.neg_()
+        m = means.detach().requires_grad_(True)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        tracer.update_from_surfels(m, leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], synth.ALPHA_MIN)
+        r1.record()
+
+        def body(b, e):
+            outs = tracer.trace_incident(pts[b:e], nrm[b:e], args.spp, m, leaf["opacity"], leaf["ru"], leaf["rv"],
+                                         leaf["normals"], None, leaf["shs"], synth.ALPHA_MIN, azimuth=azim[b:e],
+                                         t_min=synth.LIGHT_T_MIN)
+            torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]],
+                                    [gout[0][:e - b], gout[1][:e - b], gout[3][:e - b], gout[4][:e - b]])
+        tracer.run_chunks(n_pts, pchunk, body)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        parallel.allreduce_sum_(tracer._fused)                 # the one collective of the step
+        a1.record()
+        if record:
+            ev["refit"].append((r0, r1))
+            ev["allreduce"].append((a0, a1))
+        return tracer.flush_grads(K=16, opacity_shape=tuple(inp["opacity"].shape), all_reduce=False)
+
+    step(False)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        grads = step(True)
+    e1.record()
+    sync_all()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device) / steps
+    n_total = args.img * args.img * args.spp
+    med = lambda k: float(np.median([a.elapsed_time(b) for a, b in ev[k]]))   # noqa: E731
+    res = {"workload": f"C5: {n_surf} surfels, {args.img}x{args.img}x{args.spp} secondary rays (generated in-kernel), geometry "
+                       f"perturbed + refit every step, fwd+bwd, ray-sharded over {world} GPU(s), one all-reduce",
+           "rays_per_step": n_total, "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "rays/s", "steps": steps,
+           "refit_ms": med("refit"), "allreduce_ms": parallel.max_over_ranks(med("allreduce"), device),
+           "allreduce_bytes": int(n_surf * 64 * 4), "tree_depth": tracer.get_info("tree_depth"),
+           "grad_checksum": float(grads["shs"].abs().sum().item())}
+    del tracer
+    return res
 
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
@@ -428,6 +634,14 @@ def run_ours(args):
                "api": "irgs_trace_fwd_bwd_host (C ABI, pinned host rays) + all-reduce + gradient read-back"}
         del oh, dh
 
+    # the other BASELINE.json configurations at their stated sizes, and the call sizes IRGS itself issues
+    other, small = None, None
+    if not args.no_other:
+        small = measure_small_calls(tracer, inp, rays_o, rays_d, device)
+        other = {"C2": measure_c2(tracer, inp, args, device)}
+        other["C4"] = measure_c4(tracer, inp, args, device, rank, world, chunk, max(1, min(args.steps, 2)), sync_all)
+        other["C5"] = measure_c5(args, device, rank, world, max(1, min(args.steps, 2)), sync_all)
+
     if rank != 0:
         return
     peaks = {}
@@ -455,7 +669,8 @@ def run_ours(args):
                    "parallelism": f"ray-sharded dp{world} (32-pixel blocks round-robin), surfels+BVH replicated, one all-reduce of N x 64 floats",
                    "l2": "inputs (3.9 GB of rays per step) exceed L2; no flush needed",
                    "shading_points": "all 640k bundles start on the surface (missed pixels re-assigned to hit pixels)"},
-        "e2e": e2e, "fused_generation": fused_gen, "rendering_equation": shaded, "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
+        "e2e": e2e, "fused_generation": fused_gen, "rendering_equation": shaded, "other_configs": other, "small_calls": small,
+        "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
         "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_ray * chunk,

@@ -225,8 +225,9 @@ int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const 
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.
  * "stride_rays_max": forward calls with at most this many rays (default and upper limit 2^19) start their rays in a stride
  * order instead of the caller's order (latency of small calls; 0 disables).
- * "slot": 0 (default) or 1 -- calls issued on two different streams at the same time must use different slots (each slot has
- * its own persistent-kernel work counter and candidate scratch).
+ * Calls issued on different streams at the same time are safe: every stream that launches on a handle owns a slot (work counter,
+ * candidate scratch) looked up from the call's own `stream`, so a backward uses the slot of the stream it runs on ("slot" is
+ * still accepted and ignored).  A handle is not thread-safe beyond that: do not build / refit while traces are in flight.
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
  * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
@@ -234,6 +235,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 /* The multiplier m of that stride order for a call of n_rays rays (the i-th ray started is (i * m) mod n_rays), 0 when the
  * caller's order is kept (fewer than 64 or more than 2^19 rays).  Pure host function, exposed for tests. */
 int64_t irgs_stride_multiplier(int64_t n_rays);
+
+/* Introspection (tests, diagnostics): "tree_depth" (levels of the PLOC tree of the last build; 0 = Karras tree), "ploc_iterations",
+ * "n_slots" (streams seen so far), "n_surfels".  -1 for unknown names. */
+int64_t irgs_get_info(irgs_tracer_t *h, const char *name);
 
 /* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with
  * irgs_set_stats(h, 1): sums over rays of node visits, surfel tests, composited hits, traversal passes. */

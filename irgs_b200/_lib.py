@@ -43,6 +43,7 @@ PROTOTYPES = {
     "irgs_launch_count": (_i64, []),
     "irgs_reset_launch_count": (None, []),
     "irgs_set_option": (_i32, [_vp, ctypes.c_char_p, _i64]),
+    "irgs_get_info": (_i64, [_vp, ctypes.c_char_p]),
     "irgs_set_stats": (_i32, [_vp, _i32]),
     "irgs_get_stats": (_i32, [_vp, ctypes.POINTER(_i64)]),
 }

@@ -38,6 +38,20 @@ static int fail(const char *msg) {
     return 1;
 }
 
+// The slot of a stream: found or assigned on first use.  When more than MAX_SLOTS distinct streams have been seen the device
+// is synchronised (nothing of this handle is in flight afterwards) and the table starts over.
+int slot_for(irgs_tracer *h, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(h->slot_mutex);
+    for (int i = 0; i < h->n_slots; ++i)
+        if (h->slot_stream[i] == s) return i;
+    if (h->n_slots == irgs_tracer::MAX_SLOTS) {
+        if (!check(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -1;
+        h->n_slots = 0;
+    }
+    h->slot_stream[h->n_slots] = s;
+    return h->n_slots++;
+}
+
 static int validate_trace(const irgs_tracer *h, int64_t n_rays, int S, int K, int deg, int hit_cap) {
     if (!h) return fail("null tracer handle");
     if (!h->built) return fail("trace called before build_bvh");
@@ -77,12 +91,12 @@ int irgs_tracer_create(irgs_tracer_t **out, int device) {
     }
     h->sm_count = prop.multiProcessorCount;
     if (!check(cudaMalloc(&h->scene, 24 * sizeof(float)), "cudaMalloc") ||
-        !check(cudaMalloc(&h->counter, 4 * sizeof(unsigned long long)), "cudaMalloc") ||
-        !check(cudaMalloc(&h->stats, 4 * sizeof(unsigned long long)), "cudaMalloc")) {
+        !check(cudaMalloc(&h->counter, irgs_tracer::MAX_SLOTS * sizeof(unsigned long long)), "cudaMalloc") ||
+        !check(cudaMalloc(&h->stats, 8 * sizeof(unsigned long long)), "cudaMalloc")) {
         irgs_tracer_destroy(h);
         return 1;
     }
-    cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(h->stats, 0, 8 * sizeof(unsigned long long));
     *out = h;
     return 0;
 }
@@ -94,10 +108,11 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->qnodes4); cudaFree(h->even); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
     cudaFree(h->ploc_cid); cudaFree(h->ploc_box); cudaFree(h->ploc_nn); cudaFree(h->ploc_counts); cudaFree(h->ploc_offs); cudaFree(h->ploc_totals);
-    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->inv_order); cudaFree(h->counter); cudaFree(h->stats); cudaFree(h->cand);
-    for (int i = 0; i < 2; ++i) {
+    cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->inv_order); cudaFree(h->counter); cudaFree(h->stats);
+    for (int i = 0; i < irgs_tracer::MAX_SLOTS; ++i) {
         for (int k = 0; k < 2; ++k) { cudaFree(h->rsort_keys[i][k]); cudaFree(h->rsort_vals[i][k]); }
         cudaFree(h->rsort_hist[i]);
+        cudaFree(h->cand[i]);
     }
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
@@ -425,14 +440,12 @@ static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, i
         a.n_rays = c; a.rays_o = d_o; a.rays_d = d_d;
         a.color = d_col; a.normal = d_nrm; a.feature = d_feat; a.depth = d_dep; a.alpha = d_alp;
         if (with_backward) { a.hit_count = d_cnt; a.hits = d_hits; a.hit_cap = hit_cap; }
-        h->slot = si;  // each stream has its own persistent-kernel work counter and scratch
-        int rc = launch_trace_forward(h, a, s);
+        int rc = launch_trace_forward(h, a, s);   // each stream has its own work counter and scratch (slot_for)
         if (!rc && with_backward) {
             a.gC = gC; a.gN = gN; a.gF = gF; a.gD = gD; a.gO = gO; a.gout_period = gout_period; a.gout_offset = done;
             a.g_rays_o = d_go; a.g_rays_d = d_gd; a.grad_fused = grad_fused; a.grad_features = grad_features;
             rc = launch_trace_backward(h, a, s);
         }
-        h->slot = h->slot_default;
         if (rc) return 1;
         IRGS_CHECK(cudaEventRecord(h->ring_free[rb], s));   // the rays of this chunk have been consumed
         if (out_color_host) IRGS_CHECK(cudaMemcpyAsync(out_color_host + 3 * done, d_col, sizeof(float) * 3 * c, cudaMemcpyDeviceToHost, s));
@@ -499,11 +512,7 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->stride_rays_max = value < 0 ? 0 : value;
         return 0;
     }
-    if (strcmp(name, "slot") == 0) {   // which of the two work-counter / scratch sets the following device-path calls use
-        h->slot_default = value == 1 ? 1 : 0;
-        h->slot = h->slot_default;
-        return 0;
-    }
+    if (strcmp(name, "slot") == 0) return 0;   // accepted for compatibility: slots follow the stream of each call now
     if (strcmp(name, "builder") == 0) {   // takes effect at the next build_bvh / build_from_surfels
         h->builder = value == 1 ? 1 : 0;
         return 0;
@@ -513,6 +522,24 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         return 0;
     }
     return fail("unknown option");
+}
+
+int64_t irgs_get_info(irgs_tracer_t *h, const char *name) {
+    if (!h || !name) return -1;
+    if (strcmp(name, "tree_depth") == 0) return h->tree_depth;        // 0: Karras tree (depth <= 62 by construction)
+    if (strcmp(name, "ploc_iterations") == 0) return h->ploc_iterations;
+    if (strcmp(name, "n_slots") == 0) return h->n_slots;
+    if (strcmp(name, "n_surfels") == 0) return h->built ? h->n : 0;
+    if (strcmp(name, "grazing_pairs") == 0 || strcmp(name, "grazing_pairs_compositing") == 0) {
+        // statistics of the last forward with irgs_set_stats(h, 1): ray / surfel pairs with |n.d| < 1e-3 that cross the surfel's
+        // support geometrically (dropped by the hit test; the reference evaluates them with its clamped depth), and how many of
+        // them that clamped evaluation would have composited
+        DeviceGuard guard(h->device);
+        unsigned long long v = 0;
+        if (cudaMemcpy(&v, h->stats + (strcmp(name, "grazing_pairs") == 0 ? 4 : 5), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int64_t)v;
+    }
+    return -1;
 }
 
 int irgs_set_stats(irgs_tracer_t *h, int enable) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/irgs_b200.h"
@@ -77,6 +78,7 @@ struct irgs_tracer {
     float *ploc_box = nullptr;          // [2][cap] PLOC cluster bounds, 8 floats each
     int *ploc_nn = nullptr, *ploc_counts = nullptr, *ploc_offs = nullptr, *ploc_totals = nullptr;
     int builder = 0;                    // 0: PLOC over the Morton order (default), 1: Karras LBVH
+    int ploc_iterations = 0;            // clustering iterations of the last PLOC build
     int tree_depth = 0;                 // depth of the PLOC tree of the last build (0: Karras tree, depth <= 62 by construction)
     int *radix_hist = nullptr;          // [256 * n_tiles]
     int64_t radix_tiles_cap = 0;
@@ -84,16 +86,21 @@ struct irgs_tracer {
                                         //       12-14 quantisation frame lo, 15-17 cell size, 18-23 bounds of the surfel boxes (ordered ints)
     irgs::SurfelRec *recs = nullptr;    // [n] leaf order
     int *inv_order = nullptr;           // [n] surfel id -> leaf position (written with the records)
-    unsigned long long *counter = nullptr;  // persistent-kernel work counters [4], one per concurrent stream slot
-    int slot = 0;                           // which counter / scratch region the next launch uses (host path: 0 / 1)
-    int slot_default = 0;                   // device path: set with irgs_set_option("slot"), one per concurrently used stream
-    uint4 *cand = nullptr;                  // forward kernel candidate scratch: [2 slots][threads][32] (t, id, alpha, -)
-    int64_t cand_threads = 0;               // threads one slot has room for
+    // Stream slots: every CUDA stream that launches on this handle owns one slot -- a persistent-kernel work counter, a
+    // candidate scratch region and a sort scratch -- looked up from the stream of the call itself (slot_for), so that a
+    // backward always uses the slot of the stream it runs on and calls on different streams never share one.
+    static constexpr int MAX_SLOTS = 8;
+    cudaStream_t slot_stream[MAX_SLOTS] = {};
+    int n_slots = 0;
+    std::mutex slot_mutex;                  // autograd runs backward on its own host thread
+    unsigned long long *counter = nullptr;  // persistent-kernel work counters [MAX_SLOTS]
+    uint4 *cand[MAX_SLOTS] = {};            // forward kernel candidate scratch of a slot: [threads][32] (t, id, alpha, leaf position)
+    int64_t cand_threads[MAX_SLOTS] = {};   // threads the slot's scratch has room for
     // ray-coherence sort scratch, per stream slot
-    uint32_t *rsort_keys[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    int *rsort_vals[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    int *rsort_hist[2] = {nullptr, nullptr};
-    int64_t rsort_cap[2] = {0, 0};
+    uint32_t *rsort_keys[MAX_SLOTS][2] = {};
+    int *rsort_vals[MAX_SLOTS][2] = {};
+    int *rsort_hist[MAX_SLOTS] = {};
+    int64_t rsort_cap[MAX_SLOTS] = {};
     int bwd_carveout_pct = -1;              // backward replay kernel: carve-out hint in percent (-1: the driver's default)
     int carveout_pct = -1;                  // forward kernel: shared-memory carve-out hint in percent (-1: what the resident blocks need)
     int64_t stride_rays_max = 1 << 19;      // forward calls with at most this many rays start them in a stride order (0: never)
@@ -130,8 +137,9 @@ void count_launch(int n = 1);
 // lbvh.cu
 int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s);  // boxes[] already filled
 int lbvh_reserve(irgs_tracer *h, int64_t n);
-int launch_ray_order(irgs_tracer *h, const float *rays_o, const float *rays_d, int64_t n_rays, int **order_out,
+int launch_ray_order(irgs_tracer *h, int slot, const float *rays_o, const float *rays_d, int64_t n_rays, int **order_out,
                      cudaStream_t s);
+int slot_for(irgs_tracer *h, cudaStream_t s);   // capi.cu; -1 on error
 int launch_bounds_from_proxy(irgs_tracer *h, const float *verts, int vps, cudaStream_t s);
 int launch_bounds_from_surfels(irgs_tracer *h, const float *means, const float *opacity, const float *ru,
                                const float *rv, const float *normals, float alpha_min, cudaStream_t s);

@@ -294,10 +294,9 @@ __global__ void ray_key_kernel(const float *__restrict__ rays_o, const float *__
     vals[i] = i;
 }
 
-int launch_ray_order(irgs_tracer *h, const float *rays_o, const float *rays_d, int64_t n_rays, int **order_out,
+int launch_ray_order(irgs_tracer *h, int slot, const float *rays_o, const float *rays_d, int64_t n_rays, int **order_out,
                      cudaStream_t s) {
     const int n = (int)n_rays;
-    const int slot = h->slot;
     if (n_rays > h->rsort_cap[slot]) {
         IRGS_CHECK(cudaDeviceSynchronize());
         for (int k = 0; k < 2; ++k) {
@@ -389,7 +388,13 @@ __global__ void ploc_init_kernel(const float *__restrict__ boxes, const int *__r
     cbox[pos] = x;
 }
 
+// Merge cost of two clusters: the surface area of their union.  EMPTY clusters (surfels with opacity < alpha_min: inverted
+// bounds, all sorted to the end of the Morton order) cost nothing among themselves and are infinitely expensive for a
+// non-empty cluster, so that they pair up with each other -- a balanced subtree of depth log2(M) -- instead of being
+// absorbed one per iteration by the clusters at the end of the occupied range (M iterations and a chain of depth M).
 __device__ __forceinline__ float union_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
+    const bool ea = !(alo.x <= ahi.x), eb = !(blo.x <= bhi.x);
+    if (ea || eb) return (ea && eb) ? 0.f : INFINITY;
     const float ex = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
     const float ey = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y);
     const float ez = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
@@ -407,14 +412,24 @@ __global__ void __launch_bounds__(PLOC_TB) ploc_nn_kernel(const PlocBox *__restr
     const int i = blockIdx.x * PLOC_TB + threadIdx.x;
     if (i >= m) return;
     const float4 lo = s_lo[threadIdx.x + PLOC_R], hi = s_hi[threadIdx.x + PLOC_R];
+    // Ties go to the pair partner i ^ 1 first (then to the lowest index): where many costs are equal -- runs of empty or of
+    // identical clusters -- everybody picks its partner and all of them merge in one iteration.
     float best = INFINITY;
     int bj = -1;
+    {
+        const int j = i ^ 1;
+        if (j < m) {
+            const int dlt = j - i;
+            best = union_area(lo, hi, s_lo[threadIdx.x + PLOC_R + dlt], s_hi[threadIdx.x + PLOC_R + dlt]);
+            bj = j;
+        }
+    }
 #pragma unroll
     for (int dlt = -PLOC_R; dlt <= PLOC_R; ++dlt) {
         const int j = i + dlt;
         if (dlt == 0 || j < 0 || j >= m) continue;
         const float ar = union_area(lo, hi, s_lo[threadIdx.x + PLOC_R + dlt], s_hi[threadIdx.x + PLOC_R + dlt]);
-        if (ar < best || bj < 0) { best = ar; bj = j; }   // ties (and non-finite areas): the lowest index
+        if (ar < best || bj < 0) { best = ar; bj = j; }
     }
     nn[i] = bj;
 }
@@ -534,7 +549,9 @@ int ploc_build(irgs_tracer *h, cudaStream_t s) {
     ploc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, n, cid[0], cbox[0]);
     count_launch();
     int m = n, free_hi = n - 1, cur = 0;
+    h->ploc_iterations = 0;
     while (m > 1) {
+        ++h->ploc_iterations;
         const int nb = (m + PLOC_SB - 1) / PLOC_SB;
         ploc_nn_kernel<<<(m + PLOC_TB - 1) / PLOC_TB, PLOC_TB, 0, s>>>(cbox[cur], m, h->ploc_nn);
         ploc_count_kernel<<<nb, PLOC_SB, 0, s>>>(h->ploc_nn, m, h->ploc_counts);

@@ -795,7 +795,7 @@ static int persistent_grid(irgs_tracer *h, const void *kernel) {
     return h->sm_count * per_sm;
 }
 
-static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
+static KParams make_params(irgs_tracer *h, const TraceArgs &a, int slot) {
     KParams p;
     p.a = a;
     p.nodes = h->qnodes;
@@ -803,7 +803,7 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a) {
     p.qframe = h->scene + 12;
     p.recs = h->recs;
     p.inv_order = h->inv_order;
-    p.counter = h->counter + h->slot;
+    p.counter = h->counter + slot;
     p.stats = h->stats;
     return p;
 }
@@ -837,7 +837,9 @@ static void set_carveout(Kern kern, int pct) {
 }
 
 int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
-    KParams p = make_params(h, a);
+    const int slot = slot_for(h, s);
+    if (slot < 0) return 1;
+    KParams p = make_params(h, a, slot);
     const bool feat = a.S > 0;
     if (a.hits != nullptr && a.hit_count != nullptr) {
         const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
@@ -868,7 +870,7 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
 }
 
 int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s) {
-    KParams p = make_params(h, a);
+    KParams p = make_params(h, a, 0);   // no work counter in this kernel
     const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
     intersection_test_kernel<<<grid, TB, 0, s>>>(p, out);
     count_launch();

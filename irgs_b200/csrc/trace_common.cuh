@@ -214,6 +214,27 @@ __device__ __forceinline__ bool leaf_stage2(const float4 r2, const float4 r3, fl
     return alpha >= alpha_min;
 }
 
+// Diagnostics (statistics builds of the forward kernel only): is this one of the GRAZING pairs the hit test drops
+// (|n.d| < 1e-3, leaf_stage1) although the ray geometrically crosses the surfel's support inside the depth range -- i.e. a
+// pair the reference, whose candidates are proxy-triangle hits at the TRUE depth, would have evaluated with its clamped depth
+// formula (gaussiantrace_forward.cu:61-81)?  *composites: that clamped evaluation would have passed alpha >= alpha_min.
+__device__ __forceinline__ bool grazing_dropped(const RayCtx &r, const float4 r0, const float4 r1, const float4 r2, const float4 r3,
+                                                float alpha_min, bool *composites) {
+    const float relx = r.ox - r0.x, rely = r.oy - r0.y, relz = r.oz - r0.z;
+    const float og = dot3_rn(r1.x, r1.y, r1.z, relx, rely, relz), dg = dot3_rn(r1.x, r1.y, r1.z, r.dx, r.dy, r.dz);
+    *composites = false;
+    if (dg * dg >= 1e-6f || dg == 0.f) return false;
+    const float tt = -og / dg;
+    if (!(tt > T_EPS && tt < IRGS_T_SCENE_MAX)) return false;
+    const float qx = relx + tt * r.dx, qy = rely + tt * r.dy, qz = relz + tt * r.dz;
+    if (qx * qx + qy * qy + qz * qz > r0.w) return false;
+    const float tc = (-og * dg) / 1e-6f;   // the reference's clamped depth
+    const float px = relx + tc * r.dx, py = rely + tc * r.dy, pz = relz + tc * r.dz;
+    float a;
+    *composites = leaf_stage2(r2, r3, px, py, pz, alpha_min, a);
+    return true;
+}
+
 __device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__restrict__ rec, float alpha_min,
                                           int back_culling, float &t_out, int &g_out, float &alpha_out) {
     float4 q0, q1, q2, q3;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     const float alpha_min = a.alpha_min, T_min = a.T_min;
     const int back_culling = a.back_culling;
     uint4 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
-    unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0;
+    unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0, st_graze = 0, st_graze_comp = 0;
 
     int phase = PH_FETCH;
     bool pool_empty = false;  // warp-uniform
@@ -321,6 +321,12 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     // latencies: measured 2 % slower than issuing both loads up front (profiles/r01_sweeps.txt)
                     if (LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, q2, q3);
                     ok = leaf_stage2(q2, q3, px, py, pz, alpha_min, alpha);
+                }
+                if (STATS && has && !ok) {   // diagnostics: grazing pairs dropped by the hit test (first pass of a ray only)
+                    float4 s2 = q2, s3 = q3;
+                    if (LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, s2, s3);
+                    bool comp = false;
+                    if (!(o_tlast > -INFINITY) && grazing_dropped(ro, q0, q1, s2, s3, alpha_min, &comp)) { ++st_graze; if (comp) ++st_graze_comp; }
                 }
                 const unsigned acc = __ballot_sync(FULL, ok);
                 // the items of one owner are contiguous in the list: bits [lo, hi) of this round
@@ -572,11 +578,12 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     if (STATS) {
         atomicAdd(p.stats + 0, st_nodes); atomicAdd(p.stats + 1, st_leaf);
         atomicAdd(p.stats + 2, st_hits); atomicAdd(p.stats + 3, st_pass);
+        atomicAdd(p.stats + 4, st_graze); atomicAdd(p.stats + 5, st_graze_comp);
     }
 }
 
 template <typename Kern>
-static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_rays, cudaStream_t s) {
+static int launch_fwd(irgs_tracer *h, int slot, Kern kern, const KParams &p, int64_t n_rays, cudaStream_t s) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     int grid = h->sm_count * per_sm;
@@ -592,19 +599,19 @@ static int launch_fwd(irgs_tracer *h, Kern kern, const KParams &p, int64_t n_ray
             cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
     }
-    // candidate scratch: one 32-entry row (512 B) per resident thread and stream slot; only rows in use are live in L2
+    // candidate scratch: one 32-entry row (512 B) per resident thread of this stream slot; only rows in use are live in L2
     const int64_t threads = (int64_t)grid * TB;
-    if (threads > h->cand_threads) {
-        IRGS_CHECK(cudaDeviceSynchronize());
-        if (h->cand) cudaFree(h->cand);
-        h->cand = nullptr;
-        IRGS_CHECK(cudaMalloc(&h->cand, sizeof(uint4) * KB * (size_t)threads * 2));
-        h->cand_threads = threads;
+    if (threads > h->cand_threads[slot]) {
+        IRGS_CHECK(cudaStreamSynchronize(s));   // earlier launches of this slot (all on this stream) are done with the old block
+        if (h->cand[slot]) cudaFree(h->cand[slot]);
+        h->cand[slot] = nullptr;
+        IRGS_CHECK(cudaMalloc(&h->cand[slot], sizeof(uint4) * KB * (size_t)threads));
+        h->cand_threads[slot] = threads;
     }
     const int64_t need = (n_rays + TB - 1) / TB;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
     IRGS_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
-    kern<<<grid, TB, 0, s>>>(p, h->cand + (size_t)h->slot * KB * (size_t)h->cand_threads);
+    kern<<<grid, TB, 0, s>>>(p, h->cand[slot]);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;
@@ -622,13 +629,17 @@ int64_t stride_multiplier(int64_t n_rays) {
 }
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+    const int slot = slot_for(h, s);
+    if (slot < 0) return 1;
     KParams p;
-    p.a = a; p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + h->slot; p.stats = h->stats;
+    p.a = a; p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
-    if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), s));
-    if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31)) {
+    if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 8 * sizeof(unsigned long long), s));
+    // (generated rays -- a.gen_pos -- have no ray arrays to take sort keys from and arrive grouped per shading point anyway)
+    if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31) && a.gen_pos == nullptr &&
+        a.rays_o != nullptr && a.rays_d != nullptr) {
         int *order = nullptr;
-        if (launch_ray_order(h, a.rays_o, a.rays_d, a.n_rays, &order, s)) return 1;
+        if (launch_ray_order(h, slot, a.rays_o, a.rays_d, a.n_rays, &order, s)) return 1;
         p.a.ray_order = order;
     }
     // Small launches are latency bound: the call ends with its slowest warp, and the heavy rays (grazing samples that run
@@ -647,10 +658,10 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     IRGS_CHECK(cudaMemsetAsync(a.alpha, 0, sizeof(float) * R, s));
     if (a.S > 0) IRGS_CHECK(cudaMemsetAsync(a.feature, 0, sizeof(float) * (size_t)a.S * R, s));
     if (a.hit_count) IRGS_CHECK(cudaMemsetAsync(a.hit_count, 0, sizeof(int32_t) * R, s));
-    if (feat) return stats ? launch_fwd(h, trace_forward_kernel<true, true>, p, a.n_rays, s)
-                           : launch_fwd(h, trace_forward_kernel<true, false>, p, a.n_rays, s);
-    return stats ? launch_fwd(h, trace_forward_kernel<false, true>, p, a.n_rays, s)
-                 : launch_fwd(h, trace_forward_kernel<false, false>, p, a.n_rays, s);
+    if (feat) return stats ? launch_fwd(h, slot, trace_forward_kernel<true, true>, p, a.n_rays, s)
+                           : launch_fwd(h, slot, trace_forward_kernel<true, false>, p, a.n_rays, s);
+    return stats ? launch_fwd(h, slot, trace_forward_kernel<false, true>, p, a.n_rays, s)
+                 : launch_fwd(h, slot, trace_forward_kernel<false, false>, p, a.n_rays, s);
 }
 
 }  // namespace irgs

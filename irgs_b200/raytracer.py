@@ -299,7 +299,7 @@ class GaussianTracer:
     def run_chunks(self, n_items, per_chunk, body, streams=None):
         """Chunk loop of the reference's renderer (gaussian_renderer/__init__.py:319-322) with consecutive chunks
         alternating between two CUDA streams: `body(begin, end)` is called for every chunk inside the stream context of
-        its turn, with the tracer switched to that stream's slot (own work counter + candidate scratch), so that the
+        its turn (the native tracer keeps one work counter + candidate scratch per stream), so that the
         drain of one chunk's persistent kernels overlaps the next chunk (+5 % on the C3 step).  `body` may call
         trace / trace_incident and run their backward.  Returns after everything has joined the current stream again.
         Pass the same `streams` list on every call to reuse them."""
@@ -316,17 +316,19 @@ class GaussianTracer:
         try:
             for i, b in enumerate(range(0, n_items, per_chunk)):
                 k = i % len(streams)
-                self.set_option("slot", k)
                 with torch.cuda.stream(streams[k]):
                     body(b, min(b + per_chunk, n_items))
         finally:
-            self.set_option("slot", 0)
             for st in streams:
                 cur.wait_stream(st)
 
     def set_option(self, name, value):
         """Tuning knobs of the native tracer (never change results), e.g. set_option("sort_rays_min", 0)."""
         _lib.check(self.impl.lib.irgs_set_option(self.impl.h, name.encode(), int(value)))
+
+    def get_info(self, name):
+        """Introspection of the native tracer: "tree_depth", "ploc_iterations", "n_slots", "n_surfels"."""
+        return int(self.impl.lib.irgs_get_info(self.impl.h, name.encode()))
 
     def set_stats(self, enable):
         _lib.check(self.impl.lib.irgs_set_stats(self.impl.h, int(enable)))

@@ -23,6 +23,9 @@ CASES = {
     "c1_primary": dict(n=4000, scale_mult=2.5, n_features=0, rays="primary", hw=64, deg=3, back_culling=False),
     "secondary_feat": dict(n=4000, scale_mult=3.0, n_features=4, rays="secondary", pix=24, S=96, deg=3, back_culling=False),
     "deg1_cull": dict(n=4000, scale_mult=2.5, n_features=2, rays="secondary", pix=16, S=64, deg=1, back_culling=True),
+    # the hot-path population: 100k surfels at the hit density of the 300k scene (x sqrt(3) in size), secondary rays that
+    # run through >= 16 proxy crossings, i.e. several reference chunks
+    "dense_100k": dict(n=100000, scale_mult=1.7320508, n_features=0, rays="secondary", pix=12, S=128, deg=3, back_culling=False),
 }
 
 
@@ -62,7 +65,23 @@ def proxy_crossings(inp, o, d, alpha_min):
     r2 = 2 * np.log(np.maximum(op / alpha_min, 1e-30)) * 1.2584 ** 2 * 1.0001
     out = np.zeros(o.shape[0], np.int64)
     oo, dd = o.double().numpy(), d.double().numpy()
+    if mu.shape[0] > 20000:
+        # large scenes: only surfels whose bounding sphere (proxy circumradius) comes within reach of the ray can be crossed
+        rad = np.sqrt(r2 / np.minimum((ru ** 2).sum(-1), (rv ** 2).sum(-1)))
     for i in range(o.shape[0]):
+        if mu.shape[0] > 20000:
+            rel = mu - oo[i]
+            tc = rel @ dd[i]
+            near = ((rel - tc[:, None] * dd[i]) ** 2).sum(-1) <= (rad * 1.01) ** 2
+            sub = np.nonzero(near)[0]
+            rel = oo[i] - mu[sub]
+            og, dg = (n[sub] * rel).sum(-1), n[sub] @ dd[i]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t = -og / dg
+            pos = rel + t[:, None] * dd[i]
+            q = (ru[sub] * pos).sum(-1) ** 2 + (rv[sub] * pos).sum(-1) ** 2
+            out[i] = np.count_nonzero((t > 0) & (t < 100) & (q <= r2[sub]) & (op[sub] > alpha_min))
+            continue
         rel = oo[i] - mu
         og, dg = (n * rel).sum(-1), n @ dd[i]
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -85,13 +104,15 @@ def strict_mask(inp, o, d, cfg):
     return (proxy_crossings(inp, o, d, synth.ALPHA_MIN) < 16) & (m[:, 0] > 2e-4) & (m[:, 1] > 2e-4) & (m[:, 2] > 2e-5)
 
 
-def main(outdir):
+def main(outdir, only=None):
     from surfel_tracer import GaussianTracer  # reference
     import surfel_tracer
     assert "baseline/_ref" in surfel_tracer.__file__, surfel_tracer.__file__
     from irgs_b200 import synth
     os.makedirs(outdir, exist_ok=True)
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
         sc, inp, o, d, gout = make_case(cfg)
         dev = "cuda"
         tracer = GaussianTracer(transmittance_min=synth.T_MIN)
@@ -136,4 +157,4 @@ def main(outdir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"), only=sys.argv[2:] or None)

@@ -8,8 +8,11 @@ What is compared strictly and what is waived (restated in D
   * rays with a near tie between consecutive hits (|dt| < 2e-5), or an alpha / transmittance within 2e-4 relative
     of its threshold are compared loosely (the reference orders by proxy-triangle depth and uses ex2.approx);
   * everything else: composited outputs within 1e-4 absolute (BASELINE.json north_star).
-Gradients (sums over all rays, including the loosely compared ones) must reach cosine >= 0.999 overall and, when
-restricted... are reported per tensor.
+"Loosely" is a number, not a waiver: on the non-strict rays (15 ... 45 % of a case) at most LOOSE_FRACTION of the rays may
+differ by more than 1e-4, none by more than LOOSE_MAX, and the median difference must stay below 1e-5 (measured with the
+oracle: 1 ... 7 % of the non-strict rays differ by more than 1e-4, worst 0.16 -- the reference's double-composited 16th
+surfel).  Gradients are asserted twice: restricted to the strict rays (cosine >= 0.9999 or 1e-3 relative, the north-star
+bar), and over ALL rays (`grad_*`, the loosely compared ones included) with cosine >= LOOSE_COS.
 """
 import json
 
@@ -43,6 +46,9 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
 
 
+LOOSE_FRACTION, LOOSE_MAX, LOOSE_COS = 0.10, 0.2, 0.99
+
+
 def check_against_golden(path, runner, out_tol=1e-4):
     """runner(inp, o, d, gout, meta) -> (fwd dict of arrays, grads dict) for the given incoming gradients."""
     z, meta = load(path)
@@ -67,6 +73,12 @@ def check_against_golden(path, runner, out_tol=1e-4):
         diff = diff.reshape(diff.shape[0], -1).max(1)
         report["worst"][k] = float(diff[strict].max())
         assert report["worst"][k] <= out_tol, (k, report["worst"][k], int(np.argmax(np.where(strict, diff, 0))))
+        loose = diff[~strict]
+        if loose.size:
+            report.setdefault("loose", {})[k] = dict(max=float(loose.max()), frac=float((loose > out_tol).mean()),
+                                                     median=float(np.median(loose)))
+            assert loose.max() <= LOOSE_MAX and (loose > out_tol).mean() <= LOOSE_FRACTION and np.median(loose) <= 1e-5, \
+                (k, report["loose"][k])
     for k, g in grads.items():
         ref = z["gstrict_" + k].reshape(g.shape)
         if ref.size == 0 or not np.any(ref):
@@ -76,4 +88,13 @@ def check_against_golden(path, runner, out_tol=1e-4):
         report["cos"][k], report["rel"][k] = cos, rel
         # BASELINE.json: gradients within 1e-3 relative or cosine similarity >= 0.9999
         assert cos >= 0.9999 or rel <= 1e-3, (k, cos, rel)
+    # all rays, the loosely compared ones included
+    _, grads_all = runner(inp, o, d, gout, meta)
+    report["cos_all"] = {}
+    for k, g in grads_all.items():
+        ref = z["grad_" + k].reshape(g.shape)
+        if ref.size == 0 or not np.any(ref):
+            continue
+        report["cos_all"][k] = _cos(g, ref)
+        assert report["cos_all"][k] >= LOOSE_COS, (k, report["cos_all"][k])
     return report

@@ -781,3 +781,125 @@ def test_start_order_of_small_launches_does_not_change_results(small_scene):
     for other in res[1:]:
         for k in res[0]:
             assert torch.equal(res[0][k], other[k]), k
+
+
+# ---------------------------------------------------------------------------------------------- round-2 additions
+def _secondary_sample(inp_cpu, S, n_pix, spp, seed):
+    """Secondary rays of the C3 kind: shading points on the surface seen by the primary camera, Fibonacci hemispheres."""
+    o, d = synth.primary_rays(400, 400)
+    full = oracle.trace_forward(S, o, d, use_bvh=True, hit_cap=4)
+    pts, nrm = synth.shading_points_from_primary(o, d, torch.from_numpy(full["depth"]), torch.from_numpy(full["alpha"]),
+                                                 torch.from_numpy(full["normal"]))
+    pix = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(seed))[:n_pix]
+    so, sd = synth.secondary_rays(pts[pix], nrm[pix], spp, seed=seed)
+    return so.reshape(-1, 3).contiguous(), sd.reshape(-1, 3).contiguous()
+
+
+@pytest.mark.parametrize("n_surfels", [300000, 1000000])
+def test_backward_matches_oracle_at_full_scene_size_on_a_ray_sample(n_surfels):
+    """C3 / C5 scene sizes: forward AND backward of the CUDA path against the oracle (canonical LBVH) on 8k secondary rays --
+    outputs <= 1e-4, all nine gradients cosine >= 0.9999 and <= 2e-3 relative."""
+    sc = synth.make_scene(n_surfels)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    S = _oracle_scene(inp)
+    o, d = _secondary_sample(inp, S, 32, 256, seed=4)
+    ref = oracle.trace_forward(S, o, d, use_bvh=True, hit_cap=4)
+    assert ref["hit_count"].mean() > 2 and ref["hit_count"].max() > 16
+    safe = torch.from_numpy(_safe(ref))
+    assert float(safe.float().mean()) > 0.97
+    gout = {k: v * (safe[:, None] if v.dim() == 2 else safe) for k, v in _gout(o.shape[0], 0).items()}
+    rb = oracle.trace_backward(S, o, d, ref, {k: v.numpy() for k, v in gout.items()}, use_bvh=True)
+    tr = _tracer(_gpu(inp))
+    fwd, grads = _cuda_fwd_bwd(tr, inp, o, d, gout, use_features=False)
+    for k in ("color", "normal", "depth", "alpha"):
+        assert np.abs(fwd[k] - ref[k])[safe.numpy()].max() <= 1e-4, k
+    names = dict(rays_o="rays_o", rays_d="rays_d", means3D="means", opacity="opacity", ru="ru", rv="rv", normals="normals",
+                 shs="shs")
+    for k, rk in names.items():
+        a, b = grads[k].reshape(rb[rk].shape), rb[rk]
+        rel = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+        assert _cos(a, b) >= 0.9999 and rel <= 2e-3, (k, _cos(a, b), rel)
+
+
+@pytest.mark.parametrize("hit_cap", [96, 0, 8])
+def test_backward_after_forwards_on_two_streams(small_scene, hit_cap):
+    """Forwards inside run_chunks (two streams), ONE loss.backward() afterwards: autograd replays every chunk's backward on
+    the stream of its forward, so two backward launches run concurrently.  Each uses the work counter of ITS stream (slots are
+    looked up from the stream of the call): gradients equal those of a single call, for saved lists, pure re-trace and overflow
+    re-trace alike."""
+    sc, inp = small_scene
+    o, d = _rays(inp, "secondary")
+    o, d = o.to(DEV), d.to(DEV)
+    R = o.shape[0]
+    gout = {k: v.to(DEV) for k, v in _gout(R, inp["features"].shape[1]).items()}
+    names = ("color", "normal", "feature", "depth", "alpha")
+    res = []
+    for chunked in (False, True):
+        tr = _tracer(_gpu(inp), hit_cap=hit_cap)
+        leaf = {k: inp[k].to(DEV).clone().requires_grad_(True) for k in KEYS}
+        ro = o.clone().requires_grad_(True)
+        losses = []
+
+        def body(b, e):
+            outs = tr.trace(ro[b:e], d[b:e], *[leaf[k] for k in KEYS], synth.ALPHA_MIN)
+            losses.append(sum((t * gout[n][b:e]).sum() for n, t in zip(names, outs)))
+        if chunked:
+            tr.run_chunks(R, 301, body)
+            assert tr.get_info("n_slots") >= 2
+        else:
+            body(0, R)
+        torch.stack(losses).sum().backward()
+        torch.cuda.synchronize()
+        res.append(dict(rays_o=ro.grad, **{k: leaf[k].grad for k in KEYS}))
+    for k in res[0]:
+        a, b = res[0][k], res[1][k]
+        assert torch.isfinite(b).all(), k
+        assert (a - b).abs().max() <= 2e-4 * (a.abs().max() + 1e-30), k
+
+
+def test_coherence_sort_option_with_generated_rays(small_scene):
+    """sort_rays_min is a tuning knob that never changes results -- also on the incident path, whose rays exist only inside
+    the kernels (the sort is skipped there instead of reading ray arrays that do not exist)."""
+    sc, inp = small_scene
+    g = _gpu(inp)
+    tr = _tracer(g)
+    P, NS = 96, 32
+    pos = (g["means3D"][:P] + 0.01 * g["normals"][:P]).contiguous()
+    nrm = g["normals"][:P].contiguous()
+    args = (g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], g["features"], g["shs"], synth.ALPHA_MIN)
+    with torch.no_grad():
+        a = tr.trace_incident(pos, nrm, NS, *args)
+        tr.set_option("sort_rays_min", 1)
+        b = tr.trace_incident(pos, nrm, NS, *args)
+        o, d = _rays(inp, "secondary")
+        c = tr.trace(o.to(DEV), d.to(DEV), *args)     # materialised rays: sorted order, same results
+        tr.set_option("sort_rays_min", 0)
+        c0 = tr.trace(o.to(DEV), d.to(DEV), *args)
+    torch.cuda.synchronize()
+    for x, y in list(zip(a, b)) + list(zip(c, c0)):
+        assert torch.equal(x, y)
+    assert bool(a[4].any())
+
+
+def test_ploc_build_with_many_invisible_surfels():
+    """A third of 60k surfels below alpha_min (empty bounds, all at the end of the Morton order): the clustering pairs them up
+    among themselves -- no chain, no fallback to the Karras tree, a normal number of iterations -- and results match the
+    brute-force oracle."""
+    sc = synth.make_scene(60000, scale_mult=2.0)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    inp["opacity"][::3] = 0.5 * synth.ALPHA_MIN
+    g = _gpu(inp)
+    tr = _tracer(g, hit_cap=96)
+    depth, iters = tr.get_info("tree_depth"), tr.get_info("ploc_iterations")
+    assert 0 < depth <= 60, depth          # PLOC tree kept (0 would be the Karras fallback)
+    assert iters <= 120, iters             # was ~ one iteration per invisible surfel
+    o, d = _rays(inp, "secondary")
+    ref = oracle.trace_forward(_oracle_scene(inp), o, d, hit_cap=96)
+    out = tr.trace_with_hits(o.to(DEV), d.to(DEV), g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], None, g["shs"],
+                             synth.ALPHA_MIN)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    safe = _safe(ref) & (ref["hit_count"] <= 96)
+    assert np.array_equal(out["hit_count"][safe], ref["hit_count"][safe]) and ref["hit_count"].sum() > 0
+    for k in ("color", "normal", "depth", "alpha"):
+        assert np.abs(out[k] - ref[k])[safe].max() <= 1e-4, k
+    assert not np.isin(out["hits"][out["hits"] >= 0] % 3, [0]).any()    # no invisible surfel is ever composited

@@ -336,8 +336,9 @@ def measure_c5(args, device, rank, world, steps, sync_all):
     pts, nrm = pts[pix].contiguous(), nrm[pix].contiguous()
     n_pts = pts.shape[0]
     n_local = n_pts * args.spp
-    chunk = min(1 << 24, max(1 << 20, 1 << (max(1, (n_local + 3) // 4) - 1).bit_length()), n_local)
-    pchunk = max(1, chunk // args.spp)
+    n_calls = max(4, -(-n_local // (1 << 24)))
+    pchunk = max(1, -(-n_pts // n_calls))
+    chunk = pchunk * args.spp
     gout = make_gout(pchunk * args.spp, device)
     gout = [g.view(pchunk, args.spp, *g.shape[1:]) if g.numel() else g for g in gout]
     means = inp["means3D"].clone()
@@ -417,7 +418,9 @@ def run_ours(args):
     n_total = args.img * args.img * args.spp
     # rays per trace call: large calls amortise the drain of the persistent kernels; at least ~4 calls per rank so that the
     # two streams have something to overlap
-    chunk = min(args.chunk, max(1 << 20, 1 << (max(1, (n_local + 3) // 4) - 1).bit_length()), n_local)
+    # EQUAL calls (a short last call would pay a whole drain for a fraction of the rays), whole pixel bundles per call
+    n_calls = max(4, -(-n_local // args.chunk))
+    chunk = min(n_local, -(-(n_local // args.spp) // n_calls) * args.spp)
     gout = make_gout(chunk, device)
     leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
     tracer.accumulate_grads = True
@@ -596,29 +599,35 @@ def run_ours(args):
                   "envmap": "256x512 lat-long, exp activation", "grad_checksum": float(sg["shs"].abs().sum().item()),
                   "env_grad_checksum": float(genv.abs().sum().item())}
 
-    # end to end through the C ABI on HOST buffers: rays pinned on the host, copied in per chunk inside the timed region;
-    # the step's result (fused per-surfel gradients after the all-reduce) is read back to the host
-    e2e = None
+    # end to end through the C ABI on HOST buffers.  The step's inputs are what the renderer holds per shaded pixel -- position,
+    # normal, azimuth (28 B per pixel, pinned host memory) -- copied in inside the timed region; the 256 rays of a pixel are
+    # generated in the kernels (irgs_trace_fwd_bwd_incident_host).  The step's result is read back to the host: dL/dposition and
+    # dL/dnormal of every pixel on every rank, and the fused per-surfel gradients after the all-reduce on rank 0.
+    e2e, e2e_rays, e2e_fwd = None, None, None
     if not args.no_e2e:
-        oh, dh = rays_o.cpu().pin_memory(), rays_d.cpu().pin_memory()
+        from irgs_b200.incident import IncidentDesc
+        pts, nrm, azim = build_workload.points
+        n_pts = pts.shape[0]
+        ph, nh, ah = pts.cpu().pin_memory(), nrm.cpu().pin_memory(), azim.cpu().pin_memory()
+        gp_h, gn_h = torch.empty(n_pts, 3).pin_memory(), torch.empty(n_pts, 3).pin_memory()
         fused = torch.zeros(args.surfels, 64, device=device)
-        fused_h = torch.empty(args.surfels, 64).pin_memory()
-        # chunk of the host-buffer path: large enough to amortise the drain of the persistent kernels, small enough that the
-        # un-overlapped first copy stays a small part of the step (at least ~8 chunks per rank)
-        e2e_chunk = min(1 << 23, max(1 << 21, 1 << max(0, (n_local // 8).bit_length() - 1)), n_local)
-        if args.e2e_chunk > 0:
-            e2e_chunk = min(args.e2e_chunk, n_local)
-        ge = make_gout(e2e_chunk, device)
+        fused_h = torch.empty(args.surfels, 64).pin_memory() if rank == 0 else None
+        pchunk_e = max(1, chunk // args.spp)
+        ge = make_gout(pchunk_e * args.spp, device)
+        desc = IncidentDesc(ph.data_ptr(), nh.data_ptr(), ah.data_ptr(), n_pts, args.spp, synth.LIGHT_T_MIN)
+        import ctypes
+        cur = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
         def e2e_step():
             fused.zero_()
-            _lib.check(lib.irgs_trace_fwd_bwd_host(
-                tracer.impl.h, n_local, 0, 16, 3, _ptr(oh), _ptr(dh), _ptr(inp["means3D"]), _ptr(inp["opacity"]),
-                _ptr(inp["ru"]), _ptr(inp["rv"]), _ptr(inp["normals"]), None, _ptr(inp["shs"]), _ptr(ge[0]), _ptr(ge[1]),
-                None, _ptr(ge[3]), _ptr(ge[4]), e2e_chunk, None, None, None, _ptr(fused), None, synth.ALPHA_MIN, synth.T_MIN,
-                0, e2e_chunk))
+            _lib.check(lib.irgs_trace_fwd_bwd_incident_host(
+                tracer.impl.h, ctypes.byref(desc), 0, 16, 3, _ptr(inp["means3D"]), _ptr(inp["opacity"]), _ptr(inp["ru"]),
+                _ptr(inp["rv"]), _ptr(inp["normals"]), None, _ptr(inp["shs"]), _ptr(ge[0]), _ptr(ge[1]), None, _ptr(ge[3]),
+                _ptr(ge[4]), pchunk_e * args.spp, None, _ptr(gp_h), _ptr(gn_h), _ptr(fused), None, synth.ALPHA_MIN, synth.T_MIN,
+                0, pchunk_e, cur))
             parallel.allreduce_sum_(fused)
-            fused_h.copy_(fused, non_blocking=True)
+            if rank == 0:
+                fused_h.copy_(fused, non_blocking=True)
             torch.cuda.synchronize()
 
         for _ in range(min(args.warmup, 2)):
@@ -629,10 +638,51 @@ def run_ours(args):
             e2e_step()
         sync_all()
         e2e_s = parallel.max_over_ranks(time.perf_counter() - w0, device) / args.steps
-        e2e = {"value": n_total / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(n_local * 24),
-               "d2h_bytes_per_step": int(fused_h.numel() * 4), "ms_per_step": e2e_s * 1e3,
-               "api": "irgs_trace_fwd_bwd_host (C ABI, pinned host rays) + all-reduce + gradient read-back"}
-        del oh, dh
+        e2e = {"value": n_total / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(n_pts * 28),
+               "d2h_bytes_per_step": int(n_pts * 24 + (fused.numel() * 4 if rank == 0 else 0)), "ms_per_step": e2e_s * 1e3,
+               "api": "irgs_trace_fwd_bwd_incident_host (C ABI; pinned host position / normal / azimuth per pixel, rays generated "
+                      "in-kernel) + all-reduce + read-back of the per-pixel gradients (every rank) and the per-surfel gradients (rank 0)"}
+        del ph, nh, ah
+
+        # the same step with the RAYS themselves in pinned host memory (24 B per ray in, irgs_trace_fwd_bwd_host), and the
+        # forward-only host path with colour-less outputs read back (alpha, 4 B per ray out, irgs_trace_forward_host)
+        oh, dh = rays_o.cpu().pin_memory(), rays_d.cpu().pin_memory()
+        alpha_h = torch.empty(n_local).pin_memory()
+        gr = make_gout(chunk, device)
+
+        def rays_step():
+            fused.zero_()
+            _lib.check(lib.irgs_trace_fwd_bwd_host(
+                tracer.impl.h, n_local, 0, 16, 3, _ptr(oh), _ptr(dh), _ptr(inp["means3D"]), _ptr(inp["opacity"]),
+                _ptr(inp["ru"]), _ptr(inp["rv"]), _ptr(inp["normals"]), None, _ptr(inp["shs"]), _ptr(gr[0]), _ptr(gr[1]),
+                None, _ptr(gr[3]), _ptr(gr[4]), chunk, None, None, None, _ptr(fused), None, synth.ALPHA_MIN, synth.T_MIN,
+                0, chunk))
+            parallel.allreduce_sum_(fused)
+            if rank == 0:
+                fused_h.copy_(fused, non_blocking=True)
+            torch.cuda.synchronize()
+
+        def fwd_step():
+            _lib.check(lib.irgs_trace_forward_host(
+                tracer.impl.h, n_local, 0, 16, 3, _ptr(oh), _ptr(dh), _ptr(inp["means3D"]), _ptr(inp["opacity"]),
+                _ptr(inp["ru"]), _ptr(inp["rv"]), _ptr(inp["normals"]), None, _ptr(inp["shs"]), None, None, None, None,
+                _ptr(alpha_h), synth.ALPHA_MIN, synth.T_MIN, 0, chunk))
+
+        res = []
+        for fn in (rays_step, fwd_step):
+            fn()
+            sync_all()
+            w0 = time.perf_counter()
+            for _ in range(args.steps):
+                fn()
+            sync_all()
+            res.append(parallel.max_over_ranks(time.perf_counter() - w0, device) / args.steps)
+        e2e_rays = {"value": n_total / res[0], "unit": "rays/s", "ms_per_step": res[0] * 1e3, "h2d_bytes_per_step": int(n_local * 24),
+                    "d2h_bytes_per_step": int(fused.numel() * 4 if rank == 0 else 0),
+                    "api": "irgs_trace_fwd_bwd_host (materialised rays in pinned host memory)"}
+        e2e_fwd = {"value": n_total / res[1], "unit": "rays/s", "ms_per_step": res[1] * 1e3, "h2d_bytes_per_step": int(n_local * 24),
+                   "d2h_bytes_per_step": int(n_local * 4), "api": "irgs_trace_forward_host, forward only, alpha read back"}
+        del oh, dh, alpha_h
 
     # the other BASELINE.json configurations at their stated sizes, and the call sizes IRGS itself issues
     other, small = None, None
@@ -669,7 +719,7 @@ def run_ours(args):
                    "parallelism": f"ray-sharded dp{world} (32-pixel blocks round-robin), surfels+BVH replicated, one all-reduce of N x 64 floats",
                    "l2": "inputs (3.9 GB of rays per step) exceed L2; no flush needed",
                    "shading_points": "all 640k bundles start on the surface (missed pixels re-assigned to hit pixels)"},
-        "e2e": e2e, "fused_generation": fused_gen, "rendering_equation": shaded, "other_configs": other, "small_calls": small,
+        "e2e": e2e, "e2e_host_rays": e2e_rays, "e2e_forward_host_rays": e2e_fwd, "fused_generation": fused_gen, "rendering_equation": shaded, "other_configs": other, "small_calls": small,
         "gpu_launches": launches, "clocks": clk, "rank_compute_ms": rank_ms,
         "roofline": {"bound": "hbm", "kernel": "trace_forward_kernel", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

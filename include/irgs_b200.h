@@ -108,7 +108,8 @@ int irgs_unpack_grads(const float *grad_fused, int64_t n_surfels, int K, float *
 
 /* End-to-end entry points on HOST buffers (pinned or pageable): rays are copied host->device in chunks on internal
  * streams, traced, and results copied device->host, overlapping copies with the kernels.  Surfel arrays and the
- * incoming-gradient arrays stay DEVICE pointers (they live on the GPU in IRGS); gout_* are periodic device arrays
+ * incoming-gradient arrays stay DEVICE pointers (they live on the GPU in IRGS); the internal streams start after everything the
+ * caller has already submitted to the legacy default stream (an event, no device-wide synchronisation).  gout_* are periodic device arrays
  * with gout_period rows (ray r of the whole batch uses row r % gout_period).  Host outputs may be NULL to skip the copy back.
  * irgs_trace_fwd_bwd_host runs forward + backward per chunk and accumulates into grad_fused (device). */
 int irgs_trace_forward_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int deg, const float *rays_o_host,
@@ -168,6 +169,21 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
                                  float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_position,
                                  float *grad_normal_pt, float *grad_fused, float *grad_features, float alpha_min, float T_min,
                                  int back_culling, void *stream);
+
+/* irgs_trace_fwd_bwd_host for generated incident rays with the per-point inputs on the HOST: gen_host->position / normals /
+ * azimuth are host pointers (pinned or pageable); 28 bytes per shading point go host -> device instead of 24 bytes per ray.
+ * Forward + backward run chunk by chunk (chunk_points shading points each, 0 = 2^22 rays' worth) on two internal streams that
+ * start after everything already submitted to `stream`; `stream` continues after them.  Host outputs (any may be NULL):
+ * out_alpha_host [P*S], grad_position_host [P,3], grad_normal_host [P,3]; per-surfel gradients accumulate into the DEVICE
+ * buffers grad_fused / grad_features; gout_* as in irgs_trace_fwd_bwd_host.  Returns when the host outputs are complete. */
+int irgs_trace_fwd_bwd_incident_host(irgs_tracer_t *h, const irgs_incident_t *gen_host, int S, int K, int deg,
+                                     const float *means3D, const float *opacity, const float *ru, const float *rv,
+                                     const float *normals, const float *features, const float *shs, const float *gout_color,
+                                     const float *gout_normal, const float *gout_feature, const float *gout_depth,
+                                     const float *gout_alpha, int64_t gout_period, float *out_alpha_host,
+                                     float *grad_position_host, float *grad_normal_host, float *grad_fused,
+                                     float *grad_features, float alpha_min, float transmittance_min, int back_culling,
+                                     int64_t chunk_points, void *stream);
 
 /* ---- Shading epilogue around the incident-ray trace (SURVEY.md 8f rank 1 + rank 3) ----------------------------------
  * Replaces the element-wise torch code of /root/reference/gaussian_renderer/__init__.py:334-415 (rendering_equation, the

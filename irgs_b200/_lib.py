@@ -39,6 +39,8 @@ PROTOTYPES = {
     "irgs_trace_forward_host": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 9 + [_vp] * 5 + [_f32, _f32, _i32, _i64]),
     "irgs_trace_fwd_bwd_host": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 9 + [_vp] * 5 + [_i64] + [_vp] * 3
                                 + [_vp] * 2 + [_f32, _f32, _i32, _i64]),
+    "irgs_trace_fwd_bwd_incident_host": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_i64] + [_vp] * 3
+                                         + [_vp] * 2 + [_f32, _f32, _i32, _i64, _vp]),
     "irgs_stride_multiplier": (_i64, [_i64]),
     "irgs_launch_count": (_i64, []),
     "irgs_reset_launch_count": (None, []),

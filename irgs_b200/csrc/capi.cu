@@ -1,4 +1,5 @@
 // C ABI of libirgs_b200.so (see include/irgs_b200.h for the contract and the reference interface each entry replaces).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdint>
@@ -113,6 +114,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
         for (int k = 0; k < 2; ++k) { cudaFree(h->rsort_keys[i][k]); cudaFree(h->rsort_vals[i][k]); }
         cudaFree(h->rsort_hist[i]);
         cudaFree(h->cand[i]);
+        cudaFree(h->inc_pts[i]);
     }
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
@@ -125,6 +127,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
         if (h->ring_free[i]) cudaEventDestroy(h->ring_free[i]);
     }
     if (h->hcopy) cudaStreamDestroy(h->hcopy);
+    cudaFree(h->pt_buf);
     delete h;
     return 0;
 }
@@ -227,7 +230,7 @@ static int validate_incident(const irgs_incident_t *gen) {
 static void set_generator(TraceArgs &a, const irgs_incident_t *gen) {
     if (!gen) return;
     a.gen_pos = gen->position; a.gen_nrm = gen->normals; a.gen_azim = gen->azimuth;
-    a.gen_S = gen->sample_num; a.gen_tmin = gen->t_min;
+    a.gen_S = gen->sample_num; a.gen_tmin = gen->t_min; a.gen_P = gen->n_points;
 }
 
 static int trace_forward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int64_t n_rays, int S, int K, int deg,
@@ -246,7 +249,7 @@ static int trace_forward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int6
     set_generator(a, gen);
     a.color = out_color; a.normal = out_normal; a.feature = out_feature; a.depth = out_depth; a.alpha = out_alpha;
     a.hit_count = out_hit_count; a.hits = out_hits; a.hit_cap = hit_cap;
-    if (launch_pack_records(h, a, s)) return 1;
+    if (launch_pack_records(h, a, s) || launch_incident_prepare(h, a, s)) return 1;
     return launch_trace_forward(h, a, s);
 }
 
@@ -307,7 +310,7 @@ static int trace_backward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int
     a.gC = gout_color; a.gN = gout_normal; a.gF = gout_feature; a.gD = gout_depth; a.gO = gout_alpha;
     a.g_rays_o = grad_rays_o; a.g_rays_d = grad_rays_d; a.grad_fused = grad_fused; a.grad_features = grad_features;
     // the records must be consistent with the arrays handed to this call
-    if (launch_pack_records(h, a, s)) return 1;
+    if (launch_pack_records(h, a, s) || launch_incident_prepare(h, a, s)) return 1;
     return launch_trace_backward(h, a, s);
 }
 
@@ -375,7 +378,7 @@ static int host_prepare(irgs_tracer *h, int64_t floats_per_stream, int64_t ray_f
         }
         h->stage_floats = floats_per_stream;
     }
-    if (ray_floats > h->ring_floats) {
+    if (ray_floats > 0 && ray_floats > h->ring_floats) {
         for (int i = 0; i < irgs_tracer::RING; ++i) {
             if (h->ring[i]) cudaFree(h->ring[i]);
             h->ring[i] = nullptr;
@@ -383,6 +386,16 @@ static int host_prepare(irgs_tracer *h, int64_t floats_per_stream, int64_t ray_f
         }
         h->ring_floats = ray_floats;
     }
+    return 0;
+}
+
+// The internal streams of the host-buffer entry points start after everything the caller has submitted to `caller` so far
+// (nullptr: the legacy default stream) -- an event, not a device-wide synchronisation.
+static int host_order_after(irgs_tracer *h, cudaStream_t caller) {
+    IRGS_CHECK(cudaEventRecord(h->hev[0], caller));
+    IRGS_CHECK(cudaStreamWaitEvent(h->hs[0], h->hev[0], 0));
+    IRGS_CHECK(cudaStreamWaitEvent(h->hs[1], h->hev[0], 0));
+    IRGS_CHECK(cudaStreamWaitEvent(h->hcopy, h->hev[0], 0));
     return 0;
 }
 
@@ -410,7 +423,7 @@ static int trace_host_impl(irgs_tracer *h, bool with_backward, int64_t n_rays, i
     //                                     g_o[3c] g_d[3c]
     const int64_t per_ray = 3 + 3 + S + 1 + 1 + (with_backward ? 1 + hit_cap + 6 : 0);
     if (host_prepare(h, per_ray * chunk, 6 * chunk)) return 1;
-    IRGS_CHECK(cudaDeviceSynchronize());
+    if (host_order_after(h, nullptr)) return 1;   // ordered after the caller's earlier work on the legacy default stream, no host sync
     TraceArgs base = make_args(0, (int)h->n, S, K, deg, nullptr, nullptr, means, opacity, ru, rv, normals, features, shs,
                                alpha_min, T_min, back_culling);
     if (launch_pack_records(h, base, h->hs[0])) return 1;
@@ -487,6 +500,88 @@ int irgs_trace_fwd_bwd_host(irgs_tracer_t *h, int64_t n_rays, int S, int K, int 
                            features, shs, gout_color, gout_normal, gout_feature, gout_depth, gout_alpha, gout_period,
                            nullptr, nullptr, nullptr, nullptr, out_alpha_host, grad_rays_o_host, grad_rays_d_host,
                            grad_fused, grad_features, alpha_min, T_min, back_culling, chunk_rays);
+}
+
+// Forward + backward on generated incident rays with the per-point inputs in HOST memory: 28 bytes per shading point travel
+// host -> device (instead of 24 bytes per ray), 24 bytes per point of gradients travel back.  Chunks of `chunk_points` points
+// alternate between the two internal compute streams.
+int irgs_trace_fwd_bwd_incident_host(irgs_tracer_t *h, const irgs_incident_t *gen_host, int S, int K, int deg,
+                                     const float *means, const float *opacity, const float *ru, const float *rv,
+                                     const float *normals, const float *features, const float *shs, const float *gC,
+                                     const float *gN, const float *gF, const float *gD, const float *gO, int64_t gout_period,
+                                     float *out_alpha_host, float *grad_position_host, float *grad_normal_host,
+                                     float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
+                                     int64_t chunk_points, void *stream) {
+    if (validate_incident(gen_host)) return 1;
+    const int64_t P = gen_host->n_points;
+    const int NS = gen_host->sample_num;
+    const int hit_cap = 96;
+    if (validate_trace(h, P * NS, S, K, deg, hit_cap)) return 1;
+    if (P == 0) return 0;
+    if (!grad_fused) return fail("grad_fused must not be null");
+    if (S > 0 && !grad_features) return fail("grad_features must not be null when S > 0");
+    if (gout_period <= 0) return fail("gout_period must be positive");
+    if (chunk_points <= 0) chunk_points = std::max<int64_t>(1, ((int64_t)1 << 22) / NS);
+    if (chunk_points > P) chunk_points = P;
+    DeviceGuard guard(h->device);
+    const int64_t chunk = chunk_points * NS;   // rays per chunk
+    const int64_t per_ray = 3 + 3 + S + 1 + 1 + 1 + hit_cap + 6;
+    if (host_prepare(h, per_ray * chunk, 0)) return 1;
+    // per-point inputs (position, normals, azimuth) and outputs (dL/dposition, dL/dnormal) of the whole batch: 13 floats a point
+    if (13 * P > h->pt_floats) {
+        if (h->pt_buf) { IRGS_CHECK(cudaDeviceSynchronize()); cudaFree(h->pt_buf); }
+        h->pt_buf = nullptr;
+        IRGS_CHECK(cudaMalloc(&h->pt_buf, sizeof(float) * (size_t)(13 * P)));
+        h->pt_floats = 13 * P;
+    }
+    float *d_pos = h->pt_buf, *d_nrm = d_pos + 3 * P, *d_az = d_nrm + 3 * P, *d_gpos = d_az + P, *d_gnrm = d_gpos + 3 * P;
+    if (host_order_after(h, (cudaStream_t)stream)) return 1;
+    IRGS_CHECK(cudaMemcpyAsync(d_pos, gen_host->position, sizeof(float) * 3 * P, cudaMemcpyHostToDevice, h->hcopy));
+    IRGS_CHECK(cudaMemcpyAsync(d_nrm, gen_host->normals, sizeof(float) * 3 * P, cudaMemcpyHostToDevice, h->hcopy));
+    if (gen_host->azimuth) IRGS_CHECK(cudaMemcpyAsync(d_az, gen_host->azimuth, sizeof(float) * P, cudaMemcpyHostToDevice, h->hcopy));
+    IRGS_CHECK(cudaEventRecord(h->ring_full[0], h->hcopy));
+    TraceArgs base = make_args(0, (int)h->n, S, K, deg, nullptr, nullptr, means, opacity, ru, rv, normals, features, shs,
+                               alpha_min, T_min, back_culling);
+    if (launch_pack_records(h, base, h->hs[0])) return 1;
+    IRGS_CHECK(cudaEventRecord(h->hev[1], h->hs[0]));
+    IRGS_CHECK(cudaStreamWaitEvent(h->hs[1], h->hev[1], 0));
+    for (int i = 0; i < 2; ++i) IRGS_CHECK(cudaStreamWaitEvent(h->hs[i], h->ring_full[0], 0));
+    int it = 0;
+    for (int64_t p0 = 0; p0 < P; p0 += chunk_points, ++it) {
+        cudaStream_t s = h->hs[it & 1];
+        const int64_t np = std::min(chunk_points, P - p0), c = np * NS;
+        float *st = h->stage[it & 1];
+        float *d_col = st, *d_nrm_o = d_col + 3 * chunk, *d_feat = d_nrm_o + 3 * chunk, *d_dep = d_feat + S * chunk,
+              *d_alp = d_dep + chunk;
+        int32_t *d_cnt = reinterpret_cast<int32_t *>(d_alp + chunk);
+        int32_t *d_hits = d_cnt + chunk;
+        float *d_go = reinterpret_cast<float *>(d_hits + (int64_t)hit_cap * chunk), *d_gd = d_go + 3 * chunk;
+        TraceArgs a = base;
+        a.n_rays = c;
+        a.gen_pos = d_pos + 3 * p0; a.gen_nrm = d_nrm + 3 * p0; a.gen_azim = gen_host->azimuth ? d_az + p0 : nullptr;
+        a.gen_S = NS; a.gen_tmin = gen_host->t_min; a.gen_P = np;
+        a.color = d_col; a.normal = d_nrm_o; a.feature = d_feat; a.depth = d_dep; a.alpha = d_alp;
+        a.hit_count = d_cnt; a.hits = d_hits; a.hit_cap = hit_cap;
+        if (launch_incident_prepare(h, a, s) || launch_trace_forward(h, a, s)) return 1;
+        a.gC = gC; a.gN = gN; a.gF = gF; a.gD = gD; a.gO = gO; a.gout_period = gout_period; a.gout_offset = p0 * NS;
+        a.g_rays_o = d_go; a.g_rays_d = d_gd; a.grad_fused = grad_fused; a.grad_features = grad_features;
+        if (launch_trace_backward(h, a, s)) return 1;
+        if (launch_incident_backward(a.gen_pos, a.gen_nrm, a.gen_azim, np, NS, a.gen_tmin, d_go, d_gd, d_gpos + 3 * p0,
+                                     d_gnrm + 3 * p0, s))
+            return 1;
+        if (out_alpha_host) IRGS_CHECK(cudaMemcpyAsync(out_alpha_host + p0 * NS, d_alp, sizeof(float) * c, cudaMemcpyDeviceToHost, s));
+        if (grad_position_host) IRGS_CHECK(cudaMemcpyAsync(grad_position_host + 3 * p0, d_gpos + 3 * p0, sizeof(float) * 3 * np, cudaMemcpyDeviceToHost, s));
+        if (grad_normal_host) IRGS_CHECK(cudaMemcpyAsync(grad_normal_host + 3 * p0, d_gnrm + 3 * p0, sizeof(float) * 3 * np, cudaMemcpyDeviceToHost, s));
+    }
+    // the caller's stream continues after both compute streams (grad_fused is complete for whatever it launches next); the
+    // host waits because the host outputs must be readable on return
+    for (int i = 0; i < 2; ++i) {
+        IRGS_CHECK(cudaEventRecord(h->ring_free[i], h->hs[i]));
+        IRGS_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, h->ring_free[i], 0));
+    }
+    IRGS_CHECK(cudaStreamSynchronize(h->hs[0]));
+    IRGS_CHECK(cudaStreamSynchronize(h->hs[1]));
+    return 0;
 }
 
 int64_t irgs_stride_multiplier(int64_t n_rays) { return stride_multiplier(n_rays); }

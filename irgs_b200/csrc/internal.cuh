@@ -101,6 +101,8 @@ struct irgs_tracer {
     int *rsort_vals[MAX_SLOTS][2] = {};
     int *rsort_hist[MAX_SLOTS] = {};
     int64_t rsort_cap[MAX_SLOTS] = {};
+    void *inc_pts[MAX_SLOTS] = {};          // per-point records of generated incident rays (IncPoint[inc_cap]), per stream slot
+    int64_t inc_cap[MAX_SLOTS] = {};
     int bwd_carveout_pct = -1;              // backward replay kernel: carve-out hint in percent (-1: the driver's default)
     int carveout_pct = -1;                  // forward kernel: shared-memory carve-out hint in percent (-1: what the resident blocks need)
     int64_t stride_rays_max = 1 << 19;      // forward calls with at most this many rays start them in a stride order (0: never)
@@ -121,6 +123,8 @@ struct irgs_tracer {
     float *ring[RING] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ring_full[RING] = {nullptr, nullptr, nullptr, nullptr}, ring_free[RING] = {nullptr, nullptr, nullptr, nullptr};
     int64_t ring_floats = 0;
+    float *pt_buf = nullptr;                // incident host path: per-point inputs and gradients of a batch, 13 floats a point
+    int64_t pt_floats = 0;
 };
 
 namespace irgs {
@@ -160,6 +164,9 @@ struct TraceArgs {
     const float *gen_pos, *gen_nrm, *gen_azim;   // [P,3], [P,3], [P] or nullptr (no random rotation)
     int gen_S;
     float gen_tmin;
+    int64_t gen_P;
+    const struct IncPoint *gen_pts;   // [P] per-point records (rotation, azimuth sin / cos), filled by launch_incident_prepare
+    const struct IncTab *gen_tab;     // [gen_S] per-sample table (incident_table)
     const int *ray_order;  // forward: optional processing order (coherence sort); results are still written per ray id
     int64_t ray_mul;       // forward: 0, or an odd multiplier coprime to n_rays (n_rays <= 2^19): the i-th ray started is (i * ray_mul) % n_rays
                            // (small launches: spreads the heavy rays of one pixel bundle over the warps, launch_trace_forward)
@@ -174,6 +181,10 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int64_t stride_multiplier(int64_t n_rays);
 int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s);
 int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, cudaStream_t s);
+// incident-ray generation: the per-sample table of a sample count (cached per device, filled once) and the per-point records
+// of a call (scratch owned by the handle, one block per stream slot); launch_incident_prepare fills a.gen_pts / a.gen_tab
+const struct IncTab *incident_table(int sample_num, cudaStream_t s);
+int launch_incident_prepare(irgs_tracer *h, TraceArgs &a, cudaStream_t s);
 int launch_incident_backward(const float *position, const float *normals, const float *azimuth, int64_t n_points,
                              int sample_num, float t_min, const float *g_rays_o, const float *g_rays_d, float *grad_position,
                              float *grad_normal_pt, cudaStream_t s);

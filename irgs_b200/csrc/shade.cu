@@ -26,6 +26,7 @@ struct ShadeArgs {
     float saturate;                                   // 1 - transmittance_min, < 0: no normalisation
     EnvMap env;
     // light_sample_num > 0 (irgs_shade_sampling_t): explicit directions instead of generated ones, mixed-sampling weights
+    const IncTab *tab;                                // [S] per-sample table of the generated directions (incident_table)
     const float *dirs;                                // [P*S,3] or null (generated from normals / azimuth)
     MisParams mis;
     float inv_count;                                  // 1 / (samples the means run over)
@@ -33,14 +34,14 @@ struct ShadeArgs {
 
 // direction of sample s of point pt: generated (q is filled, q.rotated tells whether it depends on the normal) or read
 template <bool MIX>
-__device__ __forceinline__ void sample_dir(const ShadeArgs &a, const float n[3], int64_t ray, int s, float az, IncidentSample &q,
+__device__ __forceinline__ void sample_dir(const ShadeArgs &a, const IncPoint &ip, int64_t ray, int s, IncidentSample &q,
                                            float d[3]) {
     if (MIX && a.dirs != nullptr) {
         d[0] = __ldg(a.dirs + 3 * ray); d[1] = __ldg(a.dirs + 3 * ray + 1); d[2] = __ldg(a.dirs + 3 * ray + 2);
         q.rotated = false; q.len = 1.f; q.zx = q.zy = q.zz = q.vx = q.vy = q.vz = 0.f;
         return;
     }
-    q = incident_sample(n[0], n[1], n[2], s, a.S, a.azimuth != nullptr, az);
+    q = incident_sample(ip, load_inc_tab(a.tab + s), a.azimuth != nullptr);
     d[0] = __fdiv_rn(q.vx, q.len); d[1] = __fdiv_rn(q.vy, q.len); d[2] = __fdiv_rn(q.vz, q.len);
 }
 
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
     float n[3];
     ShadePoint p;
     load_point(a, pt, n, p);
-    const float az = a.azimuth ? __ldg(a.azimuth + pt) : 0.f;
+    const IncPoint ip = incident_point(n[0], n[1], n[2], a.azimuth != nullptr, a.azimuth ? __ldg(a.azimuth + pt) : 0.f);
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(128) shade_forward_kernel(ShadeArgs a, float *
         const int64_t ray = pt * a.S + s;
         IncidentSample q;
         float d[3];
-        sample_dir<MIX>(a, n, ray, s, az, q, d);
+        sample_dir<MIX>(a, ip, ray, s, q, d);
         const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
                                 __ldg(a.trace_color + 3 * ray + 2)};
         ShadeSample o;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_ker
     float n[3];
     ShadePoint p;
     load_point(a, pt, n, p);
-    const float az = a.azimuth ? __ldg(a.azimuth + pt) : 0.f;
+    const IncPoint ip = incident_point(n[0], n[1], n[2], a.azimuth != nullptr, a.azimuth ? __ldg(a.azimuth + pt) : 0.f);
     const float inv = a.inv_count;
     float go = (lane < 16) ? __ldg(g_out + 16 * pt + lane) * inv : 0.f;     // the mean over S folded into the gradients
     float gD[3], gS[3], gE[3], gLi[3], gLocal[3];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(128, IRGS_SHADE_BWD_BLOCKS) shade_backward_ker
         const int64_t ray = pt * a.S + s;
         IncidentSample q;
         float d[3];
-        sample_dir<MIX>(a, n, ray, s, az, q, d);
+        sample_dir<MIX>(a, ip, ray, s, q, d);
         const float c_raw[3] = {__ldg(a.trace_color + 3 * ray), __ldg(a.trace_color + 3 * ray + 1),
                                 __ldg(a.trace_color + 3 * ray + 2)};
         float g_c[3], g_a, gd[3];
@@ -241,6 +242,7 @@ static int make_args(const irgs_incident_t *gen, const irgs_envmap_t *env, const
     a.trace_color = trace_color; a.trace_alpha = trace_alpha; a.saturate = saturate_alpha;
     a.dirs = nullptr; a.mis.pdf = nullptr; a.mis.p_diffuse = 1.f; a.mis.p_light = 0.f;
     a.inv_count = 1.0f / (float)gen->sample_num;
+    a.tab = nullptr;
     if (smp != nullptr) {
         if (smp->total_samples < gen->sample_num) return fail_msg("shade: total_samples must be >= the samples of this call");
         if (smp->pdf != nullptr && !(smp->p_diffuse >= 0.f && smp->p_light >= 0.f))
@@ -264,6 +266,7 @@ int irgs_shade_forward(const irgs_incident_t *gen, const irgs_envmap_t *env, con
     if (make_args(gen, env, sampling, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
     if (a.n_points == 0) return 0;
     if (!out) return fail_msg("shade: null output array");
+    if (a.dirs == nullptr && !(a.tab = incident_table(a.S, (cudaStream_t)stream))) return 1;
     const unsigned grid = (unsigned)((a.n_points * 32 + 127) / 128);
     if (sampling != nullptr) shade_forward_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, out);
     else shade_forward_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a, out);
@@ -280,6 +283,7 @@ int irgs_shade_backward(const irgs_incident_t *gen, const irgs_envmap_t *env, co
     if (make_args(gen, env, sampling, base_color, roughness, viewdirs, trace_color, trace_alpha, saturate_alpha, a)) return 1;
     if (a.n_points == 0) return 0;
     if (!g_out || !g_trace_color || !g_trace_alpha || !g_point) return fail_msg("shade backward: null array");
+    if (a.dirs == nullptr && !(a.tab = incident_table(a.S, (cudaStream_t)stream))) return 1;
     const unsigned grid = (unsigned)((a.n_points * 32 + 127) / 128);
     if (sampling != nullptr)
         shade_backward_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, g_out, g_trace_color, g_trace_alpha, g_point, grad_env);

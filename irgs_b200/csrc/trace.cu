@@ -16,6 +16,10 @@
 //   * intersection_test_kernel, incident_rays_kernel, incident_backward_kernel, unpack_grads_kernel
 // The depth of a hit is computed with the same explicit sequence of IEEE operations as oracle/surfel_oracle.c, so the hit
 // order is bit-identical to the oracle's.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "trace_common.cuh"
 
 namespace irgs {
@@ -691,18 +695,38 @@ __global__ void __launch_bounds__(TB) intersection_test_kernel(const KParams p, 
 }
 
 // ------------------------------------------------------------------------------------------------ incident rays
-// The generated rays written out (for callers that also shade with the directions, and for tests).
+// Per-sample table and per-point records of the generated incident rays (trace_common.cuh).
+__global__ void incident_table_kernel(int S, IncTab *__restrict__ tab) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) tab[s] = incident_tab_entry(s, S);
+}
+__global__ void incident_point_kernel(const float *__restrict__ normals, const float *__restrict__ azimuth, int64_t n_points,
+                                      IncPoint *__restrict__ pts) {
+    const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= n_points) return;
+    pts[pt] = incident_point(__ldg(normals + 3 * pt), __ldg(normals + 3 * pt + 1), __ldg(normals + 3 * pt + 2), azimuth != nullptr,
+                             azimuth ? __ldg(azimuth + pt) : 0.f);
+}
+
+// The generated rays written out (for callers that also shade with the directions, and for tests): one ray per thread, the
+// point record computed on the spot (no handle, hence no scratch, on this entry).
 __global__ void incident_rays_kernel(const float *__restrict__ position, const float *__restrict__ normals,
                                      const float *__restrict__ azimuth, int64_t n_rays, int S, float t_min,
-                                     float *__restrict__ rays_o, float *__restrict__ rays_d) {
+                                     const IncTab *__restrict__ tab, float *__restrict__ rays_o, float *__restrict__ rays_d) {
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= n_rays) return;
-    TraceArgs a;
-    a.gen_pos = position; a.gen_nrm = normals; a.gen_azim = azimuth; a.gen_S = S; a.gen_tmin = t_min;
-    RayCtx r;
-    load_ray(a, ray, r);
-    if (rays_o) { rays_o[3 * ray] = r.ox; rays_o[3 * ray + 1] = r.oy; rays_o[3 * ray + 2] = r.oz; }
-    if (rays_d) { rays_d[3 * ray] = r.dx; rays_d[3 * ray + 1] = r.dy; rays_d[3 * ray + 2] = r.dz; }
+    const int64_t pt = ray / S;
+    const int s = (int)(ray - pt * S);
+    const IncPoint ip = incident_point(__ldg(normals + 3 * pt), __ldg(normals + 3 * pt + 1), __ldg(normals + 3 * pt + 2),
+                                       azimuth != nullptr, azimuth ? __ldg(azimuth + pt) : 0.f);
+    const IncidentSample q = incident_sample(ip, load_inc_tab(tab + s), azimuth != nullptr);
+    const float dx = __fdiv_rn(q.vx, q.len), dy = __fdiv_rn(q.vy, q.len), dz = __fdiv_rn(q.vz, q.len);
+    if (rays_o) {
+        rays_o[3 * ray] = __fadd_rn(__ldg(position + 3 * pt), __fmul_rn(dx, t_min));
+        rays_o[3 * ray + 1] = __fadd_rn(__ldg(position + 3 * pt + 1), __fmul_rn(dy, t_min));
+        rays_o[3 * ray + 2] = __fadd_rn(__ldg(position + 3 * pt + 2), __fmul_rn(dz, t_min));
+    }
+    if (rays_d) { rays_d[3 * ray] = dx; rays_d[3 * ray + 1] = dy; rays_d[3 * ray + 2] = dz; }
 }
 
 // Chain rule from the per-ray gradients of the tracer back to the shading point: one warp per point.
@@ -713,7 +737,8 @@ __global__ void incident_rays_kernel(const float *__restrict__ position, const f
 __global__ void __launch_bounds__(128) incident_backward_kernel(const float *__restrict__ position,
                                                                 const float *__restrict__ normals,
                                                                 const float *__restrict__ azimuth, int64_t n_points, int S,
-                                                                float t_min, const float *__restrict__ g_rays_o,
+                                                                float t_min, const IncTab *__restrict__ tab,
+                                                                const float *__restrict__ g_rays_o,
                                                                 const float *__restrict__ g_rays_d,
                                                                 float *__restrict__ grad_position,
                                                                 float *__restrict__ grad_normal) {
@@ -721,13 +746,13 @@ __global__ void __launch_bounds__(128) incident_backward_kernel(const float *__r
     const int lane = threadIdx.x & 31;
     if (pt >= n_points) return;
     const float nx = __ldg(normals + 3 * pt), ny = __ldg(normals + 3 * pt + 1), nz = __ldg(normals + 3 * pt + 2);
-    const float az = azimuth ? __ldg(azimuth + pt) : 0.f;
+    const IncPoint ip = incident_point(nx, ny, nz, azimuth != nullptr, azimuth ? __ldg(azimuth + pt) : 0.f);
     float acc[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) acc[j] = 0.f;
     for (int s = lane; s < S; s += 32) {
         const int64_t ray = pt * S + s;
-        const IncidentSample q = incident_sample(nx, ny, nz, s, S, azimuth != nullptr, az);
+        const IncidentSample q = incident_sample(ip, load_inc_tab(tab + s), azimuth != nullptr);
         const float dx = __fdiv_rn(q.vx, q.len), dy = __fdiv_rn(q.vy, q.len), dz = __fdiv_rn(q.vz, q.len);
         const float gox = g_rays_o[3 * ray], goy = g_rays_o[3 * ray + 1], goz = g_rays_o[3 * ray + 2];
         const float gdx = g_rays_d[3 * ray] + t_min * gox, gdy = g_rays_d[3 * ray + 1] + t_min * goy,
@@ -878,12 +903,57 @@ int launch_intersection_test(irgs_tracer *h, const TraceArgs &a, uint8_t *out, c
     return 0;
 }
 
+// The per-sample table of a sample count: built once per (device, S) and kept for the life of the process (32 bytes per
+// sample).  The first request fills it on `s` and waits, so that every later user on any stream finds it complete.
+const IncTab *incident_table(int sample_num, cudaStream_t s) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, IncTab *> cache;
+    int dev = 0;
+    if (!check(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, sample_num});
+    if (it != cache.end()) return it->second;
+    IncTab *tab = nullptr;
+    if (!check(cudaMalloc(&tab, sizeof(IncTab) * (size_t)sample_num), "cudaMalloc")) return nullptr;
+    incident_table_kernel<<<(sample_num + 127) / 128, 128, 0, s>>>(sample_num, tab);
+    count_launch();
+    if (!check(cudaGetLastError(), "incident_table_kernel") || !check(cudaStreamSynchronize(s), "cudaStreamSynchronize")) {
+        cudaFree(tab);
+        return nullptr;
+    }
+    cache[{dev, sample_num}] = tab;
+    return tab;
+}
+
+int launch_incident_prepare(irgs_tracer *h, TraceArgs &a, cudaStream_t s) {
+    if (a.gen_pos == nullptr) return 0;
+    const int slot = slot_for(h, s);
+    if (slot < 0) return 1;
+    a.gen_tab = incident_table(a.gen_S, s);
+    if (!a.gen_tab) return 1;
+    if (a.gen_P > h->inc_cap[slot]) {
+        IRGS_CHECK(cudaStreamSynchronize(s));   // earlier users of this slot's block (all on this stream) are done
+        if (h->inc_pts[slot]) cudaFree(h->inc_pts[slot]);
+        h->inc_pts[slot] = nullptr;
+        IRGS_CHECK(cudaMalloc(&h->inc_pts[slot], sizeof(IncPoint) * (size_t)a.gen_P));
+        h->inc_cap[slot] = a.gen_P;
+    }
+    IncPoint *pts = static_cast<IncPoint *>(h->inc_pts[slot]);
+    incident_point_kernel<<<(unsigned)((a.gen_P + 255) / 256), 256, 0, s>>>(a.gen_nrm, a.gen_azim, a.gen_P, pts);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    a.gen_pts = pts;
+    return 0;
+}
+
 int launch_incident_rays(const float *position, const float *normals, const float *azimuth, int64_t n_points, int sample_num,
                          float t_min, float *rays_o, float *rays_d, cudaStream_t s) {
     const int64_t n_rays = n_points * sample_num;
     if (n_rays <= 0) return 0;
+    const IncTab *tab = incident_table(sample_num, s);
+    if (!tab) return 1;
     incident_rays_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, s>>>(position, normals, azimuth, n_rays, sample_num, t_min,
-                                                                          rays_o, rays_d);
+                                                                          tab, rays_o, rays_d);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;
@@ -893,8 +963,10 @@ int launch_incident_backward(const float *position, const float *normals, const 
                              int sample_num, float t_min, const float *g_rays_o, const float *g_rays_d, float *grad_position,
                              float *grad_normal, cudaStream_t s) {
     if (n_points <= 0) return 0;
+    const IncTab *tab = incident_table(sample_num, s);
+    if (!tab) return 1;
     incident_backward_kernel<<<(unsigned)((n_points * 32 + 127) / 128), 128, 0, s>>>(
-        position, normals, azimuth, n_points, sample_num, t_min, g_rays_o, g_rays_d, grad_position, grad_normal);
+        position, normals, azimuth, n_points, sample_num, t_min, tab, g_rays_o, g_rays_d, grad_position, grad_normal);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;

@@ -249,35 +249,82 @@ __device__ __forceinline__ bool leaf_test(const RayCtx &r, const SurfelRec *__re
 __device__ __forceinline__ bool key_less(float ta, int ga, float tb, int gb) { return ta < tb || (ta == tb && ga < gb); }
 
 // ------------------------------------------------------------------------------------------------ incident rays
-// Sample `s` of the Fibonacci hemisphere around `normal`, the reference's fibonacci_sphere_sampling +
-// rotation_between_z (utils/graphics_utils.py:19-47,133-165) with its order of float32 operations (restated and pinned
-// in oracle/incident.py); azim is the per-point `rand * 2 pi` of the training mode (0 and has_azim = false otherwise).
-// zs = the sample around +z, v = R zs (not yet normalised), len = max(|v|, 1e-12); rotated = false on the -identity branch.
-struct IncidentSample { float zx, zy, zz, vx, vy, vz, len; bool rotated; };
-__device__ __forceinline__ IncidentSample incident_sample(float nx, float ny, float nz, int s, int S, bool has_azim, float azim) {
-    IncidentSample o;
+// Sample `s` of the Fibonacci hemisphere around `normal`: the reference's fibonacci_sphere_sampling + rotation_between_z
+// (utils/graphics_utils.py:19-47,133-165), restated and pinned in oracle/incident.py; azim is the per-point `rand * 2 pi`
+// of the training mode (has_azim = false otherwise).  The work is split by what it depends on, so that nothing is
+// recomputed per ray that 256 rays share:
+//   * IncTab   per SAMPLE index (a table of S entries, filled once per S by incident_table_kernel): the float32 angle
+//              delta = 2.39996.. * s exactly as the reference rounds it, sin / cos of THAT float32 value in double
+//              precision, z and the radius sqrt(1 - z^2);
+//   * IncPoint per shading POINT (incident_point: one 64-byte record, precomputed for the tracing kernels, computed once per
+//              warp by the kernels that own a point per warp): the rotation taking +z to the normal -- the reference's
+//              four IEEE divisions -- and sin / cos of the azimuth in double precision;
+//   * per RAY  (incident_sample) only the angle addition, the 3x3 product and the normalisation remain.
+// The reference evaluates sin / cos of theta = fl(azim + delta), a float32 SUM whose rounding error (up to 6e-5 rad at
+// theta ~ 1200) is far above the 4e-7 the directions are compared at; the two-sum below recovers that error exactly and the
+// angle addition is corrected to first order (second order: 2e-9), in double precision (half rate on B200), which is
+// MORE accurate than sincosf of the rounded sum was: directions agree with the unmodified reference to <= 4e-7.
+struct __align__(32) IncTab { double sd, cd; float delta, z, rad, pad; };
+struct __align__(32) IncPoint { float r[9]; float az; int rotated; int pad; double saz, caz; };
+static_assert(sizeof(IncTab) == 32 && sizeof(IncPoint) == 64, "incident-ray records are 32 / 64 bytes");
+
+__device__ __forceinline__ IncTab incident_tab_entry(int s, int S) {
+    IncTab t;
     const float idx = (float)s;
-    const float z = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, idx), (float)(2 * S - 1))), 0.17364817766693033f);
-    const float rad = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(z, z)));
-    float theta = __fmul_rn(2.399963229728653f, idx);
-    if (has_azim) theta = __fadd_rn(azim, theta);
-    float sn, cs;
-    sincosf(theta, &sn, &cs);
-    o.zy = __fmul_rn(cs, rad);
-    o.zx = __fmul_rn(sn, rad);
-    o.zz = z;
-    o.rotated = __fadd_rn(nz, 1.0f) > 0.0f;
-    if (o.rotated) {
+    t.z = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, idx), (float)(2 * S - 1))), 0.17364817766693033f);
+    t.rad = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(t.z, t.z)));
+    t.delta = __fmul_rn(2.399963229728653f, idx);
+    sincos((double)t.delta, &t.sd, &t.cd);
+    t.pad = 0.f;
+    return t;
+}
+
+__device__ __forceinline__ IncPoint incident_point(float nx, float ny, float nz, bool has_azim, float azim) {
+    IncPoint p;
+    p.rotated = __fadd_rn(nz, 1.0f) > 0.0f ? 1 : 0;
+    p.pad = 0;
+    p.az = has_azim ? azim : 0.f;
+    p.saz = 0.0; p.caz = 1.0;
+    if (has_azim) sincos((double)azim, &p.saz, &p.caz);
+    if (p.rotated) {
         const float v1 = -ny, v2 = nx;
         const float c = fmaxf(__fadd_rn(nz, 1.0f), 1e-7f);
         const float v11 = __fmul_rn(v1, v1), v22 = __fmul_rn(v2, v2), v12 = __fmul_rn(v1, v2);
-        const float r00 = __fadd_rn(1.0f, __fdiv_rn(-v22, c)), r01 = __fdiv_rn(v12, c), r02 = v2;
-        const float r10 = r01, r11 = __fadd_rn(1.0f, __fdiv_rn(-v11, c)), r12 = -v1;
-        const float r20 = -v2, r21 = v1, r22 = __fadd_rn(1.0f, __fdiv_rn(__fsub_rn(-v22, v11), c));
-        o.vx = __fmaf_rn(r02, o.zz, __fmaf_rn(r01, o.zy, __fmul_rn(r00, o.zx)));
-        o.vy = __fmaf_rn(r12, o.zz, __fmaf_rn(r11, o.zy, __fmul_rn(r10, o.zx)));
-        o.vz = __fmaf_rn(r22, o.zz, __fmaf_rn(r21, o.zy, __fmul_rn(r20, o.zx)));
+        p.r[0] = __fadd_rn(1.0f, __fdiv_rn(-v22, c)); p.r[1] = __fdiv_rn(v12, c); p.r[2] = v2;
+        p.r[3] = p.r[1]; p.r[4] = __fadd_rn(1.0f, __fdiv_rn(-v11, c)); p.r[5] = -v1;
+        p.r[6] = -v2; p.r[7] = v1; p.r[8] = __fadd_rn(1.0f, __fdiv_rn(__fsub_rn(-v22, v11), c));
     } else {   // graphics_utils.py:163-164: -identity
+        p.r[0] = -1.f; p.r[1] = 0.f; p.r[2] = 0.f; p.r[3] = 0.f; p.r[4] = -1.f; p.r[5] = 0.f; p.r[6] = 0.f; p.r[7] = 0.f; p.r[8] = -1.f;
+    }
+    return p;
+}
+
+// zs = the sample around +z, v = R zs (not yet normalised), len = max(|v|, 1e-12); rotated = false on the -identity branch.
+struct IncidentSample { float zx, zy, zz, vx, vy, vz, len; bool rotated; };
+__device__ __forceinline__ IncidentSample incident_sample(const IncPoint &p, const IncTab &t, bool has_azim) {
+    IncidentSample o;
+    float sn, cs;
+    if (has_azim) {
+        // theta = fl(az + delta) = az + delta - err (two-sum: exact); sin / cos(az + delta) by angle addition, then - err
+        const float th = __fadd_rn(p.az, t.delta);
+        const float bv = __fsub_rn(th, p.az), av = __fsub_rn(th, bv);
+        const float err = __fadd_rn(__fsub_rn(p.az, av), __fsub_rn(t.delta, bv));   // az + delta = th + err
+        const double s0 = fma(p.saz, t.cd, p.caz * t.sd), c0 = fma(p.caz, t.cd, -(p.saz * t.sd));
+        const double e = (double)err;
+        sn = (float)fma(-e, c0, s0);
+        cs = (float)fma(e, s0, c0);
+    } else {
+        sn = (float)t.sd; cs = (float)t.cd;
+    }
+    o.zy = __fmul_rn(cs, t.rad);
+    o.zx = __fmul_rn(sn, t.rad);
+    o.zz = t.z;
+    o.rotated = p.rotated != 0;
+    if (o.rotated) {
+        o.vx = __fmaf_rn(p.r[2], o.zz, __fmaf_rn(p.r[1], o.zy, __fmul_rn(p.r[0], o.zx)));
+        o.vy = __fmaf_rn(p.r[5], o.zz, __fmaf_rn(p.r[4], o.zy, __fmul_rn(p.r[3], o.zx)));
+        o.vz = __fmaf_rn(p.r[8], o.zz, __fmaf_rn(p.r[7], o.zy, __fmul_rn(p.r[6], o.zx)));
+    } else {
         o.vx = -o.zx; o.vy = -o.zy; o.vz = -o.zz;
     }
     const float len = __fsqrt_rn(__fmaf_rn(o.vz, o.vz, __fmaf_rn(o.vy, o.vy, __fmul_rn(o.vx, o.vx))));
@@ -285,13 +332,33 @@ __device__ __forceinline__ IncidentSample incident_sample(float nx, float ny, fl
     return o;
 }
 
+__device__ __forceinline__ IncPoint load_inc_point(const IncPoint *__restrict__ p) {
+    float4 a, b, c, d;
+    ldg256(p, a, b);
+    ldg256(reinterpret_cast<const char *>(p) + 32, c, d);
+    IncPoint q;
+    q.r[0] = a.x; q.r[1] = a.y; q.r[2] = a.z; q.r[3] = a.w; q.r[4] = b.x; q.r[5] = b.y; q.r[6] = b.z; q.r[7] = b.w;
+    q.r[8] = c.x; q.az = c.y; q.rotated = __float_as_int(c.z); q.pad = 0;
+    q.saz = __hiloint2double(__float_as_int(d.y), __float_as_int(d.x));
+    q.caz = __hiloint2double(__float_as_int(d.w), __float_as_int(d.z));
+    return q;
+}
+__device__ __forceinline__ IncTab load_inc_tab(const IncTab *__restrict__ t) {
+    float4 a, b;
+    ldg256(t, a, b);
+    IncTab q;
+    q.sd = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
+    q.cd = __hiloint2double(__float_as_int(a.w), __float_as_int(a.z));
+    q.delta = b.x; q.z = b.y; q.rad = b.z; q.pad = 0.f;
+    return q;
+}
+
 __device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
     if (a.gen_pos != nullptr) {
         // gaussian_renderer/__init__.py:376: origin = position + dir * light_t_min, generated instead of read
         const int64_t pt = ray / a.gen_S;
         const int s = (int)(ray - pt * a.gen_S);
-        const IncidentSample q = incident_sample(__ldg(a.gen_nrm + 3 * pt), __ldg(a.gen_nrm + 3 * pt + 1), __ldg(a.gen_nrm + 3 * pt + 2),
-                                                 s, a.gen_S, a.gen_azim != nullptr, a.gen_azim ? __ldg(a.gen_azim + pt) : 0.f);
+        const IncidentSample q = incident_sample(load_inc_point(a.gen_pts + pt), load_inc_tab(a.gen_tab + s), a.gen_azim != nullptr);
         r.dx = __fdiv_rn(q.vx, q.len); r.dy = __fdiv_rn(q.vy, q.len); r.dz = __fdiv_rn(q.vz, q.len);
         r.ox = __fadd_rn(__ldg(a.gen_pos + 3 * pt), __fmul_rn(r.dx, a.gen_tmin));
         r.oy = __fadd_rn(__ldg(a.gen_pos + 3 * pt + 1), __fmul_rn(r.dy, a.gen_tmin));

@@ -138,3 +138,45 @@ def test_gradients_reach_position_normals_and_surfels(small_scene, train):
     assert torch.isfinite(z.grad).all() and torch.isfinite(p.grad).all()
     e = tr.trace_incident(p[:0], z[:0], 8, *[g[k] for k in keys], synth.ALPHA_MIN)
     assert e[0].shape == (0, 8, 3)
+
+
+def test_incident_host_entry_matches_the_device_path(small_scene):
+    """irgs_trace_fwd_bwd_incident_host (per-point inputs in pinned host memory, chunks on two internal streams) against
+    trace_incident + autograd on device tensors: identical alpha, per-point and per-surfel gradients up to the order noise of
+    the float reductions."""
+    import ctypes
+    from irgs_b200 import _lib
+    from irgs_b200.incident import IncidentDesc
+    from irgs_b200.raytracer import _ptr
+    sc, inp = small_scene
+    tr, g = _tracer(inp)
+    pos, nrm, azim = _points(inp, n=77, seed=5)
+    S, t_min = 32, 0.05
+    P, N, F = pos.shape[0], g["means3D"].shape[0], g["features"].shape[1]
+    keys = ("means3D", "opacity", "ru", "rv", "normals", "features", "shs")
+    period = 13 * S                                    # periodic incoming gradients, a whole number of points
+    gen = torch.Generator().manual_seed(8)
+    gout = [torch.randn(period, c, generator=gen).to(DEV) for c in (3, 3, F)] + [torch.randn(period, generator=gen).to(DEV) for _ in range(2)]
+    # device path
+    leaf = {k: g[k].clone().requires_grad_(True) for k in keys}
+    p, n = pos.to(DEV).clone().requires_grad_(True), nrm.to(DEV).clone().requires_grad_(True)
+    outs = tr.trace_incident(p, n, S, *[leaf[k] for k in keys], synth.ALPHA_MIN, azimuth=azim.to(DEV), t_min=t_min)
+    rep = (P * S + period - 1) // period
+    full = [t.repeat(*([rep] + [1] * (t.dim() - 1)))[:P * S] for t in gout]
+    sum((o.reshape(P * S, *o.shape[2:]) * w).sum() for o, w in zip(outs, full)).backward()
+    # host path
+    ph, nh, ah = pos.contiguous().pin_memory(), nrm.contiguous().pin_memory(), azim.contiguous().pin_memory()
+    al_h, gp_h, gn_h = torch.empty(P * S).pin_memory(), torch.empty(P, 3).pin_memory(), torch.empty(P, 3).pin_memory()
+    fused, gfeat = torch.zeros(N, 64, device=DEV), torch.zeros(N, F, device=DEV)
+    desc = IncidentDesc(ph.data_ptr(), nh.data_ptr(), ah.data_ptr(), P, S, t_min)
+    lib = _lib.load()
+    _lib.check(lib.irgs_trace_fwd_bwd_incident_host(
+        tr.impl.h, ctypes.byref(desc), F, 16, 3, *[_ptr(g[k]) for k in keys], *[_ptr(t) for t in gout], period, _ptr(al_h),
+        _ptr(gp_h), _ptr(gn_h), _ptr(fused), _ptr(gfeat), synth.ALPHA_MIN, synth.T_MIN, 0, 10,
+        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(al_h.view(P, S), outs[4].detach().cpu())
+    for got, want in ((gp_h, p.grad), (gn_h, n.grad)):
+        assert (got - want.cpu()).abs().max() <= 2e-4 * (want.abs().max().item() + 1e-30)
+    got = tr._unpack(fused, gfeat, tuple(g["opacity"].shape), 16)
+    for k, t in zip(keys, got):
+        assert (t - leaf[k].grad).abs().max() <= 2e-4 * (leaf[k].grad.abs().max() + 1e-30), k

@@ -236,6 +236,26 @@ int irgs_env_lookup_forward(const irgs_envmap_t *env, const float *dirs, int64_t
 int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const float *g_out, int64_t n_dirs, float *g_dirs,
                              float *grad_env, void *stream);
 
+/* ---- Parameter-level entry -----------------------------------------------------------------------
+ * The caller glue of /root/reference/scene/gaussian_model.py:733-756 as kernels: surfel PARAMETERS (means [N,3], activated
+ * scales [N,2], quaternions (w,x,y,z) [N,4], not necessarily normalised) -> the tracer's ru / rv / normals (utils/general_utils.py
+ * :78-99 build_rotation, :135-146 safe_normalize + flip_align_view towards camera_center_host, a HOST float[3] or NULL = no flip),
+ * the gradients of the parameters from the fused [N,64] buffer (chain rule through ru = R[:,0]/s_u, rv = R[:,1]/s_v,
+ * normals = +-R[:,2]/|R[:,2]| and the quaternion normalisation; means / opacity / SH rows are copied out), and the
+ * normalisation of saturated rays (alpha >= threshold = 1 - T_min: accumulations divided by alpha, alpha set to 1) with its
+ * backward (g_* arrive for the normalised outputs and are rewritten in place as gradients of the raw ones). */
+int irgs_surfel_frames(const float *means3D, const float *scales, const float *rotations, const float *camera_center_host,
+                       int64_t n_surfels, float *ru, float *rv, float *normals, void *stream);
+int irgs_unpack_grads_params(const float *grad_fused, int64_t n_surfels, int K, const float *means3D, const float *scales,
+                             const float *rotations, const float *camera_center_host, float *grad_means3D, float *grad_opacity,
+                             float *grad_scales, float *grad_rotations, float *grad_shs, void *stream);
+int irgs_normalize_outputs(int64_t n_rays, int S, float threshold, const float *color, const float *normal, const float *feature,
+                           const float *depth, const float *alpha, float *out_color, float *out_normal, float *out_feature,
+                           float *out_depth, float *out_alpha, void *stream);
+int irgs_normalize_outputs_backward(int64_t n_rays, int S, float threshold, const float *color, const float *normal,
+                                    const float *feature, const float *depth, const float *alpha, float *g_color,
+                                    float *g_normal, float *g_feature, float *g_depth, float *g_alpha, void *stream);
+
 /* Tuning knobs (never change results).  "sort_rays_min": forward calls with at least this many rays process them in
  * a coherence-sorted order (origin cell, direction bin); 0 disables the sort.  "bwd_mode": 0 (default) replays the saved
  * hit lists one hit per lane (segmented warp scans, 256-byte row reductions), 1 one ray per thread.

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["capi.cu", "lbvh.cu", "trace.cu", "trace_fwd.cu", "shade.cu"]
+SOURCES = ["capi.cu", "lbvh.cu", "trace.cu", "trace_fwd.cu", "shade.cu", "surfel_params.cu"]
 HEADERS = ["internal.cuh", "trace_common.cuh", "shade_math.cuh", os.path.join("..", "..", "include", "irgs_b200.h")]
 LIB = os.path.join(CSRC, "libirgs_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -220,11 +220,12 @@ int irgs_intersection_test(irgs_tracer_t *h, int64_t n_rays, const float *rays_o
     return launch_intersection_test(h, a, out, s);
 }
 
-static int validate_incident(const irgs_incident_t *gen) {
+static int validate_incident(const irgs_incident_t *gen, bool one_call = true) {
     if (!gen) return fail("null incident-ray descriptor");
     if (gen->n_points < 0) return fail("n_points < 0");
     if (gen->sample_num < 1) return fail("sample_num must be positive");
     if (gen->n_points > 0 && (!gen->position || !gen->normals)) return fail("position / normals must not be null");
+    if (one_call && gen->n_points * (int64_t)gen->sample_num >= ((int64_t)1 << 31)) return fail("n_points * sample_num must be below 2^31 per call");
     return 0;
 }
 static void set_generator(TraceArgs &a, const irgs_incident_t *gen) {
@@ -512,7 +513,7 @@ int irgs_trace_fwd_bwd_incident_host(irgs_tracer_t *h, const irgs_incident_t *ge
                                      float *out_alpha_host, float *grad_position_host, float *grad_normal_host,
                                      float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
                                      int64_t chunk_points, void *stream) {
-    if (validate_incident(gen_host)) return 1;
+    if (validate_incident(gen_host, false)) return 1;
     const int64_t P = gen_host->n_points;
     const int NS = gen_host->sample_num;
     const int hit_cap = 96;
@@ -523,6 +524,7 @@ int irgs_trace_fwd_bwd_incident_host(irgs_tracer_t *h, const irgs_incident_t *ge
     if (gout_period <= 0) return fail("gout_period must be positive");
     if (chunk_points <= 0) chunk_points = std::max<int64_t>(1, ((int64_t)1 << 22) / NS);
     if (chunk_points > P) chunk_points = P;
+    if (chunk_points * NS >= ((int64_t)1 << 31)) return fail("chunk_points * sample_num must be below 2^31");
     DeviceGuard guard(h->device);
     const int64_t chunk = chunk_points * NS;   // rays per chunk
     const int64_t per_ray = 3 + 3 + S + 1 + 1 + 1 + hit_cap + 6;

@@ -333,19 +333,47 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
     for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) carry_remF[j] = 0.f;
     const int nvec = ((a.deg + 1) * (a.deg + 1) * 3 + 3) >> 2;
 
+    // Software pipeline over the 32-hit rounds: the chain hit id -> inverse order -> record is three dependent L2 accesses; the
+    // id of a hit is fetched two rounds ahead and its leaf position one round ahead, so that a round only waits for one level
+    // (record and SH row, issued together).  locate(): flat index -> (owning lane, index inside that ray's list).
+    auto locate = [&](int idx, int &own, int &kk) {
+        int o = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int v = __shfl_sync(FULL, incl, o + step - 1);
+            if (v <= idx) o += step;
+        }
+        const bool in = idx < total;
+        o = in ? o : lane;
+        const int st = __shfl_sync(FULL, start, o);
+        own = o; kk = in ? idx - st : 0;
+        return in;
+    };
+    auto fetch_id = [&](int idx) {
+        int own, kk;
+        const bool in = locate(idx, own, kk);
+        return in ? __ldg(a.hits + (ray0 + own) * a.hit_cap + kk) : 0;
+    };
+#ifndef IRGS_BWD_PIPELINE
+#define IRGS_BWD_PIPELINE 1   // 0: every round fetches its own ids and positions (comparison builds)
+#endif
+    int g_cur = fetch_id(lane), g_nxt = fetch_id(32 + lane);
+    int pos_cur = lane < total ? __ldg(p.inv_order + g_cur) : 0;
     for (int base = 0; base < total; base += 32) {
         const int idx = base + lane;
         const bool act = idx < total;
-        // owner = number of lanes whose inclusive count is <= idx (binary lifting over shuffles)
-        int owner = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            const int v = __shfl_sync(FULL, incl, owner + step - 1);
-            if (v <= idx) owner += step;
-        }
-        owner = act ? owner : lane;
-        const int o_start = __shfl_sync(FULL, start, owner), n_o = __shfl_sync(FULL, c_eff, owner);
-        const int k = act ? idx - o_start : 0;
+#if IRGS_BWD_PIPELINE
+        const int pos_nxt = idx + 32 < total ? __ldg(p.inv_order + g_nxt) : 0;   // next round's leaf positions
+        const int g_nxt2 = fetch_id(idx + 64);                                     // ids of the round after next
+#else
+        const int pos_nxt = 0, g_nxt2 = 0;
+        g_cur = fetch_id(idx);
+        pos_cur = act ? __ldg(p.inv_order + g_cur) : 0;
+#endif
+        int owner, k_loc;
+        locate(idx, owner, k_loc);
+        const int n_o = __shfl_sync(FULL, c_eff, owner);
+        const int k = k_loc;
         const int64_t ray = ray0 + owner;
         RayCtx ro;
         ro.ox = __shfl_sync(FULL, r.ox, owner); ro.oy = __shfl_sync(FULL, r.oy, owner); ro.oz = __shfl_sync(FULL, r.oz, owner);
@@ -370,11 +398,11 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         float Y[16];
         int g = 0;
         if (act) {
-            g = __ldg(a.hits + ray * a.hit_cap + k);
+            g = g_cur;
             sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
             // the surfel's packed record (re-packed from the saved inputs before this launch): two 32-byte loads
             float4 q0, q1, q2, q3;
-            const SurfelRec *rec = p.recs + __ldg(p.inv_order + g);
+            const SurfelRec *rec = p.recs + pos_cur;
             ldg256(&rec->r0, q0, q1);
             ldg256(&rec->r2, q2, q3);
             const float mx = q0.x, my = q0.y, mz = q0.z;
@@ -557,6 +585,7 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
                 }
             }
         }
+        g_cur = g_nxt; pos_cur = pos_nxt; g_nxt = g_nxt2;
     }
     if (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until it has been read
     if (valid && cnt <= a.hit_cap) {  // rays with longer lists are written by the re-trace kernel

@@ -356,8 +356,9 @@ __device__ __forceinline__ IncTab load_inc_tab(const IncTab *__restrict__ t) {
 __device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
     if (a.gen_pos != nullptr) {
         // gaussian_renderer/__init__.py:376: origin = position + dir * light_t_min, generated instead of read
-        const int64_t pt = ray / a.gen_S;
-        const int s = (int)(ray - pt * a.gen_S);
+        // (a call's rays number < 2^31, checked by the launcher: one 32-bit division instead of a 64-bit one)
+        const int64_t pt = (int64_t)((unsigned)ray / (unsigned)a.gen_S);
+        const int s = (int)((unsigned)ray - (unsigned)pt * (unsigned)a.gen_S);
         const IncidentSample q = incident_sample(load_inc_point(a.gen_pts + pt), load_inc_tab(a.gen_tab + s), a.gen_azim != nullptr);
         r.dx = __fdiv_rn(q.vx, q.len); r.dy = __fdiv_rn(q.vy, q.len); r.dz = __fdiv_rn(q.vz, q.len);
         r.ox = __fadd_rn(__ldg(a.gen_pos + 3 * pt), __fmul_rn(r.dx, a.gen_tmin));

@@ -903,3 +903,61 @@ def test_ploc_build_with_many_invisible_surfels():
     for k in ("color", "normal", "depth", "alpha"):
         assert np.abs(out[k] - ref[k])[safe].max() <= 1e-4, k
     assert not np.isin(out["hits"][out["hits"] >= 0] % 3, [0]).any()    # no invisible surfel is ever composited
+
+
+def test_parameter_level_trace_is_kernels_only_and_matches_the_torch_glue(small_scene):
+    """SurfelScene.trace (frames, trace, normalisation of saturated rays and all of their backward as native kernels inside one
+    autograd node) against the same computation spelled as the reference spells it -- differentiable torch glue around
+    GaussianTracer.trace (surfel_frames + torch.where, scene/gaussian_model.py:733-756): outputs bit-identical up to the
+    1-ulp difference of the frame arithmetic, gradients of means / scales / rotations / opacities / shs / features cosine
+    >= 0.9999.  And the launch list of the native path holds no element-wise torch kernel."""
+    from irgs_b200.surfels import SurfelScene, surfel_frames
+    sc, inp = small_scene
+    o, d = _rays(inp, "secondary")
+    o, d = o[:2048].to(DEV), d[:2048].to(DEV)
+    names = ("color", "normal", "feature", "depth", "alpha")
+    keys = ("means", "scales", "rotations", "opacity", "shs", "features")
+    gout = {k: v.to(DEV) for k, v in _gout(o.shape[0], sc["features"].shape[1]).items()}
+    scene = SurfelScene(transmittance_min=synth.T_MIN, alpha_min=synth.ALPHA_MIN)
+    p0 = {k: sc[k].to(DEV) for k in keys}
+    scene.build(p0["means"], p0["scales"], p0["rotations"], p0["opacity"], synth.CAMERA_CENTER)
+    res = []
+    for native in (True, False):
+        leaf = {k: p0[k].clone().requires_grad_(True) for k in keys}
+        if native:
+            out = scene.trace(o, d, leaf["means"], leaf["scales"], leaf["rotations"], leaf["opacity"], leaf["shs"],
+                              leaf["features"], camera_center=synth.CAMERA_CENTER)
+        else:
+            ru, rv, nrm = surfel_frames(leaf["means"], leaf["scales"], leaf["rotations"], synth.CAMERA_CENTER)
+            c, n, f, dep, a = scene.tracer.trace(o, d, leaf["means"], leaf["opacity"], ru, rv, nrm, leaf["features"], leaf["shs"],
+                                                 synth.ALPHA_MIN)
+            sat = a >= 1 - synth.T_MIN
+            out = dict(color=torch.where(sat[:, None], c / a[:, None], c), normal=torch.where(sat[:, None], n / a[:, None], n),
+                       feature=torch.where(sat[:, None], f / a[:, None], f), depth=torch.where(sat, dep / a, dep),
+                       alpha=torch.where(sat, torch.ones_like(a), a))
+        sum((out[k] * gout[k]).sum() for k in names).backward()
+        res.append(({k: out[k].detach() for k in names}, {k: leaf[k].grad for k in keys}))
+    assert bool((res[0][0]["alpha"] == 1).any())
+    for k in names:
+        assert (res[0][0][k] - res[1][0][k]).abs().max() <= 1e-5, k
+    for k in keys:
+        a, b = res[0][1][k].cpu().numpy(), res[1][1][k].cpu().numpy()
+        assert np.any(b) and _cos(a, b) >= 0.9999, (k, _cos(a, b))
+    # launch list of one native forward + backward
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        leaf = {k: p0[k].clone().requires_grad_(True) for k in keys}
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            out = scene.trace(o, d, leaf["means"], leaf["scales"], leaf["rotations"], leaf["opacity"], leaf["shs"],
+                              leaf["features"], camera_center=synth.CAMERA_CENTER)
+            torch.autograd.backward([out[k] for k in names], [gout[k] for k in names])
+            torch.cuda.synchronize()
+        kernels = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
+    except Exception:
+        kernels = []
+    if kernels:
+        foreign = [k for k in kernels if "irgs::" not in k and "Memset" not in k and "Memcpy" not in k and "fill" not in k.lower()
+                   and "copy" not in k.lower()]
+        assert not foreign, foreign
+        assert any("frames_forward_kernel" in k for k in kernels) and any("unpack_params_kernel" in k for k in kernels)

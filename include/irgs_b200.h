@@ -236,6 +236,23 @@ int irgs_env_lookup_forward(const irgs_envmap_t *env, const float *dirs, int64_t
 int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const float *g_out, int64_t n_dirs, float *g_dirs,
                              float *grad_env, void *stream);
 
+/* ---- Relight branch of rendering_equation (gaussian_renderer/__init__.py:362-381) ---------------------------------------------
+ * The hit point of every secondary ray is shaded under the novel environment: irgs_relight_hit turns the tracer's raw normal
+ * [R,3] / feature [R,4] = (base colour, roughness) / alpha [R] of rays with directions dirs [R,3] into the arguments of the
+ * caller's two environment lookups -- hit_normal [R,3] for mode 'diffuse', reflected [R,3] + roughness [R] for mode 'specular'
+ * (cube-map prefilters of scene/light.py:264-328, evaluated by the caller) -- and a packed row pack [R,8];
+ * irgs_relight_combine takes the two lookups' results [R,3] and the FG table fg_lut [H,W,2] (nvdiffrast 'linear' / 'clamp'
+ * lookup at (N.V, roughness)) and writes local_light [R,3] = (base * diffuse + specular * (f0 * FG.x + FG.y)) * alpha (zeros when
+ * wo_indirect) and alpha_out [R], which irgs_shade_forward takes as (trace_color, trace_alpha) with saturate_alpha < 0.
+ * saturate_alpha = 1 - transmittance_min (GaussianModel.trace's normalisation), negative to skip.  Forward only (the reference
+ * runs this branch under torch.no_grad()). */
+int irgs_relight_hit(int64_t n_rays, const float *dirs, const float *trace_normal, const float *trace_feature,
+                     const float *trace_alpha, float saturate_alpha, float *hit_normal, float *reflected, float *roughness,
+                     float *pack, void *stream);
+int irgs_relight_combine(int64_t n_rays, const float *pack, const float *env_diffuse, const float *env_specular,
+                         const float *fg_lut, int lut_height, int lut_width, float f0, int wo_indirect, float *local_light,
+                         float *alpha_out, void *stream);
+
 /* ---- Parameter-level entry -----------------------------------------------------------------------
  * The caller glue of /root/reference/scene/gaussian_model.py:733-756 as kernels: surfel PARAMETERS (means [N,3], activated
  * scales [N,2], quaternions (w,x,y,z) [N,4], not necessarily normalised) -> the tracer's ru / rv / normals (utils/general_utils.py

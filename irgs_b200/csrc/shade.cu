@@ -214,6 +214,83 @@ __global__ void env_lookup_backward_kernel(EnvMap env, const float *__restrict__
     if (g_dirs) { g_dirs[3 * i] = gd[0]; g_dirs[3 * i + 1] = gd[1]; g_dirs[3 * i + 2] = gd[2]; }
 }
 
+
+// ------------------------------------------------------------------------------------------------ relight branch
+// gaussian_renderer/__init__.py:362-381: under novel lighting the radiance arriving from a surface point seen by a secondary
+// ray is not the baked SH colour but a split-sum shading of that HIT point: the ray composites the surfels' base colour and
+// roughness (S = 4 feature channels) and their normals; the hit point is shaded with the environment's diffuse / specular
+// prefilter (the caller's own envmap object: cube-map mips built by nvdiffrec / nvdiffrast, scene/light.py:264-328 -- out of
+// scope here) and the FG lookup table.  Two element-wise kernels around those two lookups replace the
+// reference's ~25 torch kernels over [P,S,*] tensors:
+//   relight_hit_kernel      raw tracer outputs + incident direction -> hit normal, reflected direction, roughness (the
+//                           arguments of the two environment lookups) and a packed row for the second kernel
+//   relight_combine_kernel  the two environment results + FG table -> local incident radiance and the normalised alpha,
+//                           in the form irgs_shade_forward consumes as (trace_color, trace_alpha) with saturate_alpha < 0
+__global__ void relight_hit_kernel(int64_t n_rays, const float *__restrict__ dirs, const float *__restrict__ normal,
+                                   const float *__restrict__ feature, const float *__restrict__ alpha, float saturate,
+                                   float *__restrict__ hit_normal, float *__restrict__ reflected, float *__restrict__ rough_out,
+                                   float *__restrict__ pack) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float a = alpha[r];
+    const bool sat = saturate >= 0.f && !(a < saturate);     // scene/gaussian_model.py:751-756
+    const float an = sat ? 1.0f : a;
+    float n[3], f[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) n[k] = sat ? normal[3 * r + k] / a : normal[3 * r + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = (sat ? feature[4 * r + k] / a : feature[4 * r + k]) / fmaxf(an, 1e-6f);   // :367
+    const float nl = fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-12f);                              // :368 F.normalize
+#pragma unroll
+    for (int k = 0; k < 3; ++k) n[k] /= nl;
+    const float wi[3] = {-dirs[3 * r], -dirs[3 * r + 1], -dirs[3 * r + 2]};                                      // :371
+    const float ndv = n[0] * wi[0] + n[1] * wi[1] + n[2] * wi[2];
+    float rf[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rf[k] = ndv * n[k] * 2.0f - wi[k];                                               // :373
+    const float rl = fmaxf(sqrtf(rf[0] * rf[0] + rf[1] * rf[1] + rf[2] * rf[2]), 1e-12f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        hit_normal[3 * r + k] = n[k];
+        reflected[3 * r + k] = rf[k] / rl;
+    }
+    rough_out[r] = f[3];
+    float4 *row = reinterpret_cast<float4 *>(pack + 8 * r);
+    row[0] = make_float4(f[0], f[1], f[2], fminf(fmaxf(ndv, 0.f), 1.f));                                          // :374 fg_uv.clamp(0, 1)
+    row[1] = make_float4(fminf(fmaxf(f[3], 0.f), 1.f), an, 0.f, 0.f);
+}
+
+// nvdiffrast texture(filter 'linear', boundary 'clamp') on the [H, W, 2] FG table, restated like the 'wrap' lookup of
+// shade_math.cuh: texel centres at (i + 0.5) / size, neighbour indices clamped to the table.
+__global__ void relight_combine_kernel(int64_t n_rays, const float *__restrict__ pack, const float *__restrict__ env_diffuse,
+                                       const float *__restrict__ env_specular, const float *__restrict__ fg_lut, int H, int W,
+                                       float f0, int wo_indirect, float *__restrict__ local, float *__restrict__ alpha_out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float4 p0 = __ldg(reinterpret_cast<const float4 *>(pack + 8 * r)), p1 = __ldg(reinterpret_cast<const float4 *>(pack + 8 * r) + 1);
+    const float x = p0.w * (float)W - 0.5f, y = p1.x * (float)H - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float tx = x - fx0, ty = y - fy0;
+    const int x0 = min(max((int)fx0, 0), W - 1), x1 = min(max((int)fx0 + 1, 0), W - 1);
+    const int y0 = min(max((int)fy0, 0), H - 1), y1 = min(max((int)fy0 + 1, 0), H - 1);
+    float fg[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float a00 = __ldg(fg_lut + ((size_t)y0 * W + x0) * 2 + c), a10 = __ldg(fg_lut + ((size_t)y0 * W + x1) * 2 + c);
+        const float a01 = __ldg(fg_lut + ((size_t)y1 * W + x0) * 2 + c), a11 = __ldg(fg_lut + ((size_t)y1 * W + x1) * 2 + c);
+        const float top = a00 + (a10 - a00) * tx, bot = a01 + (a11 - a01) * tx;
+        fg[c] = top + (bot - top) * ty;
+    }
+    const float ks = f0 * fg[0] + fg[1];                                                                          // :376
+    const float base[3] = {p0.x, p0.y, p0.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v = (base[k] * env_diffuse[3 * r + k] + env_specular[3 * r + k] * ks) * p1.y;                 // :370,376-377
+        local[3 * r + k] = wo_indirect ? 0.f : v;                                                                 // :378-379
+    }
+    alpha_out[r] = p1.y;
+}
+
 static int fail_msg(const char *msg) {
     set_error(msg);
     return 1;
@@ -315,6 +392,34 @@ int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const 
     if (!dirs || !g_out) return fail_msg("env lookup backward: null array");
     env_lookup_backward_kernel<<<(unsigned)((n_dirs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e, dirs, g_out, n_dirs, g_dirs,
                                                                                                    grad_env);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int irgs_relight_hit(int64_t n_rays, const float *dirs, const float *trace_normal, const float *trace_feature,
+                     const float *trace_alpha, float saturate_alpha, float *hit_normal, float *reflected, float *roughness,
+                     float *pack, void *stream) {
+    if (n_rays < 0) return fail_msg("n_rays < 0");
+    if (n_rays == 0) return 0;
+    if (!dirs || !trace_normal || !trace_feature || !trace_alpha || !hit_normal || !reflected || !roughness || !pack)
+        return fail_msg("relight_hit: null array");
+    relight_hit_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n_rays, dirs, trace_normal, trace_feature, trace_alpha, saturate_alpha, hit_normal, reflected, roughness, pack);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int irgs_relight_combine(int64_t n_rays, const float *pack, const float *env_diffuse, const float *env_specular,
+                         const float *fg_lut, int lut_height, int lut_width, float f0, int wo_indirect, float *local_light,
+                         float *alpha_out, void *stream) {
+    if (n_rays < 0) return fail_msg("n_rays < 0");
+    if (n_rays == 0) return 0;
+    if (!pack || !env_diffuse || !env_specular || !fg_lut || !local_light || !alpha_out) return fail_msg("relight_combine: null array");
+    if (lut_height < 1 || lut_width < 1) return fail_msg("relight_combine: the FG table must be at least 1 x 1");
+    relight_combine_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n_rays, pack, env_diffuse, env_specular, fg_lut, lut_height, lut_width, f0, wo_indirect ? 1 : 0, local_light, alpha_out);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;

@@ -265,20 +265,101 @@ def shade_incident(normals, sample_num, base_color, roughness, viewdirs, env_bas
     return {k: out[:, s] for k, s in OUT_SLICES.items()}
 
 
+@torch.no_grad()
+def relight_local_lights(dirs, trace_normal, trace_feature, trace_alpha, envmap, fg_lut, f0=0.04, transmittance_min=None,
+                         wo_indirect_relight=False):
+    """gaussian_renderer/__init__.py:365-379: the light a secondary ray brings back under NOVEL lighting -- its hit point shaded
+    with the environment's diffuse / specular prefilter and the FG table -- from the tracer's RAW normal [...,3], feature
+    [...,4] = (base colour, roughness) and alpha [...] of rays with directions dirs [...,3].  `envmap(l, mode='diffuse')` and
+    `envmap(l, roughness=r, mode='specular')` are the caller's (scene/light.py:264-328: cube-map mips, out of scope here); the
+    arithmetic around them runs in two kernels (irgs_relight_hit / irgs_relight_combine).  fg_lut: pc.FG_LUT, [1,H,W,2] or
+    [H,W,2].  Returns (local_incident_lights [...,3], alpha [...] after GaussianModel.trace's normalisation)."""
+    dev = dirs.device
+    shape = dirs.shape[:-1]
+    f = lambda t, c: t.reshape(-1, c).contiguous() if c else t.reshape(-1).contiguous()      # noqa: E731
+    d, n, ft, a = f(dirs, 3), f(trace_normal, 3), f(trace_feature, 4), f(trace_alpha, 0)
+    for name, t in (("dirs", d), ("trace_normal", n), ("trace_feature", ft), ("trace_alpha", a)):
+        if t.dtype != torch.float32 or t.device != dev or not t.is_cuda:
+            raise TypeError(f"{name} must be a float32 CUDA tensor on {dev}")
+    R = d.shape[0]
+    if n.shape[0] != R or ft.shape[0] != R or a.shape[0] != R:
+        raise ValueError("dirs, trace_normal, trace_feature [...,4] and trace_alpha must describe the same rays")
+    lut = fg_lut.reshape(fg_lut.shape[-3], fg_lut.shape[-2], 2).contiguous().float()
+    hit_n, refl, rough = torch.empty(R, 3, device=dev), torch.empty(R, 3, device=dev), torch.empty(R, device=dev)
+    pack, local, alpha_n = torch.empty(R, 8, device=dev), torch.empty(R, 3, device=dev), torch.empty(R, device=dev)
+    if R == 0:
+        return local.view(*shape, 3), alpha_n.view(*shape)
+    lib, st = _lib.load(), _stream(dev)
+    sat = -1.0 if transmittance_min is None else 1.0 - float(transmittance_min)
+    _lib.check(lib.irgs_relight_hit(R, _ptr(d), _ptr(n), _ptr(ft), _ptr(a), sat, _ptr(hit_n), _ptr(refl), _ptr(rough), _ptr(pack), st))
+    env_d = envmap(hit_n, mode="diffuse").reshape(R, 3).contiguous().float()                   # __init__.py:370
+    env_s = envmap(refl, roughness=rough[:, None], mode="specular").reshape(R, 3).contiguous().float()   # :376
+    _lib.check(lib.irgs_relight_combine(R, _ptr(pack), _ptr(env_d), _ptr(env_s), _ptr(lut), lut.shape[0], lut.shape[1], float(f0),
+                                        int(bool(wo_indirect_relight)), _ptr(local), _ptr(alpha_n), st))
+    return local.view(*shape, 3), alpha_n.view(*shape)
+
+
+def _rendering_equation_relight(base_color, roughness, normals, position, viewdirs, tracer, surfels, envmap, sample_num,
+                                light_sample_num, light_t_min, alpha_min, deg, fg_lut, f0, wo_indirect_relight):
+    """The relight branch (evaluation only, like eval_relighting_*.py: under torch.no_grad()).  `surfels`' feature slot holds
+    cat([pc.get_base_color, pc.get_rough], 1) [N,4] (__init__.py:363)."""
+    from . import incident
+    if fg_lut is None:
+        raise ValueError("relight=True needs fg_lut (pc.FG_LUT, the split-sum table assets/bsdf_256_256.bin)")
+    means3D, opacity, ru, rv, surf_normals, features, shs = surfels
+    if features is None or features.shape[-1] != 4:
+        raise ValueError("relight=True traces cat([base_color, roughness]) as features: surfels[5] must be [N,4]")
+    base, activation, transform = _env_fields(envmap)
+    P = base_color.shape[0]
+    with torch.no_grad():
+        _, t_normal, t_feature, _, t_alpha = tracer.trace_incident(position, normals, sample_num, means3D, opacity, ru, rv,
+                                                                   surf_normals, features, shs, alpha_min, t_min=light_t_min, deg=deg)
+        dirs = incident.incident_dirs(normals.contiguous(), sample_num)
+        local, alpha_n = relight_local_lights(dirs, t_normal, t_feature, t_alpha, envmap, fg_lut, f0, tracer.transmittance_min,
+                                              wo_indirect_relight)
+        common = dict(activation=activation, transform=transform, transmittance_min=None)
+        if light_sample_num == 0:
+            return shade_incident(normals, sample_num, base_color, roughness, viewdirs, base, local, alpha_n, **common)
+        pdf = getattr(envmap, "_pdf", None)
+        if pdf is None:
+            raise RuntimeError("light_sample_num > 0 needs the texel probabilities: call envmap.update_pdf() first")
+        total = sample_num + light_sample_num
+        mix = dict(pdf=pdf, p_diffuse=sample_num / total, p_light=light_sample_num / total, total_samples=total)
+        out_d = shade_incident(normals, sample_num, base_color, roughness, viewdirs, base, local, alpha_n, **common, **mix)
+        light_dirs, _ = envmap.sample_light_directions(P, light_sample_num, False)
+        light_dirs = light_dirs.detach().contiguous()
+        _, l_normal, l_feature, _, l_alpha = tracer.trace(position[:, None] + light_dirs * light_t_min, light_dirs, means3D, opacity,
+                                                          ru, rv, surf_normals, features, shs, alpha_min, deg=deg)
+        local_l, alpha_l = relight_local_lights(light_dirs, l_normal, l_feature, l_alpha, envmap, fg_lut, f0,
+                                                tracer.transmittance_min, wo_indirect_relight)
+        out_l = shade_incident(normals, light_sample_num, base_color, roughness, viewdirs, base, local_l, alpha_l, dirs=light_dirs,
+                               **common, **mix)
+        return {k: out_d[k] + out_l[k] for k in out_d}
+
+
 def rendering_equation(base_color, roughness, normals, position, viewdirs, tracer, surfels, envmap, sample_num,
                        training=False, azimuth=None, light_sample_num=0, light_t_min=0.05, alpha_min=1 / 255, deg=3,
-                       relight=False, wo_indirect=False, detach_indirect=False):
+                       relight=False, wo_indirect=False, detach_indirect=False, fg_lut=None, f0=0.04,
+                       wo_indirect_relight=False):
     """gaussian_renderer/__init__.py:334-415.  `tracer` + `surfels` stand for the reference's `pc.trace`, `envmap` for
     `pc.get_envmap`, sample_num / light_sample_num / light_t_min / wo_indirect / detach_indirect for the `pipe` fields of
     the same names (arguments/__init__.py:92-101).  training=True draws the per-point random azimuth like
     fibonacci_sphere_sampling(random_rotate=True) unless `azimuth` [P] is given.  light_sample_num > 0 additionally draws
     that many directions per point from `envmap` (its `_pdf` / `sample_light_directions`, like the reference)."""
-    if relight or sample_num <= 0 or light_sample_num < 0:
-        raise NotImplementedError("only the non-relight path with diffuse_sample_num > 0 is built")
+    if sample_num <= 0 or light_sample_num < 0:
+        raise NotImplementedError("diffuse_sample_num > 0 is required (the reference raises likewise, __init__.py:358-359)")
     P = base_color.shape[0]
     keys = ("diffuse", "specular", "light_direct") if training else tuple(OUT_SLICES)
     if P == 0:
         return {k: base_color.new_zeros(0, 1 if k == "visibility" else 3) for k in keys}
+    if relight:
+        # __init__.py:362-381; evaluation only (eval_relighting_*.py run it under no_grad): fg_lut = pc.FG_LUT, f0 as passed by
+        # rendering_equation_chunk, wo_indirect_relight = pipe.wo_indirect_relight; the Fibonacci samples are not rotated
+        if training:
+            raise NotImplementedError("the relight branch is forward-only (the reference evaluates it under torch.no_grad())")
+        out = _rendering_equation_relight(base_color, roughness, normals, position, viewdirs, tracer, surfels, envmap, sample_num,
+                                          light_sample_num, light_t_min, alpha_min, deg, fg_lut, f0, wo_indirect_relight)
+        return {k: out[k] for k in keys}
     if training and azimuth is None:
         azimuth = torch.rand(P, device=normals.device) * (2 * math.pi)                   # graphics_utils.py:31
     means3D, opacity, ru, rv, surf_normals, features, shs = surfels

@@ -188,3 +188,87 @@ def fibonacci_dirs(normals, sample_num, azimuth=None):
     flip = -torch.eye(3, dtype=dt).expand(P, 3, 3)
     R = torch.where((normals[..., 2] + 1 > 0)[:, None, None], R, flip)
     return F.normalize(R @ zs, dim=-2).transpose(-1, -2)
+
+
+# ------------------------------------------------------------------------------------------------ relight branch
+def texture_linear_clamp(tex, uv):
+    """nvdiffrast.torch.texture(filter_mode='linear', boundary_mode='clamp') restated like texture_linear_wrap (texel centres
+    at (i + 0.5) / size, neighbour indices clamped to the texture): tex [H, W, C], uv [..., 2] -> [..., C].  Used for the FG
+    table lookup of gaussian_renderer/__init__.py:375; "parity unpinned" like the wrap lookup (nvdiffrast is not in this image)."""
+    H, W = tex.shape[:2]
+    u = uv[..., 0].clamp(0, 1) * W - 0.5
+    v = uv[..., 1].clamp(0, 1) * H - 0.5
+    iu0, iv0 = torch.floor(u).long(), torch.floor(v).long()
+    fu, fv = (u - iu0)[..., None], (v - iv0)[..., None]
+    iu1, iv1 = (iu0 + 1).clamp(0, W - 1), (iv0 + 1).clamp(0, H - 1)
+    iu0, iv0 = iu0.clamp(0, W - 1), iv0.clamp(0, H - 1)
+    a00, a10, a01, a11 = tex[iv0, iu0], tex[iv0, iu1], tex[iv1, iu0], tex[iv1, iu1]
+    top = a00 + (a10 - a00) * fu
+    bot = a01 + (a11 - a01) * fu
+    return top + (bot - top) * fv
+
+
+class RelightEnvStandIn(torch.nn.Module):
+    """A test double for the reference's EnvLight with ALL THREE lookup modes (scene/light.py:264-328).  The real modes
+    'diffuse' / 'specular' read cube-map mips prefiltered by nvdiffrec's renderutils through nvdiffrast -- neither is in this
+    image and both are out of scope -- so this stand-in answers them from lat-long maps: 'diffuse' from
+    `base_diffuse`, 'specular' from a roughness-weighted blend of `base_spec0` / `base_spec1`.  'pure_env' is env_pure, the
+    reference's own lat-long path.  The reference's rendering_equation (relight=True) runs unmodified around it when the golden
+    vectors are recorded, and the same object (moved to the GPU) is handed to irgs_b200.shading.rendering_equation in the tests."""
+
+    def __init__(self, base, base_diffuse, base_spec0, base_spec1, activation="exp", transform=None):
+        super().__init__()
+        self.base = torch.nn.Parameter(base.clone(), requires_grad=False)
+        self.base_diffuse, self.base_spec0, self.base_spec1 = base_diffuse, base_spec0, base_spec1
+        self.activation_name, self.transform = activation, transform
+
+    def to(self, device):
+        self.base.data = self.base.data.to(device)
+        self.base_diffuse, self.base_spec0, self.base_spec1 = (t.to(device) for t in (self.base_diffuse, self.base_spec0, self.base_spec1))
+        return self
+
+    def _uv(self, l):
+        if self.transform is not None:
+            l = l @ torch.as_tensor(self.transform, dtype=l.dtype, device=l.device).T
+        return torch.cat([torch.atan2(l[..., :1], -l[..., 2:3]).nan_to_num() / (2.0 * math.pi) + 0.5,
+                          torch.acos(l[..., 1:2].clamp(-1.0 + 1e-6, 1.0 - 1e-6)) / math.pi], dim=-1).clamp(0, 1)
+
+    def __call__(self, l, mode="pure_env", roughness=None):
+        act = ACTIVATIONS[self.activation_name]
+        if mode == "pure_env":
+            return env_pure(self.base, l, self.activation_name, self.transform)
+        if mode == "diffuse":
+            return act(texture_linear_wrap(self.base_diffuse, self._uv(l))).clamp_min(0.0)
+        r = roughness.reshape(*l.shape[:-1], 1).clamp(0, 1)
+        uv = self._uv(l)
+        return act((1 - r) * texture_linear_wrap(self.base_spec0, uv) + r * texture_linear_wrap(self.base_spec1, uv)).clamp_min(0.0)
+
+
+def relight_local(dirs, normal_raw, feature_raw, alpha_raw, envmap, fg_lut, f0=0.04, transmittance_min=None,
+                  wo_indirect_relight=False):
+    """__init__.py:363-379 given the tracer's RAW normal [...,3] / feature [...,4] / alpha [...] (GaussianModel.trace's
+    normalisation, scene/gaussian_model.py:751-756, applied here when transmittance_min is given).  Returns
+    (local_incident_lights [...,3], trace_alpha [...])."""
+    alpha = alpha_raw
+    normal, feature = normal_raw, feature_raw
+    if transmittance_min is not None:
+        a_ = alpha[..., None]
+        sat = a_ < 1 - transmittance_min
+        normal = torch.where(sat, normal, normal / a_)
+        feature = torch.where(sat, feature, feature / a_)
+        alpha = torch.where(alpha < 1 - transmittance_min, alpha, torch.ones_like(alpha))
+    trace_alpha = alpha[..., None]
+    trace_feature = feature / trace_alpha.clamp_min(1e-6)
+    trace_normal = F.normalize(normal, dim=-1)
+    trace_base_color, trace_roughness = trace_feature.split([3, 1], dim=-1)
+    trace_diffuse = trace_base_color * envmap(trace_normal, mode="diffuse")
+    trace_wi = -dirs
+    trace_NdotV = (trace_normal * trace_wi).sum(-1, keepdim=True)
+    trace_reflected = F.normalize(trace_NdotV * trace_normal * 2 - trace_wi, dim=-1)
+    fg_uv = torch.cat([trace_NdotV, trace_roughness], -1).clamp(0, 1)
+    fg = texture_linear_clamp(fg_lut.reshape(fg_lut.shape[-3], fg_lut.shape[-2], 2), fg_uv)
+    trace_specular = envmap(trace_reflected, roughness=trace_roughness, mode="specular") * (f0 * fg[..., 0:1] + fg[..., 1:2])
+    local = (trace_diffuse + trace_specular) * trace_alpha
+    if wo_indirect_relight:
+        local = torch.zeros_like(local)
+    return local, alpha

@@ -16,7 +16,7 @@ want = ['launch__grid_size', 'launch__block_size', 'launch__registers_per_thread
        ['smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % k for k in
         ('long_scoreboard', 'short_scoreboard', 'wait', 'branch_resolving', 'not_selected', 'math_pipe_throttle',
          'mio_throttle', 'lg_throttle')]
-OUT = sys.argv[3] if len(sys.argv) > 3 else "r01_full_summary.csv"   # e.g. r01_shade_summary.csv for the shading kernels
+OUT = sys.argv[3] if len(sys.argv) > 3 else "r02_full_summary.csv"   # e.g. r01_shade_summary.csv for the shading kernels
 with open(os.path.join(ROOT, "profiles", OUT), "w") as f:
     w = csv.writer(f)
     w.writerow(['metric', 'unit'] + [r[hdr.index('Kernel Name')].split('(')[0] for r in rows[2:]])
@@ -34,7 +34,7 @@ for r in rows[2:]:
         json.dump({"kernel": "trace_forward_kernel<0,0>", "rays_per_launch": int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 24,
                    "dram_bytes_read": val(r, 'dram__bytes_read.sum'), "dram_bytes_write": val(r, 'dram__bytes_write.sum'),
                    "gpu_time_ms_under_ncu": float(r[hdr.index('gpu__time_duration.sum')]),
-                   "source": "profiles/r01_full_summary.csv (ncu --set full --clock-control none, bench.py C3 step, one forward launch)"},
+                   "source": "profiles/" + OUT + "  (ncu --set full --clock-control none, bench.py C3 step, one forward launch)"},
                   open(os.path.join(ROOT, "profiles", "fwd_kernel_traffic.json"), "w"), indent=1)
         break
 print(open(os.path.join(ROOT, "profiles", OUT)).read())

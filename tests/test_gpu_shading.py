@@ -201,8 +201,10 @@ def test_flags_empty_input_and_errors(small_scene):
     assert torch.equal(det["diffuse"], full["diffuse"])
     e = shading.rendering_equation(bc[:0], ro[:0], nrm[:0], pos[:0], view[:0], tr, surf, env, S, training=True)
     assert e["diffuse"].shape == (0, 3) and set(e) == {"diffuse", "specular", "light_direct"}
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                     # the relight branch needs the FG table and [N,4] features
         shading.rendering_equation(*args, relight=True)
+    with pytest.raises(NotImplementedError):            # ... and is forward-only
+        shading.rendering_equation(*args, relight=True, training=True, fg_lut=torch.zeros(1, 4, 4, 2, device=DEV))
     with pytest.raises(ValueError):
         shading.shade_incident(nrm, S, bc, ro, view, env.base, torch.zeros(P, S + 1, 3, device=DEV), torch.zeros(P, S, device=DEV))
     with pytest.raises(TypeError):
@@ -363,3 +365,95 @@ def test_light_sampling_matches_the_oracle_and_the_unfused_composition(small_sce
     with pytest.raises(RuntimeError):
         shading.rendering_equation(pt["base_color"], pt["roughness"], nrm, pos, view, tr, surf,
                                    shading.EnvLight(resolution=(8, 16), device=DEV), S, light_sample_num=4)
+
+
+# ---------------------------------------------------------------------------------------------- relight branch
+RELIGHT_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_relight.npz")
+RELIGHT_CASES = ("eval32", "eval24_light12_xf", "eval16_sigmoid_wo")
+
+
+def _relight_case(name):
+    z = np.load(RELIGHT_GOLDEN)
+    return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(name + "/")}
+
+
+def _relight_env(case, device):
+    t = lambda k: torch.from_numpy(case[k])                                                     # noqa: E731
+    tr = t("in_transform") if "in_transform" in case else None
+    env = osh.RelightEnvStandIn(t("in_base"), t("in_base_diffuse"), t("in_base_spec0"), t("in_base_spec1"), str(case["activation"]), tr)
+    return env.to(device)
+
+
+@pytest.mark.parametrize("name", RELIGHT_CASES)
+def test_relight_kernels_match_reference_golden(name):
+    """gaussian_renderer/__init__.py:362-381 recorded from the unmodified reference source (oracle/gen_golden_relight.py): the
+    relight kernels (irgs_relight_hit / irgs_relight_combine) + the shading epilogue, fed with the recorded raw tracer outputs
+    and the same environment stand-in the reference ran with, reproduce all six outputs."""
+    from irgs_b200 import incident, shading
+    case = _relight_case(name)
+    t = lambda k: torch.from_numpy(case[k]).to(DEV)                                             # noqa: E731
+    env = _relight_env(case, DEV)
+    S, Sl = int(case["S"]), int(case["n_light"])
+    f0, wo = float(case["f0"]), bool(case["wo_indirect_relight"])
+    nrm, bc, ro, view = t("in_normals"), t("in_base_color"), t("in_roughness"), t("in_viewdirs")
+    P = nrm.shape[0]
+    dirs = incident.incident_dirs(nrm, S)
+    assert np.abs(dirs.cpu().numpy() - case["rays_d"][:, :S]).max() <= 4e-7      # the directions the reference traced
+    raw = (t("in_normal_raw"), t("in_feature_raw"), t("in_alpha_raw"))
+    common = dict(activation=str(case["activation"]), transform=env.transform, transmittance_min=None)
+    local, alpha_n = shading.relight_local_lights(dirs, raw[0][:, :S], raw[1][:, :S], raw[2][:, :S], env, t("in_fg_lut"), f0, T_MIN, wo)
+    if Sl == 0:
+        out = shading.shade_incident(nrm, S, bc, ro, view, env.base, local, alpha_n, **common)
+    else:
+        mix = dict(pdf=t("in_pdf"), p_diffuse=S / (S + Sl), p_light=Sl / (S + Sl), total_samples=S + Sl)
+        ld = t("in_light_dirs")
+        assert np.abs(ld.cpu().numpy() - case["rays_d"][:, S:]).max() == 0
+        local_l, alpha_l = shading.relight_local_lights(ld, raw[0][:, S:], raw[1][:, S:], raw[2][:, S:], env, t("in_fg_lut"), f0, T_MIN, wo)
+        od = shading.shade_incident(nrm, S, bc, ro, view, env.base, local, alpha_n, **common, **mix)
+        ol = shading.shade_incident(nrm, Sl, bc, ro, view, env.base, local_l, alpha_l, dirs=ld, **common, **mix)
+        out = {k: od[k] + ol[k] for k in od}
+    for k in shading.OUT_SLICES:
+        _close(out[k], case["out_" + k].reshape(out[k].shape), f"{name}/{k}", tol=3e-4, cos_min=0.99999)
+    if wo:
+        assert float(out["light_indirect"].abs().max()) == 0.0
+
+
+def test_relight_rendering_equation_end_to_end(small_scene):
+    """shading.rendering_equation(relight=True) on a real scene -- S = 4 feature trace (base colour + roughness), hit-point
+    shading, epilogue -- against the CPU composition: oracle trace of the same incident rays -> oracle.shading.relight_local ->
+    oracle.shading.rendering_equation."""
+    import oracle
+    from irgs_b200 import incident, shading
+    from irgs_b200.raytracer import GaussianTracer
+    sc, inp = small_scene
+    g = {k: v.to(DEV) for k, v in inp.items()}
+    tr = GaussianTracer(transmittance_min=synth.T_MIN)
+    tr.build_from_surfels(g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], synth.ALPHA_MIN)
+    gen = torch.Generator().manual_seed(44)
+    N = inp["means3D"].shape[0]
+    feats = torch.cat([torch.rand(N, 3, generator=gen), 0.05 + 0.9 * torch.rand(N, 1, generator=gen)], 1)
+    surf = (g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], feats.to(DEV), g["shs"])
+    P, S = 48, 32
+    idx = torch.randint(0, N, (P,), generator=gen)
+    pos = (inp["means3D"][idx] + 0.01 * inp["normals"][idx]).contiguous()
+    nrm = inp["normals"][idx].contiguous()
+    view = torch.nn.functional.normalize(torch.tensor(synth.CAMERA_CENTER)[None] - pos, dim=-1)
+    bc, ro = torch.rand(P, 3, generator=gen), 0.1 + 0.8 * torch.rand(P, 1, generator=gen)
+    maps = [0.6 * torch.randn(16, 32, 3, generator=gen) for _ in range(4)]
+    env = osh.RelightEnvStandIn(*maps, "exp", None)
+    lut = 0.05 + 0.9 * torch.rand(1, 32, 32, 2, generator=gen)
+    with torch.no_grad():
+        out = shading.rendering_equation(bc.to(DEV), ro.to(DEV), nrm.to(DEV), pos.to(DEV), view.to(DEV), tr, surf,
+                                         osh.RelightEnvStandIn(*maps, "exp", None).to(DEV), S, relight=True, fg_lut=lut.to(DEV),
+                                         f0=0.02, light_t_min=synth.LIGHT_T_MIN, alpha_min=synth.ALPHA_MIN)
+        io, idr = incident.incident_rays(pos.to(DEV), nrm.to(DEV), S, None, synth.LIGHT_T_MIN)
+    Sc = oracle.Scene(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], inp["shs"], feats)
+    rt = oracle.trace_forward(Sc, io.reshape(-1, 3).cpu(), idr.reshape(-1, 3).cpu())
+    ok = torch.from_numpy(((rt["margin"][:, 0] > 2e-4) & (rt["margin"][:, 1] > 2e-4)).reshape(P, S).all(-1))
+    assert int(ok.sum()) >= P // 2 and rt["hit_count"].sum() > 0
+    f = lambda k, c: torch.from_numpy(rt[k]).view(P, S, c) if c else torch.from_numpy(rt[k]).view(P, S)    # noqa: E731
+    local, alpha_n = osh.relight_local(idr.cpu(), f("normal", 3), f("feature", 4), f("alpha", 0), env, lut, 0.02, synth.T_MIN)
+    want = osh.rendering_equation(bc, ro, nrm, view, idr.cpu(), local, alpha_n, maps[0], "exp", None, None)
+    for k in shading.OUT_SLICES:
+        err = float((out[k].cpu() - want[k])[ok].abs().max())
+        assert err <= 2e-4 * max(1.0, float(want[k].abs().max())), (k, err)

@@ -210,3 +210,28 @@ def test_oracle_light_sampling_matches_the_reference(name):
     areas = osh.mis_areas(torch.from_numpy(case["rays_d"]), torch.from_numpy(case["in_pdf"]), S, Sl, tr)
     assert areas.shape == (dirs.shape[0], S + Sl, 1) and bool(torch.isfinite(areas).all())
     assert float(areas.min()) > 0 and float(areas.max()) <= 2 * np.pi * (S + Sl) / S + 1e-3
+
+
+RELIGHT_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_relight.npz")
+
+
+@pytest.mark.parametrize("name", ["eval32", "eval24_light12_xf", "eval16_sigmoid_wo"])
+def test_oracle_relight_branch_matches_reference_golden(name):
+    """oracle.shading.relight_local + rendering_equation against the outputs of the UNMODIFIED reference rendering_equation
+    (relight=True, gaussian_renderer/__init__.py:362-381) recorded by oracle/gen_golden_relight.py."""
+    z = np.load(RELIGHT_GOLDEN)
+    case = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(name + "/")}
+    t = lambda k: torch.from_numpy(case[k])                                                     # noqa: E731
+    tr = t("in_transform") if "in_transform" in case else None
+    act = str(case["activation"])
+    env = osh.RelightEnvStandIn(t("in_base"), t("in_base_diffuse"), t("in_base_spec0"), t("in_base_spec1"), act, tr)
+    S, Sl = int(case["S"]), int(case["n_light"])
+    dirs = t("rays_d")
+    local, alpha_n = osh.relight_local(dirs, t("in_normal_raw"), t("in_feature_raw"), t("in_alpha_raw"), env, t("in_fg_lut"),
+                                       float(case["f0"]), 0.03, bool(case["wo_indirect_relight"]))
+    areas = osh.mis_areas(dirs, t("in_pdf"), S, Sl, tr) if Sl > 0 else None
+    out = osh.rendering_equation(t("in_base_color"), t("in_roughness"), t("in_normals"), t("in_viewdirs"), dirs, local, alpha_n,
+                                 t("in_base"), act, tr, None, areas)
+    for k, v in out.items():
+        ref = case["out_" + k].reshape(v.shape)
+        assert np.abs(v.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (k, np.abs(v.numpy() - ref).max())

@@ -614,10 +614,6 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->builder = value == 1 ? 1 : 0;
         return 0;
     }
-    if (strcmp(name, "bwd_waves") == 0) {
-        h->bwd_waves = value < 1 ? 1 : (value > 1024 ? 1024 : (int)value);
-        return 0;
-    }
     if (strcmp(name, "bwd_mode") == 0) {
         h->bwd_mode = (value == 1 || value == 2) ? (int)value : 0;
         return 0;

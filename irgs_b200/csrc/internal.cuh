@@ -110,7 +110,6 @@ struct irgs_tracer {
                                             // measured on B200: the sort costs more than it saves, profiles/r01_notes.md)
     unsigned long long *stats = nullptr;    // [4]
     int stats_enabled = 0;
-    int bwd_waves = 4;                      // hit-parallel replay: blocks launched per resident block (grid-stride loop)
     int bwd_mode = 0;                       // 0: hit-parallel replay (default), 1: thread-per-ray replay
     bool built = false;
     // host-streaming resources

@@ -254,13 +254,29 @@ def measure_c2(tracer, inp, args, device):
         for v in leaf.values():
             v.grad = None
 
-    for _ in range(3):
-        fwd_bwd()
-    torch.cuda.synchronize()
-    ms = _median_ms(fwd_bwd, 9, torch.cuda.synchronize)
+    # the same image with the pinhole rays generated inside the kernels (irgs_b200.primary.trace_camera)
+    from irgs_b200 import primary
+    cam = primary.Camera.look_at(synth.CAMERA_CENTER, (0.0, 0.0, 0.0), (0.0, 0.0, -1.0), 0.6911, args.img, args.img)
+
+    def cam_fwd_bwd():
+        outs = primary.trace_camera(tracer, cam, leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], None,
+                                    leaf["shs"], synth.ALPHA_MIN)
+        torch.autograd.backward([outs[0], outs[1], outs[3], outs[4]],
+                                [g[0].view(args.img, args.img, 3), g[1].view(args.img, args.img, 3), g[3].view(args.img, args.img),
+                                 g[4].view(args.img, args.img)])
+        for v in leaf.values():
+            v.grad = None
+
+    res = []
+    for f in (fwd_bwd, cam_fwd_bwd):
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        res.append(_median_ms(f, 9, torch.cuda.synchronize))
     tracer.accumulate_grads = was
     return {"workload": f"C2: {args.surfels} surfels, {args.img}x{args.img} primary rays, fwd+bwd, one call per GPU",
-            "rays": n, "ms": ms, "value": n / (ms * 1e-3), "unit": "rays/s"}
+            "rays": n, "ms": res[0], "value": n / (res[0] * 1e-3), "unit": "rays/s",
+            "generated_rays": {"ms": res[1], "value": n / (res[1] * 1e-3), "api": "irgs_b200.primary.trace_camera"}}
 
 
 def measure_c4(tracer, inp, args, device, rank, world, chunk, steps, sync_all):

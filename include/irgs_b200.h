@@ -236,6 +236,36 @@ int irgs_env_lookup_forward(const irgs_envmap_t *env, const float *dirs, int64_t
 int irgs_env_lookup_backward(const irgs_envmap_t *env, const float *dirs, const float *g_out, int64_t n_dirs, float *g_dirs,
                              float *grad_env, void *stream);
 
+/* ---- Primary pass through the tracer -------------------------------------------------------------
+ * The G-buffer the reference takes from its tile rasteriser (gaussian_renderer/__init__.py:121-131: alpha, normal, depth, base
+ * colour + roughness as features, SH colour) traced instead: the H x W pinhole rays of scene/cameras.py:87-100 are generated in
+ * the kernels from the camera (ray = v * width + u; d = normalize(cam_to_world ((u - W/2 + 0.5) / fx, (v - H/2 + 0.5) / fy, 1)),
+ * origin = the camera centre; cam_to_world = world_view_transform[:3,:3] of the reference, row-major), so no ray array exists.
+ * Outputs / gradients exactly as irgs_trace_forward / irgs_trace_backward (outputs [H*W, ...]); ray gradients go to the two
+ * scratch arrays [H*W,3] (the camera is not a parameter).  irgs_camera_rays writes the generated rays out (tests, callers that
+ * need rays_d_hw).  Not reproduced (stated parity risk): the rasteriser's per-tile ray-splat intersection in screen space, its
+ * low-pass filter, its median depth and distortion maps. */
+typedef struct {
+    float origin[3];          /* camera centre, world space */
+    float cam_to_world[9];    /* row-major 3x3: d_world = cam_to_world d_camera */
+    float fx, fy;             /* focal lengths in pixels */
+    int32_t width, height;
+} irgs_camera_t;
+int irgs_camera_rays(const irgs_camera_t *cam, float *rays_o, float *rays_d, void *stream);
+int irgs_trace_forward_camera(irgs_tracer_t *h, const irgs_camera_t *cam, int S, int K, int deg, const float *means3D,
+                              const float *opacity, const float *ru, const float *rv, const float *normals,
+                              const float *features, const float *shs, float *out_color, float *out_normal, float *out_feature,
+                              float *out_depth, float *out_alpha, int32_t *out_hit_count, int32_t *out_hits, int hit_cap,
+                              float alpha_min, float transmittance_min, int back_culling, void *stream);
+int irgs_trace_backward_camera(irgs_tracer_t *h, const irgs_camera_t *cam, int S, int K, int deg, const float *means3D,
+                               const float *opacity, const float *ru, const float *rv, const float *normals,
+                               const float *features, const float *shs, const float *color, const float *normal,
+                               const float *feature, const float *depth, const float *alpha, const int32_t *hit_count,
+                               const int32_t *hits, int hit_cap, const float *gout_color, const float *gout_normal,
+                               const float *gout_feature, const float *gout_depth, const float *gout_alpha,
+                               float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_fused, float *grad_features,
+                               float alpha_min, float transmittance_min, int back_culling, void *stream);
+
 /* ---- Relight branch of rendering_equation (gaussian_renderer/__init__.py:362-381) ---------------------------------------------
  * The hit point of every secondary ray is shaded under the novel environment: irgs_relight_hit turns the tracer's raw normal
  * [R,3] / feature [R,4] = (base colour, roughness) / alpha [R] of rays with directions dirs [R,3] into the arguments of the

@@ -41,6 +41,10 @@ PROTOTYPES = {
                                 + [_vp] * 2 + [_f32, _f32, _i32, _i64]),
     "irgs_trace_fwd_bwd_incident_host": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_i64] + [_vp] * 3
                                          + [_vp] * 2 + [_f32, _f32, _i32, _i64, _vp]),
+    "irgs_camera_rays": (_i32, [_vp, _vp, _vp, _vp]),
+    "irgs_trace_forward_camera": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_vp, _vp, _i32, _f32, _f32, _i32, _vp]),
+    "irgs_trace_backward_camera": (_i32, [_vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp] * 5 + [_vp, _vp, _i32] + [_vp] * 5
+                                   + [_vp] * 4 + [_f32, _f32, _i32, _vp]),
     "irgs_relight_hit": (_i32, [_i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
     "irgs_relight_combine": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
     "irgs_surfel_frames": (_i32, [_vp, _vp, _vp, ctypes.POINTER(_f32), _i64, _vp, _vp, _vp, _vp]),

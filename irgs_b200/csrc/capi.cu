@@ -234,12 +234,26 @@ static void set_generator(TraceArgs &a, const irgs_incident_t *gen) {
     a.gen_S = gen->sample_num; a.gen_tmin = gen->t_min; a.gen_P = gen->n_points;
 }
 
+static int validate_camera(const irgs_camera_t *cam) {
+    if (!cam) return fail("null camera descriptor");
+    if (cam->width < 1 || cam->height < 1) return fail("camera: width and height must be positive");
+    if (!(cam->fx > 0.f) || !(cam->fy > 0.f)) return fail("camera: focal lengths must be positive");
+    if ((int64_t)cam->width * cam->height >= ((int64_t)1 << 31)) return fail("camera: width * height must be below 2^31");
+    return 0;
+}
+static void set_camera(TraceArgs &a, const irgs_camera_t *cam) {
+    if (!cam) return;
+    a.cam_W = cam->width; a.cam_H = cam->height; a.cam_fx = cam->fx; a.cam_fy = cam->fy;
+    for (int k = 0; k < 3; ++k) a.cam_o[k] = cam->origin[k];
+    for (int k = 0; k < 9; ++k) a.cam_M[k] = cam->cam_to_world[k];
+}
+
 static int trace_forward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int64_t n_rays, int S, int K, int deg,
                               const float *rays_o, const float *rays_d, const float *means, const float *opacity,
                               const float *ru, const float *rv, const float *normals, const float *features,
                               const float *shs, float *out_color, float *out_normal, float *out_feature, float *out_depth,
                               float *out_alpha, int32_t *out_hit_count, int32_t *out_hits, int hit_cap, float alpha_min,
-                              float T_min, int back_culling, void *stream) {
+                              float T_min, int back_culling, void *stream, const irgs_camera_t *cam = nullptr) {
     if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
     if (n_rays == 0) return 0;
     if (out_hits && hit_cap == 0) out_hits = nullptr;
@@ -248,6 +262,7 @@ static int trace_forward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int6
     TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
                             alpha_min, T_min, back_culling);
     set_generator(a, gen);
+    set_camera(a, cam);
     a.color = out_color; a.normal = out_normal; a.feature = out_feature; a.depth = out_depth; a.alpha = out_alpha;
     a.hit_count = out_hit_count; a.hits = out_hits; a.hit_cap = hit_cap;
     if (launch_pack_records(h, a, s) || launch_incident_prepare(h, a, s)) return 1;
@@ -292,7 +307,7 @@ static int trace_backward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int
                                int hit_cap, const float *gout_color, const float *gout_normal, const float *gout_feature,
                                const float *gout_depth, const float *gout_alpha, float *grad_rays_o, float *grad_rays_d,
                                float *grad_fused, float *grad_features, float alpha_min, float T_min, int back_culling,
-                               void *stream) {
+                               void *stream, const irgs_camera_t *cam = nullptr) {
     if (validate_trace(h, n_rays, S, K, deg, hit_cap)) return 1;
     if (n_rays == 0) return 0;
     if (!grad_fused) return fail("grad_fused must not be null");
@@ -303,6 +318,7 @@ static int trace_backward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int
     TraceArgs a = make_args(n_rays, (int)h->n, S, K, deg, rays_o, rays_d, means, opacity, ru, rv, normals, features, shs,
                             alpha_min, T_min, back_culling);
     set_generator(a, gen);
+    set_camera(a, cam);
     a.color = const_cast<float *>(color); a.normal = const_cast<float *>(normal);
     a.feature = const_cast<float *>(feature); a.depth = const_cast<float *>(depth); a.alpha = const_cast<float *>(alpha);
     if (hits && hit_count && hit_cap > 0) {
@@ -351,6 +367,41 @@ int irgs_trace_backward_incident(irgs_tracer_t *h, const irgs_incident_t *gen, i
     return launch_incident_backward(gen->position, gen->normals, gen->azimuth, gen->n_points, gen->sample_num, gen->t_min,
                                     scratch_grad_rays_o, scratch_grad_rays_d, grad_position, grad_normal_pt,
                                     (cudaStream_t)stream);
+}
+
+int irgs_trace_forward_camera(irgs_tracer_t *h, const irgs_camera_t *cam, int S, int K, int deg, const float *means,
+                              const float *opacity, const float *ru, const float *rv, const float *normals,
+                              const float *features, const float *shs, float *out_color, float *out_normal, float *out_feature,
+                              float *out_depth, float *out_alpha, int32_t *out_hit_count, int32_t *out_hits, int hit_cap,
+                              float alpha_min, float T_min, int back_culling, void *stream) {
+    if (validate_camera(cam)) return 1;
+    return trace_forward_impl(h, nullptr, (int64_t)cam->width * cam->height, S, K, deg, nullptr, nullptr, means, opacity, ru, rv,
+                              normals, features, shs, out_color, out_normal, out_feature, out_depth, out_alpha, out_hit_count,
+                              out_hits, hit_cap, alpha_min, T_min, back_culling, stream, cam);
+}
+
+int irgs_trace_backward_camera(irgs_tracer_t *h, const irgs_camera_t *cam, int S, int K, int deg, const float *means,
+                               const float *opacity, const float *ru, const float *rv, const float *normals,
+                               const float *features, const float *shs, const float *color, const float *normal,
+                               const float *feature, const float *depth, const float *alpha, const int32_t *hit_count,
+                               const int32_t *hits, int hit_cap, const float *gout_color, const float *gout_normal,
+                               const float *gout_feature, const float *gout_depth, const float *gout_alpha,
+                               float *scratch_grad_rays_o, float *scratch_grad_rays_d, float *grad_fused, float *grad_features,
+                               float alpha_min, float T_min, int back_culling, void *stream) {
+    if (validate_camera(cam)) return 1;
+    return trace_backward_impl(h, nullptr, (int64_t)cam->width * cam->height, S, K, deg, nullptr, nullptr, means, opacity, ru, rv,
+                               normals, features, shs, color, normal, feature, depth, alpha, hit_count, hits, hit_cap, gout_color,
+                               gout_normal, gout_feature, gout_depth, gout_alpha, scratch_grad_rays_o, scratch_grad_rays_d,
+                               grad_fused, grad_features, alpha_min, T_min, back_culling, stream, cam);
+}
+
+int irgs_camera_rays(const irgs_camera_t *cam, float *rays_o, float *rays_d, void *stream) {
+    if (validate_camera(cam)) return 1;
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    set_camera(a, cam);
+    a.n_rays = (int64_t)cam->width * cam->height;
+    return launch_generated_rays(a, rays_o, rays_d, (cudaStream_t)stream);
 }
 
 int irgs_unpack_grads(const float *grad_fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,

@@ -167,6 +167,10 @@ struct TraceArgs {
     int64_t gen_P;
     const struct IncPoint *gen_pts;   // [P] per-point records (rotation, azimuth sin / cos), filled by launch_incident_prepare
     const struct IncTab *gen_tab;     // [gen_S] per-sample table (incident_table)
+    // fused PRIMARY-ray generation: when cam_W > 0 ray = v * cam_W + u is the pinhole ray of pixel (u, v),
+    // scene/cameras.py:87-100: d = normalize(M ((u - W/2 + 0.5) / fx, (v - H/2 + 0.5) / fy, 1)), origin = the camera centre
+    int cam_W, cam_H;
+    float cam_fx, cam_fy, cam_o[3], cam_M[9];
     const int *ray_order;  // forward: optional processing order (coherence sort); results are still written per ray id
     int64_t ray_mul;       // forward: 0, or an odd multiplier coprime to n_rays (n_rays <= 2^19): the i-th ray started is (i * ray_mul) % n_rays
                            // (small launches: spreads the heavy rays of one pixel bundle over the warps, launch_trace_forward)
@@ -190,6 +194,7 @@ int launch_incident_backward(const float *position, const float *normals, const 
                              float *grad_normal_pt, cudaStream_t s);
 int launch_incident_rays(const float *position, const float *normals, const float *azimuth, int64_t n_points, int sample_num,
                          float t_min, float *rays_o, float *rays_d, cudaStream_t s);
+int launch_generated_rays(const TraceArgs &a, float *rays_o, float *rays_d, cudaStream_t s);   // the rays load_ray() produces, written out
 int launch_unpack_grads(const float *fused, int64_t n, int K, float *gm, float *go, float *gru, float *grv,
                         float *gn, float *gsh, cudaStream_t s);
 

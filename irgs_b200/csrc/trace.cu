@@ -761,6 +761,16 @@ __global__ void incident_rays_kernel(const float *__restrict__ position, const f
     if (rays_d) { rays_d[3 * ray] = dx; rays_d[3 * ray + 1] = dy; rays_d[3 * ray + 2] = dz; }
 }
 
+// The rays of a generator (camera rays here; incident rays have their own entry) exactly as load_ray() hands them to the tracer.
+__global__ void generated_rays_kernel(const TraceArgs a, float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.n_rays) return;
+    RayCtx r;
+    load_ray(a, ray, r);
+    if (rays_o) { rays_o[3 * ray] = r.ox; rays_o[3 * ray + 1] = r.oy; rays_o[3 * ray + 2] = r.oz; }
+    if (rays_d) { rays_d[3 * ray] = r.dx; rays_d[3 * ray + 1] = r.dy; rays_d[3 * ray + 2] = r.dz; }
+}
+
 // Chain rule from the per-ray gradients of the tracer back to the shading point: one warp per point.
 //   o = x + t_min d,  d = v / |v|,  v = R(n) zs   =>   dL/dx = sum_s g_o,   dL/dd = g_d + t_min g_o,
 //   dL/dv = (dL/dd - d (d . dL/dd)) / |v|,   dL/dR = sum_s dL/dv zs^T   (zero on the constant -identity branch).
@@ -1000,6 +1010,14 @@ int launch_incident_backward(const float *position, const float *normals, const 
     if (!tab) return 1;
     incident_backward_kernel<<<(unsigned)((n_points * 32 + 127) / 128), 128, 0, s>>>(
         position, normals, azimuth, n_points, sample_num, t_min, tab, g_rays_o, g_rays_d, grad_position, grad_normal);
+    count_launch();
+    IRGS_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_generated_rays(const TraceArgs &a, float *rays_o, float *rays_d, cudaStream_t s) {
+    if (a.n_rays <= 0) return 0;
+    generated_rays_kernel<<<(unsigned)((a.n_rays + 255) / 256), 256, 0, s>>>(a, rays_o, rays_d);
     count_launch();
     IRGS_CHECK(cudaGetLastError());
     return 0;

@@ -354,6 +354,19 @@ __device__ __forceinline__ IncTab load_inc_tab(const IncTab *__restrict__ t) {
 }
 
 __device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
+    if (a.cam_W > 0) {
+        // scene/cameras.py:87-100 (rays_d_camera @ world_view_transform[:3,:3].T, F.normalize), generated instead of read
+        const int v = (int)((unsigned)ray / (unsigned)a.cam_W), u = (int)((unsigned)ray - (unsigned)v * (unsigned)a.cam_W);
+        const float cx = __fdiv_rn(__fadd_rn(__fsub_rn((float)u, 0.5f * (float)a.cam_W), 0.5f), a.cam_fx);
+        const float cy = __fdiv_rn(__fadd_rn(__fsub_rn((float)v, 0.5f * (float)a.cam_H), 0.5f), a.cam_fy);
+        const float wx = __fmaf_rn(a.cam_M[0], cx, __fmaf_rn(a.cam_M[1], cy, a.cam_M[2]));
+        const float wy = __fmaf_rn(a.cam_M[3], cx, __fmaf_rn(a.cam_M[4], cy, a.cam_M[5]));
+        const float wz = __fmaf_rn(a.cam_M[6], cx, __fmaf_rn(a.cam_M[7], cy, a.cam_M[8]));
+        const float len = fmaxf(__fsqrt_rn(__fmaf_rn(wz, wz, __fmaf_rn(wy, wy, __fmul_rn(wx, wx)))), 1e-12f);
+        r.dx = __fdiv_rn(wx, len); r.dy = __fdiv_rn(wy, len); r.dz = __fdiv_rn(wz, len);
+        r.ox = a.cam_o[0]; r.oy = a.cam_o[1]; r.oz = a.cam_o[2];
+        return;
+    }
     if (a.gen_pos != nullptr) {
         // gaussian_renderer/__init__.py:376: origin = position + dir * light_t_min, generated instead of read
         // (a call's rays number < 2^31, checked by the launcher: one 32-bit division instead of a 64-bit one)

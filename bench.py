@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--e2e-chunk", type=int, default=0, help="rays per chunk of the host-buffer path (0: chosen from the shard size)")
     p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
     p.add_argument("--no-shade", action="store_true", help="skip the rendering-equation measurement (fused generation + shading epilogue)")
+    p.add_argument("--shard-block", type=int, default=32, help="pixel bundles are dealt to the ranks in blocks of this many consecutive pixels")
     p.add_argument("--no-other", action="store_true", help="skip the other BASELINE.json configurations (C2, C4, C5) and the small-call timings")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
@@ -119,7 +120,7 @@ def build_workload(args, device, rank, world, tracer_factory):
                             synth.ALPHA_MIN)
     pts, nrm = synth.shading_points_from_primary(o, d, outs[3], outs[4], outs[1])
     # this rank's pixel bundles: blocks of 32 consecutive pixels dealt round-robin (load balance; world 1: all pixels)
-    pix = parallel.shard_interleaved(args.img * args.img, rank, world, block=32)
+    pix = parallel.shard_interleaved(args.img * args.img, rank, world, block=getattr(args, "shard_block", 32))
     n_pix = pix.numel()
     rays_o = torch.empty(n_pix * args.spp, 3, device=device)
     rays_d = torch.empty(n_pix * args.spp, 3, device=device)
@@ -162,6 +163,32 @@ def canonical_counters(inp, rays_o, rays_d, n_sample=1 << 16):
     sel = torch.randint(0, rays_o.shape[0], (n_sample,), generator=g).to(rays_o.device)
     r = oracle.trace_forward(S, rays_o[sel].cpu(), rays_d[sel].cpu(), use_bvh=True, hit_cap=4)
     return S, (r["counters"] / float(n_sample)).tolist()
+
+
+def ncu_counters(path=os.path.join(ROOT, "profiles", "r02_full_summary.csv")):
+    """What actually bounds the forward kernel, from the committed `ncu --set full` capture of the same build (scripts/
+    profile_final.sh -> scripts/ncu_summary.py): the L1TEX data pipe, the issue slots, DRAM -- not the contractual roofline
+    numerator, which counts algorithmic bytes of a structure the kernel mostly finds in L2."""
+    try:
+        import csv
+        rows = {r[0]: r for r in csv.reader(open(path))}
+        col = next(i for i, name in enumerate(rows["metric"]) if "trace_forward" in name)
+        f = lambda k: float(rows[k][col].replace(",", ""))                                 # noqa: E731
+        gb = {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}
+        dram = sum(f(k) * gb[rows[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        ms = f("gpu__time_duration.sum")
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if \
+            os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        return {"source": "profiles/" + os.path.basename(path) + " (ncu --set full, one forward launch of the C3 step)",
+                "l1tex_lsu_pct": f("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                "issue_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "dram_pct": 100.0 * dram / (ms * 1e-3) / peak,
+                "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "l2_hit_pct": f("lts__t_sector_hit_rate.pct"), "inst_executed": f("smsp__inst_executed.sum"),
+                "lsu_wavefronts_shared": f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                "gpu_time_ms_under_ncu": ms, "registers": f("launch__registers_per_thread")}
+    except Exception as e:      # the capture is evidence, not a dependency of the measurement
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def cpu_baseline(S, rays_o, rays_d, seconds):
@@ -415,6 +442,11 @@ def run_ours(args):
     from irgs_b200.raytracer import GaussianTracer, _ptr
     # NCCL's own log lines (e.g. "NCCL version ..." when NCCL_DEBUG is set on the box) go to stderr: stdout carries the JSON line only
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # ... and whatever a library still writes to file descriptor 1 (NCCL prints its version line there) is sent to stderr until
+    # the result line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, local, world = parallel.init_from_env()
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
@@ -723,6 +755,7 @@ def run_ours(args):
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass
+    counters = ncu_counters()
     S, (V, P, H) = canonical_counters(inp, rays_o, rays_d)
     bytes_per_ray = 24 + 32 + 32 * V + 64 * P + 192 * H  # BASELINE.md section 4, forward, S = 0
     achieved = bytes_per_ray * fwd_rays / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None
@@ -742,6 +775,7 @@ def run_ours(args):
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_ray * chunk,
                      "algorithmic_bytes_per_ray": bytes_per_ray,
                      "canonical_counters_per_ray": {"V_boxes": V, "P_surfel_tests": P, "H_hits": H},
+                     "ncu_counters": counters,
                      "kernel_ms_per_step": fwd_ms, "serial_step_ms": serial_step_ms,
                      "kernel_share_of_step": fwd_ms / serial_step_ms,
                      "timing": "one extra single-stream step right after the timed region, CUDA events around each forward "
@@ -753,6 +787,8 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(S, rays_o, rays_d, args.cpu_seconds)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)
 
 

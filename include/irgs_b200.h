@@ -312,6 +312,9 @@ int irgs_normalize_outputs_backward(int64_t n_rays, int S, float threshold, cons
  * candidate scratch) looked up from the call's own `stream`, so a backward uses the slot of the stream it runs on ("slot" is
  * still accepted and ignored).  A handle is not thread-safe beyond that: do not build / refit while traces are in flight.
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
+ * "gen_in_kernel": 0 (default) incident / camera rays of a forward call are written to an internal scratch block by a small
+ * kernel and read back by the forward kernel (measured faster: DRAM is idle, the persistent walk is not), 1 generates them
+ * inside the forward kernel (24 B per ray of a call less memory).  The backward always regenerates them in its kernels.
  * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 

@@ -115,6 +115,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
         cudaFree(h->rsort_hist[i]);
         cudaFree(h->cand[i]);
         cudaFree(h->inc_pts[i]);
+        cudaFree(h->ray_scratch[i]);
     }
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
@@ -663,6 +664,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
     if (strcmp(name, "slot") == 0) return 0;   // accepted for compatibility: slots follow the stream of each call now
     if (strcmp(name, "builder") == 0) {   // takes effect at the next build_bvh / build_from_surfels
         h->builder = value == 1 ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "gen_in_kernel") == 0) {
+        h->gen_in_kernel = value ? 1 : 0;
         return 0;
     }
     if (strcmp(name, "bwd_mode") == 0) {

@@ -101,6 +101,9 @@ struct irgs_tracer {
     int *rsort_vals[MAX_SLOTS][2] = {};
     int *rsort_hist[MAX_SLOTS] = {};
     int64_t rsort_cap[MAX_SLOTS] = {};
+    float *ray_scratch[MAX_SLOTS] = {};     // generated rays of a forward call, materialised per stream slot (o[3n] d[3n])
+    int64_t ray_scratch_cap[MAX_SLOTS] = {};
+    int gen_in_kernel = 0;                  // 1: generate incident / camera rays inside the forward kernel instead
     void *inc_pts[MAX_SLOTS] = {};          // per-point records of generated incident rays (IncPoint[inc_cap]), per stream slot
     int64_t inc_cap[MAX_SLOTS] = {};
     int bwd_carveout_pct = -1;              // backward replay kernel: carve-out hint in percent (-1: the driver's default)

@@ -353,6 +353,11 @@ __device__ __forceinline__ IncTab load_inc_tab(const IncTab *__restrict__ t) {
     return q;
 }
 
+__device__ __forceinline__ void load_ray_mem(const TraceArgs &a, int64_t ray, RayCtx &r) {
+    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
+    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
+}
+
 __device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx &r) {
     if (a.cam_W > 0) {
         // scene/cameras.py:87-100 (rays_d_camera @ world_view_transform[:3,:3].T, F.normalize), generated instead of read
@@ -379,8 +384,7 @@ __device__ __forceinline__ void load_ray(const TraceArgs &a, int64_t ray, RayCtx
         r.oz = __fadd_rn(__ldg(a.gen_pos + 3 * pt + 2), __fmul_rn(r.dz, a.gen_tmin));
         return;
     }
-    r.ox = __ldg(a.rays_o + 3 * ray); r.oy = __ldg(a.rays_o + 3 * ray + 1); r.oz = __ldg(a.rays_o + 3 * ray + 2);
-    r.dx = __ldg(a.rays_d + 3 * ray); r.dy = __ldg(a.rays_d + 3 * ray + 1); r.dz = __ldg(a.rays_d + 3 * ray + 2);
+    load_ray_mem(a, ray, r);
 }
 
 }  // namespace irgs

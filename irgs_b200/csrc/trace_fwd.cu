@@ -84,16 +84,33 @@ struct WarpSmem {
     float seg_T[32];
     int64_t seg_ray[32];
 };
+// GENERATED rays (incident / camera): a per-warp queue of the next 32 rays -- 7 words a slot: origin, direction, ray id (a
+// forward call traces fewer than 2^31 rays: checked by the launcher) -- lives in the seven deepest shared-memory entries of
+// the traversal stack, which then holds SSTK - 7 entries before it spills to local memory (a dedicated 3.5 KB per block
+// measured 2 % slower on every path: the L1 that the shared memory carve-out leaves matters more than seven stack entries).
+constexpr int RQ_WORDS = 7;
 
-template <bool FEAT, bool STATS>
+// One lane's share of a queue fill: generate ray `qr` and store it in slot `lane`.  (Keeping this out of line would keep the
+// ray arithmetic out of the persistent loop's register allocation, but ptxas 12.9 crashes on a call inside this kernel.)
+__device__ __forceinline__ void fill_ray_queue(const TraceArgs &a, int64_t qr, float *rq, int lane) {
+    RayCtx t;
+    load_ray(a, qr, t);
+    rq[0 * 32 + lane] = t.ox; rq[1 * 32 + lane] = t.oy; rq[2 * 32 + lane] = t.oz;
+    rq[3 * 32 + lane] = t.dx; rq[4 * 32 + lane] = t.dy; rq[5 * 32 + lane] = t.dz;
+    rq[6 * 32 + lane] = __int_as_float((int)qr);
+}
+
+template <bool FEAT, bool STATS, bool GEN>
 __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(const KParams p, uint4 *__restrict__ cand_base) {
+    constexpr int SS = GEN ? SSTK - RQ_WORDS : SSTK;   // traversal stack entries in shared memory
     __shared__ WarpSmem<FEAT> smem[TB / 32];
+
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
     WarpSmem<FEAT> &ws = smem[tid >> 5];
     int *stk = ws.stack + lane;
     int *pend = ws.pend + lane;
-    int stack_spill[STACK - SSTK];
+    int stack_spill[STACK - SS];
     const unsigned FULL = 0xffffffffu;
     const TraceArgs &a = p.a;
     const float alpha_min = a.alpha_min, T_min = a.T_min;
@@ -102,7 +119,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0, st_graze = 0, st_graze_comp = 0;
 
     int phase = PH_FETCH;
-    bool pool_empty = false;  // warp-uniform
+    bool pool_empty = false;  // warp-uniform: the global counter has run past the last ray (the queue may still hold some)
+    int q_head = 0, q_cnt = 0; // warp-uniform: the ray queue of this warp
     int64_t ray = 0;
     RayCtx r;
     float T = 1.f;
@@ -114,10 +132,52 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         // (a refill serves whatever lanes are idle: it waits until FETCH_MIN of them are, or until the walk is short of lanes)
+        // Rays come from a per-warp QUEUE of 32: when it runs dry the warp takes the next 32 rays off the global counter and all
+        // 32 lanes load -- or, for incident / camera rays, GENERATE -- one ray each into shared memory.  Generating at the
+        // refill itself ran the ray arithmetic (point record, table entry, angle addition, three divisions) at 7 of 32 lanes and
+        // put its dependent loads in front of every refill: trace_incident was 5.3 % behind trace on the same 2^24 rays.
         const unsigned need = __ballot_sync(FULL, phase == PH_FETCH);
         const bool refill = __popc(need) >= FETCH_MIN ||
                             __popc(__ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE)) < MIN_ACTIVE;
-        if (need != 0u && !pool_empty && refill) {
+        if (GEN) {
+            float *rq = reinterpret_cast<float *>(ws.stack + SS * 32);   // [word][slot]
+            if (need != 0u && refill && !(pool_empty && q_cnt == 0)) {
+                const int want = __popc(need), my_rank = __popc(need & lt_mask);
+                int given = 0;
+                for (int round = 0; round < 2 && given < want; ++round) {
+                    if (q_cnt == 0 && !pool_empty) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(p.counter, 32ull);
+                        base = __shfl_sync(FULL, base, 0);
+                        int64_t qr = (int64_t)base + lane;
+                        __syncwarp();
+                        if (qr < a.n_rays) {
+                            if (a.ray_mul != 0) qr = (int64_t)(((unsigned)qr * (unsigned)a.ray_mul) % (unsigned)a.n_rays);   // < 2^32
+                            fill_ray_queue(a, qr, rq, (int)lane);
+                        }
+                        __syncwarp();
+                        q_head = 0;
+                        q_cnt = (int)min((long long)32, max((long long)0, (long long)a.n_rays - (long long)base));
+                        if (base + 32ull >= (unsigned long long)a.n_rays) pool_empty = true;
+                    }
+                    const int take = min(want - given, q_cnt);
+                    if (phase == PH_FETCH && my_rank >= given && my_rank < given + take) {
+                        const int slot = q_head + (my_rank - given);
+                        r.ox = rq[0 * 32 + slot]; r.oy = rq[1 * 32 + slot]; r.oz = rq[2 * 32 + slot];
+                        r.dx = rq[3 * 32 + slot]; r.dy = rq[4 * 32 + slot]; r.dz = rq[5 * 32 + slot];
+                        ray = __float_as_int(rq[6 * 32 + slot]);
+                        ray_setup(r, p.qframe);
+                        T = 1.f;
+                        t_last = -INFINITY; g_last = -1; total = 0;
+                        cnt = 0; sp = 0; pn = 0; cur = 0; t_lo = 0.f; t_hi = IRGS_T_SCENE_MAX; g_hi = INT_MAX; more = false;
+                        phase = PH_TRAV;
+                        if (STATS) ++st_pass;
+                    }
+                    q_head += take; q_cnt -= take; given += take;
+                    if (pool_empty && q_cnt == 0) break;
+                }
+            }
+        } else if (need != 0u && !pool_empty && refill) {
             const int leader = __ffs(need) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));
@@ -127,7 +187,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 if (ray < a.n_rays) {
                     if (a.ray_order != nullptr) ray = __ldg(a.ray_order + ray);
                     else if (a.ray_mul != 0) ray = (int64_t)(((unsigned)ray * (unsigned)a.ray_mul) % (unsigned)a.n_rays);   // < 2^32
-                    load_ray(a, ray, r);
+                    load_ray_mem(a, ray, r);   // (generated rays never reach this kernel variant: launch_trace_forward)
                     ray_setup(r, p.qframe);
                     T = 1.f;
                     t_last = -INFINITY; g_last = -1; total = 0;
@@ -138,10 +198,10 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             }
             if (base + (unsigned long long)__popc(need) >= (unsigned long long)a.n_rays) pool_empty = true;
         }
-        if (__ballot_sync(FULL, phase != PH_FETCH) == 0u) break;  // pool empty and every lane idle
+        if (__ballot_sync(FULL, phase != PH_FETCH) == 0u) break;  // no rays left (a refill would have handed some out) and every lane idle
 
         // ------------------------------------------------------------------ BVH walk, NODE sub-phase
-        const int thr = pool_empty ? 1 : MIN_ACTIVE;
+        const int thr = (GEN ? (pool_empty && q_cnt == 0) : pool_empty) ? 1 : MIN_ACTIVE;
         unsigned walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
         // (a node visit can queue four leaves: the loop is left for the LEAF sub-phase before any queue could overflow)
         bool wide = false;
@@ -179,12 +239,12 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     const bool nearest = inner[k] && !taken && tk[k] == tmin;
                     if (nearest) { next = (int)c[k].w; taken = true; }
                     else if (inner[k]) {
-                        if (sp < SSTK) stk[sp * 32] = (int)c[k].w;
-                        else if (sp < STACK) stack_spill[sp - SSTK] = (int)c[k].w;
+                        if (sp < SS) stk[sp * 32] = (int)c[k].w;
+                        else if (sp < STACK) stack_spill[sp - SS] = (int)c[k].w;
                         if (sp < STACK) ++sp;
                     }
                 }
-                if (next == CUR_NONE && sp > 0) { --sp; next = sp < SSTK ? stk[sp * 32] : stack_spill[sp - SSTK]; }
+                if (next == CUR_NONE && sp > 0) { --sp; next = sp < SS ? stk[sp * 32] : stack_spill[sp - SS]; }
                 cur = next;
             }
             walking = __ballot_sync(FULL, phase == PH_TRAV && cur != CUR_NONE);
@@ -629,10 +689,31 @@ int64_t stride_multiplier(int64_t n_rays) {
 }
 
 int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+    if (a.n_rays >= ((int64_t)1 << 31)) { set_error("a forward call traces fewer than 2^31 rays: split the batch"); return 1; }
     const int slot = slot_for(h, s);
     if (slot < 0) return 1;
     KParams p;
-    p.a = a; p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + slot; p.stats = h->stats;
+    p.a = a;
+    // Generated rays (incident / camera): by default a small kernel writes them into a scratch block of this stream slot first
+    // and the forward kernel reads them like any other rays.  Measured on 2^24 C3 rays, same box: rays from memory 20.96 ms,
+    // generated inside the persistent kernel (ray queue, full lanes) 22.5 ms, generated at the refill 23.1 ms -- DRAM is 4 % busy,
+    // the 24 B per ray are free, while every instruction and register inside the latency- and issue-bound walk is not.  The
+    // caller-visible contract is unchanged (no ray arrays in, 28 B per point); irgs_set_option("gen_in_kernel", 1) keeps the
+    // in-kernel generation (no scratch: 24 B per ray of a call less memory).
+    if ((a.gen_pos != nullptr || a.cam_W > 0) && !h->gen_in_kernel) {
+        if (a.n_rays > h->ray_scratch_cap[slot]) {
+            IRGS_CHECK(cudaStreamSynchronize(s));
+            if (h->ray_scratch[slot]) cudaFree(h->ray_scratch[slot]);
+            h->ray_scratch[slot] = nullptr;
+            IRGS_CHECK(cudaMalloc(&h->ray_scratch[slot], sizeof(float) * 6 * (size_t)a.n_rays));
+            h->ray_scratch_cap[slot] = a.n_rays;
+        }
+        float *so = h->ray_scratch[slot], *sd = so + 3 * (size_t)a.n_rays;
+        if (launch_generated_rays(a, so, sd, s)) return 1;
+        p.a.rays_o = so; p.a.rays_d = sd;
+        p.a.gen_pos = nullptr; p.a.cam_W = 0;
+    }
+    p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + slot; p.stats = h->stats;
     const bool feat = a.S > 0, stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 8 * sizeof(unsigned long long), s));
     // (generated rays -- a.gen_pos -- have no ray arrays to take sort keys from and arrive grouped per shading point anyway)
@@ -658,10 +739,17 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     IRGS_CHECK(cudaMemsetAsync(a.alpha, 0, sizeof(float) * R, s));
     if (a.S > 0) IRGS_CHECK(cudaMemsetAsync(a.feature, 0, sizeof(float) * (size_t)a.S * R, s));
     if (a.hit_count) IRGS_CHECK(cudaMemsetAsync(a.hit_count, 0, sizeof(int32_t) * R, s));
-    if (feat) return stats ? launch_fwd(h, slot, trace_forward_kernel<true, true>, p, a.n_rays, s)
-                           : launch_fwd(h, slot, trace_forward_kernel<true, false>, p, a.n_rays, s);
-    return stats ? launch_fwd(h, slot, trace_forward_kernel<false, true>, p, a.n_rays, s)
-                 : launch_fwd(h, slot, trace_forward_kernel<false, false>, p, a.n_rays, s);
+    const bool gen = p.a.gen_pos != nullptr || p.a.cam_W > 0;   // generated inside the forward kernel: the per-warp ray queue
+    if (gen) {
+        if (feat) return stats ? launch_fwd(h, slot, trace_forward_kernel<true, true, true>, p, a.n_rays, s)
+                               : launch_fwd(h, slot, trace_forward_kernel<true, false, true>, p, a.n_rays, s);
+        return stats ? launch_fwd(h, slot, trace_forward_kernel<false, true, true>, p, a.n_rays, s)
+                     : launch_fwd(h, slot, trace_forward_kernel<false, false, true>, p, a.n_rays, s);
+    }
+    if (feat) return stats ? launch_fwd(h, slot, trace_forward_kernel<true, true, false>, p, a.n_rays, s)
+                           : launch_fwd(h, slot, trace_forward_kernel<true, false, false>, p, a.n_rays, s);
+    return stats ? launch_fwd(h, slot, trace_forward_kernel<false, true, false>, p, a.n_rays, s)
+                 : launch_fwd(h, slot, trace_forward_kernel<false, false, false>, p, a.n_rays, s);
 }
 
 }  // namespace irgs

@@ -180,3 +180,26 @@ def test_incident_host_entry_matches_the_device_path(small_scene):
     got = tr._unpack(fused, gfeat, tuple(g["opacity"].shape), 16)
     for k, t in zip(keys, got):
         assert (t - leaf[k].grad).abs().max() <= 2e-4 * (leaf[k].grad.abs().max() + 1e-30), k
+
+
+def test_generation_in_kernel_and_through_the_scratch_block_agree(small_scene):
+    """The two ways a forward call can produce generated rays -- a small kernel writing them to the tracer's scratch block (the
+    default) or the forward kernel's own ray queue (`gen_in_kernel`) -- run the same device function: bit-identical results, for
+    incident and for camera rays."""
+    from irgs_b200.primary import Camera, trace_camera
+    sc, inp = small_scene
+    tr, g = _tracer(inp)
+    pos, nrm, azim = _points(inp, n=90, seed=2)
+    args = (g["means3D"], g["opacity"], g["ru"], g["rv"], g["normals"], g["features"], g["shs"], synth.ALPHA_MIN)
+    cam = Camera.look_at(synth.CAMERA_CENTER, (0.0, 0.0, 0.0), (0.0, 0.0, -1.0), 0.7, 61, 47)
+    res = []
+    for mode in (0, 1):
+        tr.set_option("gen_in_kernel", mode)
+        with torch.no_grad():
+            a = tr.trace_incident(pos.to(DEV), nrm.to(DEV), 48, *args, azimuth=azim.to(DEV), t_min=0.05)
+            b = trace_camera(tr, cam, *args)
+        res.append(list(a) + list(b) + [tr.last_hit_count.clone()])
+    tr.set_option("gen_in_kernel", 0)
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
+    assert bool(res[0][4].any()) and bool(res[0][9].any())

@@ -74,9 +74,9 @@ constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
-template <bool FEAT>
+template <int NF>   // feature channels the variant is built for: 0, 4 (base colour + roughness: relight, primary pass) or 12
 struct WarpSmem {
-    float scratch[(8 + (FEAT ? NFMAX : 0)) * 32];   // co-operative sort (4 x 32) / accumulation scratch (one row per output channel)
+    float scratch[(8 + NF) * 32];   // co-operative sort (4 x 32) / accumulation scratch (one row per output channel)
     int pend[PQ * 32];        // pending leaves [entry][lane]
     int stack[SSTK * 32];     // traversal stack [entry][lane]
     // per-segment table of the packed COMP phase
@@ -100,14 +100,15 @@ __device__ __forceinline__ void fill_ray_queue(const TraceArgs &a, int64_t qr, f
     rq[6 * 32 + lane] = __int_as_float((int)qr);
 }
 
-template <bool FEAT, bool STATS, bool GEN>
+template <int NF, bool STATS, bool GEN>
 __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(const KParams p, uint4 *__restrict__ cand_base) {
     constexpr int SS = GEN ? SSTK - RQ_WORDS : SSTK;   // traversal stack entries in shared memory
-    __shared__ WarpSmem<FEAT> smem[TB / 32];
+    constexpr bool FEAT = NF > 0;
+    __shared__ WarpSmem<NF> smem[TB / 32];
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
-    WarpSmem<FEAT> &ws = smem[tid >> 5];
+    WarpSmem<NF> &ws = smem[tid >> 5];
     int *stk = ws.stack + lane;
     int *pend = ws.pend + lane;
     int stack_spill[STACK - SS];
@@ -548,9 +549,9 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const int total_o = __shfl_sync(FULL, total, owner);
             // shade one hit per lane
             float c0 = 0.f, c1 = 0.f, c2c = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dd = 0.f, oo = 0.f;
-            float f[FEAT ? NFMAX : 1];
+            float f[FEAT ? NF : 1];
 #pragma unroll
-            for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) f[j] = 0.f;
+            for (int j = 0; j < (FEAT ? NF : 1); ++j) f[j] = 0.f;
             const bool mine = act && k < n_comp;
             if (mine) {
                 float Y[16];
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 dd = my_w * my_t; oo = my_w;
                 if (FEAT) {
 #pragma unroll
-                    for (int j = 0; j < NFMAX; ++j)
+                    for (int j = 0; j < NF; ++j)
                         if (j < a.S) f[j] = my_w * __ldg(a.features + (size_t)my_g * a.S + j);
                 }
                 if (a.hits != nullptr && total_o + k < a.hit_cap) a.hits[ray_o * a.hit_cap + total_o + k] = my_g;
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 s_c[6 * 32 + lane] = dd; s_c[7 * 32 + lane] = oo;
                 if (FEAT) {
 #pragma unroll
-                    for (int j = 0; j < NFMAX; ++j)
+                    for (int j = 0; j < NF; ++j)
                         if (j < a.S) s_c[(8 + j) * 32 + lane] = f[j];
                 }
                 // per-segment table, written by the first lane of each segment
@@ -714,7 +715,7 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
         p.a.gen_pos = nullptr; p.a.cam_W = 0;
     }
     p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + slot; p.stats = h->stats;
-    const bool feat = a.S > 0, stats = h->stats_enabled != 0;
+    const bool stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 8 * sizeof(unsigned long long), s));
     // (generated rays -- a.gen_pos -- have no ray arrays to take sort keys from and arrive grouped per shading point anyway)
     if (h->sort_rays_min > 0 && a.n_rays >= h->sort_rays_min && a.n_rays < ((int64_t)1 << 31) && a.gen_pos == nullptr &&
@@ -740,16 +741,16 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     if (a.S > 0) IRGS_CHECK(cudaMemsetAsync(a.feature, 0, sizeof(float) * (size_t)a.S * R, s));
     if (a.hit_count) IRGS_CHECK(cudaMemsetAsync(a.hit_count, 0, sizeof(int32_t) * R, s));
     const bool gen = p.a.gen_pos != nullptr || p.a.cam_W > 0;   // generated inside the forward kernel: the per-warp ray queue
-    if (gen) {
-        if (feat) return stats ? launch_fwd(h, slot, trace_forward_kernel<true, true, true>, p, a.n_rays, s)
-                               : launch_fwd(h, slot, trace_forward_kernel<true, false, true>, p, a.n_rays, s);
-        return stats ? launch_fwd(h, slot, trace_forward_kernel<false, true, true>, p, a.n_rays, s)
-                     : launch_fwd(h, slot, trace_forward_kernel<false, false, true>, p, a.n_rays, s);
-    }
-    if (feat) return stats ? launch_fwd(h, slot, trace_forward_kernel<true, true, false>, p, a.n_rays, s)
-                           : launch_fwd(h, slot, trace_forward_kernel<true, false, false>, p, a.n_rays, s);
-    return stats ? launch_fwd(h, slot, trace_forward_kernel<false, true, false>, p, a.n_rays, s)
-                 : launch_fwd(h, slot, trace_forward_kernel<false, false, false>, p, a.n_rays, s);
+    // kernel variant: feature channels 0 / <= 4 / <= 12 (shared-memory scratch and registers are sized by it), statistics, ray queue
+#define IRGS_FWD_CASE(NF_, ST_, GEN_) \
+    if (nf == NF_ && stats == ST_ && gen == GEN_) return launch_fwd(h, slot, trace_forward_kernel<NF_, ST_, GEN_>, p, a.n_rays, s);
+    const int nf = a.S == 0 ? 0 : (a.S <= 4 ? 4 : NFMAX);
+    IRGS_FWD_CASE(0, false, false) IRGS_FWD_CASE(0, false, true) IRGS_FWD_CASE(0, true, false) IRGS_FWD_CASE(0, true, true)
+    IRGS_FWD_CASE(4, false, false) IRGS_FWD_CASE(4, false, true) IRGS_FWD_CASE(4, true, false) IRGS_FWD_CASE(4, true, true)
+    IRGS_FWD_CASE(NFMAX, false, false) IRGS_FWD_CASE(NFMAX, false, true) IRGS_FWD_CASE(NFMAX, true, false) IRGS_FWD_CASE(NFMAX, true, true)
+#undef IRGS_FWD_CASE
+    set_error("no forward kernel variant");
+    return 1;
 }
 
 }  // namespace irgs

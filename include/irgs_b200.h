@@ -6,9 +6,12 @@
  * (/root/reference/submodules/surfel_tracer/src/bindings.cu:24-116) or of the `TriangleBvh` it forwards to
  * (src/bvh.cu:163-252).  Plain pointers and sizes only; no torch types.  All `const float*` / `float*` arguments
  * are DEVICE pointers to contiguous row-major float32 arrays unless the name ends in `_host`; `stream` is a
- * `cudaStream_t` passed as `void*` (0 = legacy default stream).  Every call is asynchronous with respect to the
- * host and ordered on `stream`, exactly like the reference, which launches on at::cuda::getCurrentCUDAStream()
- * (bindings.cu:32,38,49,66,82).
+ * `cudaStream_t` passed as `void*` (0 = legacy default stream).  Trace, refit and unpack calls are asynchronous with respect to
+ * the host and ordered on `stream`, exactly like the reference, which launches on at::cuda::getCurrentCUDAStream()
+ * (bindings.cu:32,38,49,66,82).  Exceptions, all outside the per-iteration path: a BUILD (irgs_build_*) synchronises `stream`
+ * once per clustering iteration (the host sizes the next grid from the cluster count, ~55 times at 300k surfels), the `_host`
+ * entry points return when their host outputs are complete, and the first call that needs a larger scratch block on a stream
+ * synchronises that stream to reallocate it.
  *
  * Error convention: 0 = success; non-zero = failure, irgs_last_error() returns a thread-local message.  The
  * reference throws std::runtime_error through pybind (gpu_memory.h:50-55); the Python layer maps a non-zero status

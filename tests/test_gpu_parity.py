@@ -962,3 +962,27 @@ def test_parameter_level_trace_is_kernels_only_and_matches_the_torch_glue(small_
                    and "copy" not in k.lower()]
         assert not foreign, foreign
         assert any("frames_forward_kernel" in k for k in kernels) and any("unpack_params_kernel" in k for k in kernels)
+
+
+def test_grazing_pairs_are_rare_at_full_scene_size():
+    """The one semantic deviation from the reference that the strict golden rays cannot see: ray / surfel pairs with |n.d| < 1e-3
+    are dropped by the hit test (trace_common.cuh leaf_stage1) where the reference evaluates them with its clamped depth
+    (gaussiantrace_forward.cu:61-81).  The statistics build counts them: on 2^20 C3-like secondary rays at 300k surfels fewer
+    than 5e-5 of the composited hits (measured 5.6e-6 on the whole C3 workload, profiles/r02_grazing_pairs.json), i.e. at most
+    one ray in ~50 000 can differ from the reference by one faint grazing hit; the all-ray bounds of the `dense_100k` golden
+    vectors (tests/golden_util.py) include whatever they contribute."""
+    sc = synth.make_scene(300000, device=DEV)
+    inp = synth.derive_tracer_inputs(sc, synth.CAMERA_CENTER)
+    tr = _tracer(inp)
+    gen = torch.Generator().manual_seed(12)
+    idx = torch.randint(0, 300000, (4096,), generator=gen).to(DEV)
+    o, d = synth.secondary_rays(inp["means3D"][idx].cpu() + 0.01 * inp["normals"][idx].cpu(), inp["normals"][idx].cpu(), 256)
+    o, d = o.reshape(-1, 3).to(DEV), d.reshape(-1, 3).to(DEV)
+    tr.set_stats(True)
+    with torch.no_grad():
+        tr.trace(o, d, inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], None, inp["shs"], synth.ALPHA_MIN)
+    nodes, leaves, hits, passes = tr.get_stats()
+    dropped, would_composite = tr.get_info("grazing_pairs"), tr.get_info("grazing_pairs_compositing")
+    tr.set_stats(False)
+    assert hits > 1e6 and 0 <= would_composite <= dropped
+    assert dropped <= 5e-5 * hits, (dropped, hits)

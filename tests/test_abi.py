@@ -57,7 +57,7 @@ def test_sass_has_the_blackwell_instructions_the_design_relies_on():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     lib = build.build()
-    fwd = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4irgs20trace_forward_kernelILb0ELb0EEEvNS_7KParamsEP5uint4", lib],
+    fwd = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4irgs20trace_forward_kernelILi0ELb0ELb0EEEvNS_7KParamsEP5uint4", lib],
                          capture_output=True, text=True).stdout
     assert len(re.findall(r"LDG\.E\S*\.256", fwd)) >= 4, "forward kernel lost its 256-bit loads"
     # L1 policy of the walk: streaming data (records, SH rows) must not allocate in L1, tree nodes evict last

@@ -131,7 +131,7 @@ class _GaussianTrace(torch.autograd.Function):
 class GaussianTracer:
     """raytracer.py:69-122 (see the module docstring for the mapping)."""
 
-    def __init__(self, transmittance_min=0.001, device=None, hit_cap=64):
+    def __init__(self, transmittance_min=0.001, device=None, hit_cap=96):
         if not torch.cuda.is_available():
             raise RuntimeError("irgs_b200.GaussianTracer needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.impl = _Impl(device if device is not None else torch.device("cuda", torch.cuda.current_device()))

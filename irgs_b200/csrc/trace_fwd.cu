@@ -232,17 +232,31 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     inner[k] = hit && ref >= 0;
                     tk[k] = inner[k] ? tn : INFINITY;
                 }
-                const float tmin = fminf(fminf(tk[0], tk[1]), fminf(tk[2], tk[3]));
-                int next = CUR_NONE;
-                bool taken = false;   // exactly one child with the smallest entry distance is walked next
+                // the nearest internal child (the first one among equals) by a select chain ...
+                float tbest = INFINITY;
+                int next = CUR_NONE, kbest = 4;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const bool nearest = inner[k] && !taken && tk[k] == tmin;
-                    if (nearest) { next = (int)c[k].w; taken = true; }
-                    else if (inner[k]) {
-                        if (sp < SS) stk[sp * 32] = (int)c[k].w;
-                        else if (sp < STACK) stack_spill[sp - SS] = (int)c[k].w;
-                        if (sp < STACK) ++sp;
+                    const bool better = tk[k] < tbest;   // tk is finite only for internal children that were hit
+                    tbest = better ? tk[k] : tbest; next = better ? (int)c[k].w : next; kbest = better ? k : kbest;
+                }
+                // ... and the others onto the stack: predicated stores without bound checks while the shared-memory part of the
+                // stack has room for all three (the rule), the two-level push otherwise
+                if (sp + 3 <= SS) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool push = inner[k] && k != kbest;
+                        if (push) stk[sp * 32] = (int)c[k].w;
+                        sp += push ? 1 : 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (inner[k] && k != kbest) {
+                            if (sp < SS) stk[sp * 32] = (int)c[k].w;
+                            else if (sp < STACK) stack_spill[sp - SS] = (int)c[k].w;
+                            if (sp < STACK) ++sp;
+                        }
                     }
                 }
                 if (next == CUR_NONE && sp > 0) { --sp; next = sp < SS ? stk[sp * 32] : stack_spill[sp - SS]; }

@@ -37,7 +37,9 @@ static_assert(sizeof(SurfelRec) == 64, "record must be 64 bytes");
 // Traversal copy of a node: 32 bytes, i.e. TWO 16-byte loads per visit instead of four (ncu: the walk is bound by the
 // L1TEX tag stage -- one lookup per 16-byte request -- not by DRAM or L2 bandwidth).  Child bounds are quantised
 // conservatively (lo rounded down, hi up) to 16 bits per coordinate on a grid spanning the padded root bound:
-//   per child: w0 = lo.x | lo.y << 16,  w1 = lo.z | hi.x << 16,  w2 = hi.y | hi.z << 16,  w3 = child reference
+//   per child: w0 = lo.x | hi.x << 16,  w1 = lo.y | hi.y << 16,  w2 = lo.z | hi.z << 16,  w3 = child reference
+//   (both planes of an axis in one word: the ray walk picks the NEAR and the FAR plane of the axis by the sign of the ray
+//   direction with a per-ray byte-permute selector instead of evaluating both and taking min / max)
 // child reference: >= 0 internal node, < 0 leaf ~pos, IRGS_CHILD_NONE = no child (empty bound).
 // Coordinate q decodes to frame_lo + q * cell; the ray walk folds the decode into one byte-permute (assembling the
 // float 2^23 + q) and one fma per plane.

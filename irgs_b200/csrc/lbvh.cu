@@ -708,7 +708,7 @@ __global__ void quantize_nodes_kernel(const Node *__restrict__ nodes, int n_int,
                 q[3 + k] = quant_hi(b[3 + k], scene[12 + k], scene[15 + k]);
             }
         }
-        out[c] = make_uint4(q[0] | (q[1] << 16), q[2] | (q[3] << 16), q[4] | (q[5] << 16), (unsigned)ref);
+        out[c] = make_uint4(q[0] | (q[3] << 16), q[1] | (q[4] << 16), q[2] | (q[5] << 16), (unsigned)ref);
     }
     qnodes[i].l = out[0];
     qnodes[i].r = out[1];
@@ -731,7 +731,7 @@ __device__ __forceinline__ uint4 quant_child(const float *b, int ref, const floa
         q[k] = quant_lo(b[k], scene[12 + k], scene[15 + k]);
         q[3 + k] = quant_hi(b[3 + k], scene[12 + k], scene[15 + k]);
     }
-    return make_uint4(q[0] | (q[1] << 16), q[2] | (q[3] << 16), q[4] | (q[5] << 16), (unsigned)ref);
+    return make_uint4(q[0] | (q[3] << 16), q[1] | (q[4] << 16), q[2] | (q[5] << 16), (unsigned)ref);
 }
 
 // Bounds part (every build and refit): one thread per even-depth binary node gathers its (up to four) grandchildren.

@@ -174,13 +174,21 @@ __device__ __forceinline__ void ray_setup(RayCtx &r, const float *__restrict__ q
 __device__ __forceinline__ float qlo16(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
 __device__ __forceinline__ float qhi16(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
-// one child of a quantised node: w = (lo.x|lo.y<<16, lo.z|hi.x<<16, hi.y|hi.z<<16, ref)
+// one child of a quantised node: w = (lo.x|hi.x<<16, lo.y|hi.y<<16, lo.z|hi.z<<16, ref).  t grows with the plane code when the
+// slope a = cell / d is positive: the NEAR plane of an axis is its lo code then, its hi code otherwise -- picked by the byte-
+// permute selector (0x7610 = low half, 0x7632 = high half; the far plane's selector is the near one ^ 0x22), so no per-axis
+// min / max is needed: 6 PRMT + 6 FFMA + two 3-input min / max chains per child.
 __device__ __forceinline__ bool slab(const RayCtx &r, const uint4 w, float t_lo, float t_hi, float &tn) {
-    const float x0 = __fmaf_rn(qlo16(w.x), r.ax, r.bx), x1 = __fmaf_rn(qhi16(w.y), r.ax, r.bx);
-    const float y0 = __fmaf_rn(qhi16(w.x), r.ay, r.by), y1 = __fmaf_rn(qlo16(w.z), r.ay, r.by);
-    const float z0 = __fmaf_rn(qlo16(w.y), r.az, r.bz), z1 = __fmaf_rn(qhi16(w.z), r.az, r.bz);
-    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
-    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+    const unsigned nx = 0x7610u + (__float_as_uint(r.ax) >> 31) * 0x22u, ny = 0x7610u + (__float_as_uint(r.ay) >> 31) * 0x22u,
+                   nz = 0x7610u + (__float_as_uint(r.az) >> 31) * 0x22u;
+    const float x0 = __fmaf_rn(__uint_as_float(__byte_perm(w.x, 0x4B000000u, nx)), r.ax, r.bx);
+    const float x1 = __fmaf_rn(__uint_as_float(__byte_perm(w.x, 0x4B000000u, nx ^ 0x22u)), r.ax, r.bx);
+    const float y0 = __fmaf_rn(__uint_as_float(__byte_perm(w.y, 0x4B000000u, ny)), r.ay, r.by);
+    const float y1 = __fmaf_rn(__uint_as_float(__byte_perm(w.y, 0x4B000000u, ny ^ 0x22u)), r.ay, r.by);
+    const float z0 = __fmaf_rn(__uint_as_float(__byte_perm(w.z, 0x4B000000u, nz)), r.az, r.bz);
+    const float z1 = __fmaf_rn(__uint_as_float(__byte_perm(w.z, 0x4B000000u, nz ^ 0x22u)), r.az, r.bz);
+    tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, t_lo));
+    const float tf = fminf(fminf(x1, y1), fminf(z1, t_hi));
     return (int)w.w != IRGS_CHILD_NONE && tn <= tf;
 }
 

@@ -433,11 +433,13 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
             const uint4 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
             float my_t = __uint_as_float(e.x), my_a = __uint_as_float(e.z); int my_g = (int)e.y, my_p = (int)e.w;
+            // (depths are positive and surfel ids non-negative: the (t, id) order is the order of the packed 64-bit keys)
+            const unsigned long long my_key = ((unsigned long long)__float_as_uint(my_t) << 32) | (unsigned)my_g;
             int rank = 0;
             for (int j = 0; j < KB; ++j) {
-                const float tj = __shfl_sync(FULL, my_t, j);
-                const int gj = __shfl_sync(FULL, my_g, j);
-                rank += key_less(tj, gj, my_t, my_g) ? 1 : 0;
+                const unsigned tj = __shfl_sync(FULL, __float_as_uint(my_t), j);
+                const unsigned gj = __shfl_sync(FULL, (unsigned)my_g, j);
+                rank += ((((unsigned long long)tj << 32) | gj) < my_key) ? 1 : 0;
             }
             {
                 float *s_f = ws.scratch;
@@ -530,12 +532,13 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 const uint4 e = __ldcg(&warp_cand[(size_t)owner * KB + k]);
                 my_t = __uint_as_float(e.x); my_g = (int)e.y; my_a = __uint_as_float(e.z); my_p = (int)e.w;
             }
+            const unsigned long long my_key = ((unsigned long long)__float_as_uint(my_t) << 32) | (unsigned)my_g;
             int rank = 0;
             for (int j = 0; j < maxn; ++j) {
                 const int src = (seg_lo + j) & 31;
-                const float tj = __shfl_sync(FULL, my_t, src);
-                const int gj = __shfl_sync(FULL, my_g, src);
-                rank += (j < n_o && key_less(tj, gj, my_t, my_g)) ? 1 : 0;
+                const unsigned tj = __shfl_sync(FULL, __float_as_uint(my_t), src);
+                const unsigned gj = __shfl_sync(FULL, (unsigned)my_g, src);
+                rank += (j < n_o && (((unsigned long long)tj << 32) | gj) < my_key) ? 1 : 0;
             }
             {
                 float *s_f = ws.scratch;

@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--e2e-chunk", type=int, default=0, help="rays per chunk of the host-buffer path (0: chosen from the shard size)")
     p.add_argument("--no-fused", action="store_true", help="skip the fused ray-generation measurement (SURVEY 8f rank 1)")
     p.add_argument("--no-shade", action="store_true", help="skip the rendering-equation measurement (fused generation + shading epilogue)")
+    p.add_argument("--calls", type=int, default=0, help="experiments: trace calls per rank and step (0: at least four, at most 2^24 rays each)")
     p.add_argument("--shard-block", type=int, default=32, help="pixel bundles are dealt to the ranks in blocks of this many consecutive pixels")
     p.add_argument("--no-other", action="store_true", help="skip the other BASELINE.json configurations (C2, C4, C5) and the small-call timings")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -467,7 +468,7 @@ def run_ours(args):
     # rays per trace call: large calls amortise the drain of the persistent kernels; at least ~4 calls per rank so that the
     # two streams have something to overlap
     # EQUAL calls (a short last call would pay a whole drain for a fraction of the rays), whole pixel bundles per call
-    n_calls = max(4, -(-n_local // args.chunk))
+    n_calls = args.calls if args.calls > 0 else max(4, -(-n_local // args.chunk))
     chunk = min(n_local, -(-(n_local // args.spp) // n_calls) * args.spp)
     gout = make_gout(chunk, device)
     leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}

@@ -315,6 +315,9 @@ int irgs_normalize_outputs_backward(int64_t n_rays, int S, float threshold, cons
  * candidate scratch) looked up from the call's own `stream`, so a backward uses the slot of the stream it runs on ("slot" is
  * still accepted and ignored).  A handle is not thread-safe beyond that: do not build / refit while traces are in flight.
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
+ * "skip_next_pack": 1 makes the next irgs_trace_backward* call on this handle reuse the packed surfel records instead of packing
+ * them again -- valid when irgs_get_info("pack_epoch") still has the value it had right after the forward of the same arrays
+ * (every pack, build and refit bumps it); the Python layer does exactly that.
  * "gen_in_kernel": 0 (default) incident / camera rays of a forward call are written to an internal scratch block by a small
  * kernel and read back by the forward kernel (measured faster: DRAM is idle, the persistent walk is not), 1 generates them
  * inside the forward kernel (24 B per ray of a call less memory).  The backward always regenerates them in its kernels.
@@ -326,7 +329,8 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 int64_t irgs_stride_multiplier(int64_t n_rays);
 
 /* Introspection (tests, diagnostics): "tree_depth" (levels of the PLOC tree of the last build; 0 = Karras tree), "ploc_iterations",
- * "n_slots" (streams seen so far), "n_surfels".  -1 for unknown names. */
+ * "n_slots" (streams seen so far), "n_surfels", "pack_epoch", "grazing_pairs" / "grazing_pairs_compositing" (statistics build).
+ * -1 for unknown names. */
 int64_t irgs_get_info(irgs_tracer_t *h, const char *name);
 
 /* Traversal statistics of the last irgs_trace_forward on this handle when statistics were enabled with

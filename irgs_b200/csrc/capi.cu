@@ -332,8 +332,11 @@ static int trace_backward_impl(irgs_tracer_t *h, const irgs_incident_t *gen, int
     }
     a.gC = gout_color; a.gN = gout_normal; a.gF = gout_feature; a.gD = gout_depth; a.gO = gout_alpha;
     a.g_rays_o = grad_rays_o; a.g_rays_d = grad_rays_d; a.grad_fused = grad_fused; a.grad_features = grad_features;
-    // the records must be consistent with the arrays handed to this call
-    if (launch_pack_records(h, a, s) || launch_incident_prepare(h, a, s)) return 1;
+    // the records must be consistent with the arrays handed to this call: packed again unless the caller vouches that nothing
+    // has packed or rebuilt since the forward of these very arrays (irgs_set_option("skip_next_pack"), see "pack_epoch")
+    const bool skip = h->skip_next_pack != 0;
+    h->skip_next_pack = 0;
+    if ((!skip && launch_pack_records(h, a, s)) || launch_incident_prepare(h, a, s)) return 1;
     return launch_trace_backward(h, a, s);
 }
 
@@ -671,6 +674,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->builder = value == 1 ? 1 : 0;
         return 0;
     }
+    if (strcmp(name, "skip_next_pack") == 0) {
+        h->skip_next_pack = value ? 1 : 0;
+        return 0;
+    }
     if (strcmp(name, "gen_in_kernel") == 0) {
         h->gen_in_kernel = value ? 1 : 0;
         return 0;
@@ -688,6 +695,7 @@ int64_t irgs_get_info(irgs_tracer_t *h, const char *name) {
     if (strcmp(name, "ploc_iterations") == 0) return h->ploc_iterations;
     if (strcmp(name, "n_slots") == 0) return h->n_slots;
     if (strcmp(name, "n_surfels") == 0) return h->built ? h->n : 0;
+    if (strcmp(name, "pack_epoch") == 0) return h->pack_epoch;
     if (strcmp(name, "grazing_pairs") == 0 || strcmp(name, "grazing_pairs_compositing") == 0) {
         // statistics of the last forward with irgs_set_stats(h, 1): ray / surfel pairs with |n.d| < 1e-3 that cross the surfel's
         // support geometrically (dropped by the hit test; the reference evaluates them with its clamped depth), and how many of

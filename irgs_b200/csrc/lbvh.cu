@@ -808,6 +808,7 @@ int launch_bounds_from_surfels(irgs_tracer *h, const float *means, const float *
 }
 
 int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
+    ++h->pack_epoch;   // a build changes the leaf order the records are packed in
     const int n = (int)h->n;
     int *scene_i = reinterpret_cast<int *>(h->scene);
     if (!refit_only) {

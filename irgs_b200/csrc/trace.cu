@@ -876,6 +876,7 @@ static KParams make_params(irgs_tracer *h, const TraceArgs &a, int slot) {
 }
 
 int launch_pack_records(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+    ++h->pack_epoch;
     const int n = (int)h->n;
     pack_records_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->order, n, a.means, a.opacity, a.ru, a.rv, a.normals, a.alpha_min, h->recs,
                                                          h->inv_order);

@@ -38,6 +38,19 @@ def _check_f32(name, t, device):
         raise ValueError(f"{name} is on {t.device}, the tracer's acceleration structure is on {device}")
 
 
+def _alloc_outputs(B, S, dev):
+    """The five outputs and the hit counts of a trace call as views of ONE allocation, back to back in the order the native
+    forward zero-fills with a single memset (color, normal, feature, depth, alpha, hit_count)."""
+    buf = torch.empty(B * (9 + S), device=dev, dtype=torch.float32)
+    o = 0
+    views = []
+    for width in (3, 3, S, 1, 1, 1):
+        views.append(buf[o:o + B * width])
+        o += B * width
+    color, normal, feature, depth, alpha, count = views
+    return (color.view(B, 3), normal.view(B, 3), feature.view(B, S), depth, alpha, count.view(torch.int32))
+
+
 class _Impl:
     """Owns the native handle (the reference's `_C.create_gaussiantracer()` object, bindings.cu:101-103)."""
 
@@ -72,12 +85,7 @@ class _GaussianTrace(torch.autograd.Function):
         B = rays_o.shape[0]
         S = features.shape[-1]
         K = shs.shape[1]
-        color = torch.empty(B, 3, device=dev, dtype=torch.float32)
-        normal = torch.empty(B, 3, device=dev, dtype=torch.float32)
-        feature = torch.empty(B, S, device=dev, dtype=torch.float32)
-        depth = torch.empty(B, device=dev, dtype=torch.float32)
-        alpha = torch.empty(B, device=dev, dtype=torch.float32)
-        hit_count = torch.empty(B, device=dev, dtype=torch.int32)
+        color, normal, feature, depth, alpha, hit_count = _alloc_outputs(B, S, dev)
         need_grad = any(ctx.needs_input_grad)
         cap = tracer.hit_cap if need_grad else 0
         hits = torch.empty(B, cap, device=dev, dtype=torch.int32) if cap > 0 else None
@@ -88,6 +96,7 @@ class _GaussianTrace(torch.autograd.Function):
             _stream(dev)))
         tracer.last_hit_count = hit_count
         ctx.tracer = tracer
+        ctx.pack_epoch = impl.lib.irgs_get_info(impl.h, b"pack_epoch") if need_grad else -1
         ctx.alpha_min, ctx.deg, ctx.back_culling, ctx.cap = alpha_min, deg, back_culling, cap
         ctx.transmittance_min = tracer.transmittance_min
         ctx.save_for_backward(rays_o, rays_d, means3D, opacity, ru, rv, normals, features, shs, color, normal,
@@ -114,6 +123,10 @@ class _GaussianTrace(torch.autograd.Function):
             fused = torch.zeros(N, GRAD_STRIDE, device=dev, dtype=torch.float32)
             gfeat = torch.zeros(N, S, device=dev, dtype=torch.float32)
         have_list = ctx.cap > 0
+        if impl.lib.irgs_get_info(impl.h, b"pack_epoch") == ctx.pack_epoch:
+            # nothing has packed or rebuilt since this node's forward (autograd itself guarantees that the saved arrays are
+            # unmodified): the records are still the ones of these arrays
+            impl.lib.irgs_set_option(impl.h, b"skip_next_pack", 1)
         _lib.check(impl.lib.irgs_trace_backward(
             impl.h, B, S, K, ctx.deg, _ptr(rays_o), _ptr(rays_d), _ptr(means3D), _ptr(opacity), _ptr(ru), _ptr(rv),
             _ptr(normals), _ptr(features), _ptr(shs), _ptr(color), _ptr(normal), _ptr(feature), _ptr(depth),

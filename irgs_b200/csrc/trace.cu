@@ -398,10 +398,11 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         float feat[FEAT ? NFMAX : 1], Ff[FEAT ? NFMAX : 1], gF[FEAT ? NFMAX : 1];
 #pragma unroll
         for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) { feat[j] = 0.f; Ff[j] = 0.f; gF[j] = 0.f; }
-        float Y[16];
         int g = 0;
         if (act) {
             g = g_cur;
+            float Y[16];   // (only for the colour here: the SH gradient row re-derives the basis when it is written, so that sixteen
+                           //  registers are not held across the segmented scans in between)
             sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
             // the surfel's packed record (re-packed from the saved inputs before this launch): two 32-byte loads
             float4 q0, q1, q2, q3;
@@ -433,9 +434,6 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
                         gF[j] = __ldg(a.gF + o_gr * a.S + j);
                     }
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) Y[j] = 0.f;
         }
         const float nf[3] = {m * nx, m * ny, m * nz};
 
@@ -524,6 +522,8 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
                 row[2] = make_float4(dpv * py, dpv * pz, dnx, dny);
                 row[3] = make_float4(dnz, 0.f, 0.f, 0.f);
                 const float gc[3] = {gO[0] * w, gO[1] * w, gO[2] * w};
+                float Y[16];
+                sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
 #pragma unroll
                 for (int v = 0; v < 12; ++v) {
                     float4 q;

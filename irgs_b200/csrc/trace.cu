@@ -289,10 +289,12 @@ constexpr int BROW = 68;   // floats per shared-memory row: 64 gradient floats +
 template <bool FEAT, bool BULK>
 __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kernel(const KParams p) {
     __shared__ __align__(16) float s_rows[TB / 32][32 * BROW];
+    __shared__ float s_ray[TB / 32][22 * 32];   // per ray of the warp: origin, direction, final outputs, incoming gradients [field][lane]
     const TraceArgs &a = p.a;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     float *rows = s_rows[threadIdx.x >> 5];
+    float *rayv = s_ray[threadIdx.x >> 5];
     // (one 32-ray group per warp, one launch wave after the other: a grid-stride loop over the groups with a resident-sized grid
     // measured 2.44 instead of 1.84 ms per 2^22 rays -- the hardware's dynamic block scheduling balances the very uneven groups)
     const int64_t ray0 = ((int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * 32;
@@ -319,6 +321,13 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         fin[6] = a.depth[my_ray]; fin[7] = a.alpha[my_ray];
         gout[6] = __ldg(a.gD + gr); gout[7] = __ldg(a.gO + gr);
     }
+    // The hits of a round reach their ray's data through shared memory ([field][owner]: conflict-free for any mix of owners)
+    // instead of 22 shuffles out of 22 registers that would stay live through the whole kernel (128 registers, 18 % warps active).
+    rayv[0 * 32 + lane] = r.ox; rayv[1 * 32 + lane] = r.oy; rayv[2 * 32 + lane] = r.oz;
+    rayv[3 * 32 + lane] = r.dx; rayv[4 * 32 + lane] = r.dy; rayv[5 * 32 + lane] = r.dz;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { rayv[(6 + j) * 32 + lane] = fin[j]; rayv[(14 + j) * 32 + lane] = gout[j]; }
+    __syncwarp();
     const int c_eff = has ? cnt : 0;
     int incl = c_eff;
 #pragma unroll
@@ -379,11 +388,11 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         const int k = k_loc;
         const int64_t ray = ray0 + owner;
         RayCtx ro;
-        ro.ox = __shfl_sync(FULL, r.ox, owner); ro.oy = __shfl_sync(FULL, r.oy, owner); ro.oz = __shfl_sync(FULL, r.oz, owner);
-        ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);
+        ro.ox = rayv[0 * 32 + owner]; ro.oy = rayv[1 * 32 + owner]; ro.oz = rayv[2 * 32 + owner];
+        ro.dx = rayv[3 * 32 + owner]; ro.dy = rayv[4 * 32 + owner]; ro.dz = rayv[5 * 32 + owner];
         float F[8], gO[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { F[j] = __shfl_sync(FULL, fin[j], owner); gO[j] = __shfl_sync(FULL, gout[j], owner); }
+        for (int j = 0; j < 8; ++j) { F[j] = rayv[(6 + j) * 32 + owner]; gO[j] = rayv[(14 + j) * 32 + owner]; }
         const int64_t o_gr = __shfl_sync(FULL, gr, owner);
         // segment of this lane's ray inside the round
         const int first = act ? lane - k : lane, last = act ? lane + (n_o - 1 - k) : lane;

@@ -315,6 +315,9 @@ int irgs_normalize_outputs_backward(int64_t n_rays, int S, float threshold, cons
  * candidate scratch) looked up from the call's own `stream`, so a backward uses the slot of the stream it runs on ("slot" is
  * still accepted and ignored).  A handle is not thread-safe beyond that: do not build / refit while traces are in flight.
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
+ * "contiguous_outputs": 1 = the caller promises that whenever a forward call's output arrays are back to back in memory (color,
+ * normal, feature, depth, alpha, hit_count) they are views of ONE allocation; they are then zero-filled with a single memset
+ * instead of six (default 0: arrays that merely happen to be adjacent may belong to different allocations).
  * "skip_next_pack": 1 makes the next irgs_trace_backward* call on this handle reuse the packed surfel records instead of packing
  * them again -- valid when irgs_get_info("pack_epoch") still has the value it had right after the forward of the same arrays
  * (every pack, build and refit bumps it); the Python layer does exactly that.

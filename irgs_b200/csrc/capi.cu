@@ -674,6 +674,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->builder = value == 1 ? 1 : 0;
         return 0;
     }
+    if (strcmp(name, "contiguous_outputs") == 0) {
+        h->contiguous_outputs = value ? 1 : 0;
+        return 0;
+    }
     if (strcmp(name, "skip_next_pack") == 0) {
         h->skip_next_pack = value ? 1 : 0;
         return 0;

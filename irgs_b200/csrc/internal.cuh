@@ -106,6 +106,7 @@ struct irgs_tracer {
     float *ray_scratch[MAX_SLOTS] = {};     // generated rays of a forward call, materialised per stream slot (o[3n] d[3n])
     int64_t ray_scratch_cap[MAX_SLOTS] = {};
     long long pack_epoch = 0;               // bumped by every pack of the records and by every build / refit
+    int contiguous_outputs = 0;             // the caller allocates a call's outputs as ONE block whenever they are back to back
     int skip_next_pack = 0;                 // the next irgs_trace_backward* reuses the records as they are (irgs_set_option)
     int gen_in_kernel = 0;                  // 1: generate incident / camera rays inside the forward kernel instead
     void *inc_pts[MAX_SLOTS] = {};          // per-point records of generated incident rays (IncPoint[inc_cap]), per stream slot

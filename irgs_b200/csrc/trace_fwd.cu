@@ -756,7 +756,9 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     {
         char *p0 = reinterpret_cast<char *>(a.color);
         const size_t o_n = 12 * R, o_f = 24 * R, o_d = o_f + 4 * (size_t)a.S * R, o_a = o_d + 4 * R, o_h = o_a + 4 * R;
-        const bool contiguous = reinterpret_cast<char *>(a.normal) == p0 + o_n && (a.S == 0 || reinterpret_cast<char *>(a.feature) == p0 + o_f) &&
+        // (only on the caller's word -- irgs_set_option("contiguous_outputs", 1): arrays that merely HAPPEN to be adjacent may belong
+        // to different allocations, which one memset must not span)
+        const bool contiguous = h->contiguous_outputs && reinterpret_cast<char *>(a.normal) == p0 + o_n && (a.S == 0 || reinterpret_cast<char *>(a.feature) == p0 + o_f) &&
                                 reinterpret_cast<char *>(a.depth) == p0 + o_d && reinterpret_cast<char *>(a.alpha) == p0 + o_a &&
                                 (a.hit_count == nullptr || reinterpret_cast<char *>(a.hit_count) == p0 + o_h);
         if (contiguous) {

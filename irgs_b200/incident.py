@@ -18,7 +18,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .raytracer import GRAD_STRIDE, _ptr, _stream
+from .raytracer import GRAD_STRIDE, _alloc_outputs, _ptr, _stream
 
 
 class IncidentDesc(ctypes.Structure):
@@ -87,12 +87,7 @@ class _IncidentTrace(torch.autograd.Function):
         impl, dev = tracer.impl, tracer.impl.device
         P = position.shape[0]
         B, S, K = P * sample_num, features.shape[-1], shs.shape[1]
-        color = torch.empty(B, 3, device=dev)
-        normal = torch.empty(B, 3, device=dev)
-        feature = torch.empty(B, S, device=dev)
-        depth = torch.empty(B, device=dev)
-        alpha = torch.empty(B, device=dev)
-        hit_count = torch.empty(B, device=dev, dtype=torch.int32)
+        color, normal, feature, depth, alpha, hit_count = _alloc_outputs(B, S, dev)
         cap = tracer.hit_cap if any(ctx.needs_input_grad) else 0
         hits = torch.empty(B, cap, device=dev, dtype=torch.int32) if cap > 0 else None
         desc = _desc(position, normals_pt, azimuth, sample_num, t_min)

@@ -19,7 +19,7 @@ import math
 import torch
 
 from . import _lib
-from .raytracer import GRAD_STRIDE, _ptr, _stream
+from .raytracer import GRAD_STRIDE, _alloc_outputs, _ptr, _stream
 
 
 class CameraDesc(ctypes.Structure):
@@ -77,9 +77,7 @@ class _CameraTrace(torch.autograd.Function):
     def forward(ctx, tracer, cam, means3D, opacity, ru, rv, normals, features, shs, alpha_min, deg, back_culling):
         impl, dev = tracer.impl, tracer.impl.device
         B, S, K = cam.width * cam.height, features.shape[-1], shs.shape[1]
-        outs = [torch.empty(B, 3, device=dev), torch.empty(B, 3, device=dev), torch.empty(B, S, device=dev),
-                torch.empty(B, device=dev), torch.empty(B, device=dev)]
-        hit_count = torch.empty(B, device=dev, dtype=torch.int32)
+        *outs, hit_count = _alloc_outputs(B, S, dev)
         cap = tracer.hit_cap if any(ctx.needs_input_grad) else 0
         hits = torch.empty(B, cap, device=dev, dtype=torch.int32) if cap > 0 else None
         desc = cam.desc()

@@ -64,6 +64,8 @@ class _Impl:
         self.device = torch.device("cuda", idx)
         _lib.check(self.lib.irgs_tracer_create(ctypes.byref(h), idx))
         self.h = h
+        # every forward of this package allocates its outputs through _alloc_outputs: one block, one memset
+        _lib.check(self.lib.irgs_set_option(h, b"contiguous_outputs", 1))
 
     def __del__(self):
         try:
@@ -297,10 +299,8 @@ class GaussianTracer:
         rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
         B, S, K = rays_o.shape[0], features.shape[-1], shs.shape[1]
         cap = self.hit_cap if hit_cap is None else hit_cap
-        out = dict(color=torch.empty(B, 3, device=dev), normal=torch.empty(B, 3, device=dev),
-                   feature=torch.empty(B, S, device=dev), depth=torch.empty(B, device=dev),
-                   alpha=torch.empty(B, device=dev), hit_count=torch.empty(B, device=dev, dtype=torch.int32),
-                   hits=torch.full((B, cap), -1, device=dev, dtype=torch.int32))
+        out = dict(zip(("color", "normal", "feature", "depth", "alpha", "hit_count"), _alloc_outputs(B, S, dev)))
+        out["hits"] = torch.full((B, cap), -1, device=dev, dtype=torch.int32)
         if B > 0:
             _lib.check(impl.lib.irgs_trace_forward(
                 impl.h, B, S, K, int(deg), _ptr(rays_o), _ptr(rays_d), _ptr(means3D), _ptr(opacity), _ptr(ru), _ptr(rv),

@@ -17,7 +17,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .raytracer import GRAD_STRIDE, GaussianTracer, _check_f32, _ptr, _stream
+from .raytracer import GRAD_STRIDE, GaussianTracer, _alloc_outputs, _check_f32, _ptr, _stream
 
 
 def _cam_ptr(camera_center):
@@ -43,9 +43,7 @@ class _SurfelTrace(torch.autograd.Function):
         ru, rv, normals = (torch.empty(N, 3, device=dev) for _ in range(3))
         st = _stream(dev)
         _lib.check(lib.irgs_surfel_frames(_ptr(means), _ptr(scales), _ptr(rotations), cam, N, _ptr(ru), _ptr(rv), _ptr(normals), st))
-        raw = [torch.empty(B, 3, device=dev), torch.empty(B, 3, device=dev), torch.empty(B, S, device=dev),
-               torch.empty(B, device=dev), torch.empty(B, device=dev)]
-        hit_count = torch.empty(B, device=dev, dtype=torch.int32)
+        *raw, hit_count = _alloc_outputs(B, S, dev)
         cap = tracer.hit_cap if any(ctx.needs_input_grad) else 0
         hits = torch.empty(B, cap, device=dev, dtype=torch.int32) if cap > 0 else None
         _lib.check(lib.irgs_trace_forward(

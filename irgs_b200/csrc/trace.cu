@@ -276,20 +276,39 @@ __global__ void __launch_bounds__(TB) trace_backward_replay_kernel(const KParams
 //     come" terms (C_final - C_i, ...) are segmented exclusive SUFFIX sums of the w * c contributions, which have no
 //     cancellation (the reference subtracts two nearly equal running sums);  a ray whose list straddles two rounds
 //     carries T and the remainders over in registers (lane 31 of one round -> the first segment of the next);
-//   * every lane writes the 64-float gradient row of its hit to shared memory; the warp then adds the rows to the
-//     fused buffer with one 16-byte reduction per lane, sixteen consecutive lanes covering one 256-byte row, i.e. 2
-//     cache lines per hit instead of 16 scattered requests.
+//   * every lane writes the 64-float gradient row of its hit to shared memory; each row is then added to the fused buffer by
+//     one TMA bulk reduction (BULK; 2 cache lines per hit instead of 16 scattered requests), or -- comparison variant -- with
+//     one 16-byte reduction per lane, sixteen consecutive lanes covering one 256-byte row.
 // ncu on the thread-per-ray replay (profiles/r01_bwd_replay_regions.txt): 7.96 of 32 lanes active, L1TEX 85 % busy
 // with the scattered reductions.
-#ifndef IRGS_BWD_BLOCKS
-#define IRGS_BWD_BLOCKS 4
+// Launch shape (round 2, same-box A/B in profiles/r02_sweeps.txt): ONE warp per block.  The warps of a block are independent
+// 32-ray groups of very uneven length (a group's hits range from 0 to > 1000), and a block keeps its registers and shared memory
+// until its slowest warp is done: with four warps per block ncu showed 11.6 warps active per SM of 16 possible.  96 registers
+// (no spills) and 11.4 KB of shared memory per warp give 18 resident warps per SM.
+#ifndef IRGS_BWD_TB
+#define IRGS_BWD_TB 32   // threads per block of the hit-parallel replay (a block's warps are independent 32-ray groups)
 #endif
+#ifndef IRGS_BWD_BLOCKS
+#define IRGS_BWD_BLOCKS 20
+#endif
+constexpr int FTB = IRGS_BWD_TB;
+#ifndef IRGS_BWD_UNIFORM_ISSUE
+#define IRGS_BWD_UNIFORM_ISSUE 1   // 0: per-lane bulk reductions under `if (act)` (comparison builds)
+#endif
+// one lane of the (converged) warp, chosen by the hardware: the compiler knows that code under it runs in a single thread
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 constexpr int BROW = 68;   // floats per shared-memory row: 64 gradient floats + pad, 68 % 32 == 4 (conflict-free float4 stores)
 
 template <bool FEAT, bool BULK>
-__global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kernel(const KParams p) {
-    __shared__ __align__(16) float s_rows[TB / 32][32 * BROW];
-    __shared__ float s_ray[TB / 32][22 * 32];   // per ray of the warp: origin, direction, final outputs, incoming gradients [field][lane]
+__global__ void __launch_bounds__(FTB, IRGS_BWD_BLOCKS) trace_backward_flat_kernel(const KParams p) {
+    __shared__ __align__(16) float s_rows[FTB / 32][32 * BROW];
+    // per ray of the warp: origin, direction, final outputs (C, N, D), incoming gradients (C, N, D) and gO * (1 - O_final), the only
+    // way the alpha output enters: [field][lane]
+    __shared__ float s_ray[FTB / 32][21 * 32];
     const TraceArgs &a = p.a;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -297,7 +316,7 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
     float *rayv = s_ray[threadIdx.x >> 5];
     // (one 32-ray group per warp, one launch wave after the other: a grid-stride loop over the groups with a resident-sized grid
     // measured 2.44 instead of 1.84 ms per 2^22 rays -- the hardware's dynamic block scheduling balances the very uneven groups)
-    const int64_t ray0 = ((int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * 32;
+    const int64_t ray0 = ((int64_t)blockIdx.x * (FTB / 32) + (threadIdx.x >> 5)) * 32;
     if (ray0 >= a.n_rays) return;
     const int64_t my_ray = ray0 + lane;
     const bool valid = my_ray < a.n_rays;
@@ -326,7 +345,8 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
     rayv[0 * 32 + lane] = r.ox; rayv[1 * 32 + lane] = r.oy; rayv[2 * 32 + lane] = r.oz;
     rayv[3 * 32 + lane] = r.dx; rayv[4 * 32 + lane] = r.dy; rayv[5 * 32 + lane] = r.dz;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { rayv[(6 + j) * 32 + lane] = fin[j]; rayv[(14 + j) * 32 + lane] = gout[j]; }
+    for (int j = 0; j < 7; ++j) { rayv[(6 + j) * 32 + lane] = fin[j]; rayv[(13 + j) * 32 + lane] = gout[j]; }
+    rayv[20 * 32 + lane] = gout[7] * (1.f - fin[7]);
     __syncwarp();
     const int c_eff = has ? cnt : 0;
     int incl = c_eff;
@@ -338,9 +358,9 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
     const int start = incl - c_eff;
     const int total = __shfl_sync(FULL, incl, 31);
     float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
-    float carryT = 1.f, carry_rem[8], carry_remF[FEAT ? NFMAX : 1];
+    float carryT = 1.f, carry_rem[7], carry_remF[FEAT ? NFMAX : 1];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) carry_rem[j] = 0.f;
+    for (int j = 0; j < 7; ++j) carry_rem[j] = 0.f;
 #pragma unroll
     for (int j = 0; j < (FEAT ? NFMAX : 1); ++j) carry_remF[j] = 0.f;
     const int nvec = ((a.deg + 1) * (a.deg + 1) * 3 + 3) >> 2;
@@ -390,9 +410,10 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         RayCtx ro;
         ro.ox = rayv[0 * 32 + owner]; ro.oy = rayv[1 * 32 + owner]; ro.oz = rayv[2 * 32 + owner];
         ro.dx = rayv[3 * 32 + owner]; ro.dy = rayv[4 * 32 + owner]; ro.dz = rayv[5 * 32 + owner];
-        float F[8], gO[8];
+        float F[7], gO[7];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { F[j] = rayv[(6 + j) * 32 + owner]; gO[j] = rayv[(14 + j) * 32 + owner]; }
+        for (int j = 0; j < 7; ++j) { F[j] = rayv[(6 + j) * 32 + owner]; gO[j] = rayv[(13 + j) * 32 + owner]; }
+        const float gO_alpha = rayv[20 * 32 + owner];   // grad_alpha * (1 - alpha_final)
         const int64_t o_gr = __shfl_sync(FULL, gr, owner);
         // segment of this lane's ray inside the round
         const int first = act ? lane - k : lane, last = act ? lane + (n_o - 1 - k) : lane;
@@ -463,10 +484,10 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         const float w = act ? T_before * alpha : 0.f;
 
         // ---- "still to come" terms: segmented exclusive suffix sums of the compositing contributions
-        float x[8] = {w * c[0], w * c[1], w * c[2], w * nf[0], w * nf[1], w * nf[2], w * t, w};
-        float R[8];
+        float x[7] = {w * c[0], w * c[1], w * c[2], w * nf[0], w * nf[1], w * nf[2], w * t};
+        float R[7];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 7; ++j) {
             float e = __shfl_down_sync(FULL, x[j], 1);
             if (!dn_ok[0]) e = 0.f;
 #pragma unroll
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
         carryT = __shfl_sync(FULL, T, 31);
 
         // ---- gradient of this hit (gaussiantrace_backward.cu:100-166)
-        float dL_dalpha = gO[6] * (T * t - R[6]) + gO[7] * (1.f - F[7]);
+        float dL_dalpha = gO[6] * (T * t - R[6]) + gO_alpha;
 #pragma unroll
         for (int j = 0; j < 3; ++j) dL_dalpha += gO[j] * (T * c[j] - R[j]) + gO[3 + j] * (T * nf[j] - R[3 + j]);
         if (FEAT) {
@@ -530,6 +551,9 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
                 row[1] = make_float4(dpu * px, dpu * py, dpu * pz, dpv * px);
                 row[2] = make_float4(dpv * py, dpv * pz, dnx, dny);
                 row[3] = make_float4(dnz, 0.f, 0.f, 0.f);
+#if IRGS_BWD_UNIFORM_ISSUE
+                rows[lane * BROW + 64] = __uint_as_float((unsigned)g);
+#endif
                 const float gc[3] = {gO[0] * w, gO[1] * w, gO[2] * w};
                 float Y[16];
                 sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
@@ -576,12 +600,34 @@ __global__ void __launch_bounds__(TB, IRGS_BWD_BLOCKS) trace_backward_flat_kerne
             // 16-byte vector reductions: the L1TEX data pipe spends one wavefront per LANE on a reduction however
             // well the addresses coalesce (1.65 M wavefronts per SM and launch = hits x 16), which bounded the kernel.
 #ifndef IRGS_DEBUG_SKIP_REDUCE   // timing experiment only: how much of the kernel is the reduction traffic
+#if IRGS_BWD_UNIFORM_ISSUE
+            // UBLKRED is a uniform-datapath instruction: one per WARP, operands in uniform registers.  Issued by every lane under
+            // `if (act)` with per-lane operands, the compiler wraps it in a serial loop over the active lanes (ELECT, three R2UR
+            // broadcasts, two predicate updates, the branch: eight DEPENDENT instructions per hit, 15 % of the kernel's stall
+            // samples).  Instead one elected lane issues the round's reductions in an unrolled loop: the row indices wait in the pad
+            // word of the rows, eight LDS / R2UR / address computations are in flight at a time (-3.4 % on the kernel).
+            {
+                const int n_here = min(32, total - base);
+                const uint32_t src0 = (uint32_t)__cvta_generic_to_shared(rows);
+                const uint32_t nbytes = (uint32_t)(4 + nvec) * 16u;
+                if (elect_one()) {
+#pragma unroll 8
+                    for (int i = 0; i < n_here; ++i) {
+                        const unsigned gi = __float_as_uint(rows[i * BROW + 64]);
+                        float *dst = a.grad_fused + (size_t)gi * IRGS_GRAD_STRIDE;
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                     :: "l"(dst), "r"(src0 + (uint32_t)(i * BROW * 4)), "r"(nbytes) : "memory");
+                    }
+                }
+            }
+#else
             if (act) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows + lane * BROW);
                 float *dst = a.grad_fused + (size_t)g * IRGS_GRAD_STRIDE;
                 asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                              :: "l"(dst), "r"(src), "r"((4 + nvec) * 16) : "memory");
             }
+#endif
 #endif
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         } else {
@@ -920,21 +966,21 @@ int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
     const bool feat = a.S > 0;
     if (a.hits != nullptr && a.hit_count != nullptr) {
         const unsigned grid = (unsigned)((a.n_rays + TB - 1) / TB);
-        auto flat_grid = [&](const void *) { return grid; };
+        auto flat_grid = [&](const void *) { return (unsigned)((a.n_rays + FTB - 1) / FTB); };
         if (h->bwd_mode == 1) {   // thread-per-ray replay (kept for comparison: irgs_set_option("bwd_mode", 1))
             if (feat) trace_backward_replay_kernel<true><<<grid, TB, 0, s>>>(p);
             else trace_backward_replay_kernel<false><<<grid, TB, 0, s>>>(p);
         } else {
             if (h->bwd_mode == 2) {   // 16-byte vector reductions instead of bulk reductions (comparison)
-                if (feat) trace_backward_flat_kernel<true, false><<<flat_grid((const void *)trace_backward_flat_kernel<true, false>), TB, 0, s>>>(p);
-                else trace_backward_flat_kernel<false, false><<<flat_grid((const void *)trace_backward_flat_kernel<false, false>), TB, 0, s>>>(p);
+                if (feat) trace_backward_flat_kernel<true, false><<<flat_grid((const void *)trace_backward_flat_kernel<true, false>), FTB, 0, s>>>(p);
+                else trace_backward_flat_kernel<false, false><<<flat_grid((const void *)trace_backward_flat_kernel<false, false>), FTB, 0, s>>>(p);
             } else {
                 if (feat) {
                     set_carveout(trace_backward_flat_kernel<true, true>, h->bwd_carveout_pct);
-                    trace_backward_flat_kernel<true, true><<<flat_grid((const void *)trace_backward_flat_kernel<true, true>), TB, 0, s>>>(p);
+                    trace_backward_flat_kernel<true, true><<<flat_grid((const void *)trace_backward_flat_kernel<true, true>), FTB, 0, s>>>(p);
                 } else {
                     set_carveout(trace_backward_flat_kernel<false, true>, h->bwd_carveout_pct);
-                    trace_backward_flat_kernel<false, true><<<flat_grid((const void *)trace_backward_flat_kernel<false, true>), TB, 0, s>>>(p);
+                    trace_backward_flat_kernel<false, true><<<flat_grid((const void *)trace_backward_flat_kernel<false, true>), FTB, 0, s>>>(p);
                 }
             }
         }

@@ -16,10 +16,11 @@ n = min(1 << 22, ro.shape[0])
 gout = bench.make_gout(n, dev)
 leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
 tr.accumulate_grads = True
-for mode in (0, 2, 1):
+if os.environ.get("CARVE"): tr.set_option("bwd_carveout_pct", int(os.environ["CARVE"]))
+for mode in [int(m) for m in os.environ.get("MODES", "0,2,1").split(",")]:
     tr.set_option("bwd_mode", mode)
     best_f = best_b = 1e9
-    for _ in range(5):
+    for _ in range(int(os.environ.get("REPS", 5))):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
         outs = tr.trace(ro[:n], rd[:n], leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], None, leaf["shs"], synth.ALPHA_MIN)

@@ -71,6 +71,9 @@ constexpr int DRAIN_G = 4;                  // lanes (= node visits in flight) p
 static_assert(DRAIN_MAX * DRAIN_G <= 32, "one group of DRAIN_G lanes per walking ray");
 static_assert(DRAIN_MAX >= 0, "0 compiles the wide walk out");
 constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide walk accepts: sp + 3 G + 1 <= SSTK entries afterwards
+#ifndef IRGS_FULL_RANK_SMEM
+#define IRGS_FULL_RANK_SMEM 1     // 0: the full-row rank loop through 64 shuffles (comparison builds)
+#endif
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -104,7 +107,7 @@ template <int NF, bool STATS, bool GEN>
 __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(const KParams p, uint4 *__restrict__ cand_base) {
     constexpr int SS = GEN ? SSTK - RQ_WORDS : SSTK;   // traversal stack entries in shared memory
     constexpr bool FEAT = NF > 0;
-    __shared__ WarpSmem<NF> smem[TB / 32];
+    __shared__ __align__(16) WarpSmem<NF> smem[TB / 32];
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
@@ -436,11 +439,26 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             // (depths are positive and surfel ids non-negative: the (t, id) order is the order of the packed 64-bit keys)
             const unsigned long long my_key = ((unsigned long long)__float_as_uint(my_t) << 32) | (unsigned)my_g;
             int rank = 0;
+#if IRGS_FULL_RANK_SMEM
+            {   // all 32 keys through shared memory, two per broadcast load (16 LDS.128 instead of 64 shuffles)
+                unsigned long long *s_k = reinterpret_cast<unsigned long long *>(ws.scratch);
+                s_k[lane] = my_key;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < KB; j += 2) {
+                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(s_k + j);
+                    rank += (kk.x < my_key) ? 1 : 0;
+                    rank += (kk.y < my_key) ? 1 : 0;
+                }
+                __syncwarp();   // the keys have been read before the scratch rows are reused below
+            }
+#else
             for (int j = 0; j < KB; ++j) {
                 const unsigned tj = __shfl_sync(FULL, __float_as_uint(my_t), j);
                 const unsigned gj = __shfl_sync(FULL, (unsigned)my_g, j);
                 rank += ((((unsigned long long)tj << 32) | gj) < my_key) ? 1 : 0;
             }
+#endif
             {
                 float *s_f = ws.scratch;
                 int *s_i = reinterpret_cast<int *>(ws.scratch);
@@ -533,6 +551,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 my_t = __uint_as_float(e.x); my_g = (int)e.y; my_a = __uint_as_float(e.z); my_p = (int)e.w;
             }
             const unsigned long long my_key = ((unsigned long long)__float_as_uint(my_t) << 32) | (unsigned)my_g;
+            // (the same loop through shared memory -- one 64-bit load per step, addresses differing by segment -- measured 3 % slower
+            //  than the two shuffles; only the full-row sort above, whose loads are broadcasts, gains from it)
             int rank = 0;
             for (int j = 0; j < maxn; ++j) {
                 const int src = (seg_lo + j) & 31;

@@ -74,6 +74,12 @@ constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide
 #ifndef IRGS_FULL_RANK_SMEM
 #define IRGS_FULL_RANK_SMEM 1     // 0: the full-row rank loop through 64 shuffles (comparison builds)
 #endif
+#ifndef IRGS_FULL_CHAIN_SMEM
+#define IRGS_FULL_CHAIN_SMEM 1    // 0: the full-row transmittance chain through one shuffle per candidate (comparison builds)
+#endif
+#ifndef IRGS_LEAF_PACK
+#define IRGS_LEAF_PACK 1          // 0: seven shuffles of per-owner integers and window ids per leaf round instead of two
+#endif
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
@@ -375,8 +381,15 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     if (v <= idx) owner += step;
                 }
                 owner = has ? owner : (int)lane;
+#if IRGS_LEAF_PACK
+                // (start < 2^10, m / pn / cnt <= 32: one shuffle instead of four)
+                const unsigned o_pk = __shfl_sync(FULL, (unsigned)start | ((unsigned)m << 10) | ((unsigned)pn << 16) | ((unsigned)cnt << 22), owner);
+                const int o_start = (int)(o_pk & 1023u), o_m = (int)((o_pk >> 10) & 63u);
+                const int o_pn = (int)((o_pk >> 16) & 63u), o_cnt = (int)(o_pk >> 22);
+#else
                 const int o_start = __shfl_sync(FULL, start, owner), o_m = __shfl_sync(FULL, m, owner);
                 const int o_pn = __shfl_sync(FULL, pn, owner), o_cnt = __shfl_sync(FULL, cnt, owner);
+#endif
                 float4 q0, q1, q2, q3;
                 q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
                 int leaf = 0;
@@ -390,10 +403,20 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 ro.ox = __shfl_sync(FULL, r.ox, owner); ro.oy = __shfl_sync(FULL, r.oy, owner); ro.oz = __shfl_sync(FULL, r.oz, owner);
                 ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);
                 const float o_tlast = __shfl_sync(FULL, t_last, owner), o_thi = __shfl_sync(FULL, t_hi, owner);
-                const int o_glast = __shfl_sync(FULL, g_last, owner), o_ghi = __shfl_sync(FULL, g_hi, owner);
                 float t, alpha = 0.f, px, py, pz; int g;
+#if IRGS_LEAF_PACK
+                // the pass window is a pair of (t, id) keys; the ids decide only when a depth equals a bound bit for bit, so they
+                // are fetched (two more shuffles) only in the rounds in which some lane needs them
+                bool ok = has && leaf_stage1(ro, q0, q1, back_culling, t, g, px, py, pz) && !(t < o_tlast) && !(o_thi < t);
+                if (__any_sync(FULL, ok && (t == o_tlast || t == o_thi))) {
+                    const int o_glast = __shfl_sync(FULL, g_last, owner), o_ghi = __shfl_sync(FULL, g_hi, owner);
+                    ok = ok && key_less(o_tlast, o_glast, t, g) && key_less(t, g, o_thi, o_ghi);
+                }
+#else
+                const int o_glast = __shfl_sync(FULL, g_last, owner), o_ghi = __shfl_sync(FULL, g_hi, owner);
                 bool ok = has && leaf_stage1(ro, q0, q1, back_culling, t, g, px, py, pz) &&
                           key_less(o_tlast, o_glast, t, g) && key_less(t, g, o_thi, o_ghi);
+#endif
                 if (ok) {
                     // fetching the second half of the record only now saves L1TEX wavefronts but serialises two L2
                     // latencies: measured 2 % slower than issuing both loads up front (profiles/r01_sweeps.txt)
@@ -432,8 +455,9 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         while (work != 0u) {
             const int L = __ffs(work) - 1;
             work &= work - 1u;
-            __syncwarp();  // lane L's appended candidates are visible to the whole warp
             // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
+            __syncwarp();  // lane L's appended candidates are visible to the whole warp
+            // (requesting the next waiting row before this one is sorted measured nothing: profiles/r02_sweeps.txt)
             const uint4 e = __ldcg(&warp_cand[(size_t)L * KB + lane]);
             float my_t = __uint_as_float(e.x), my_a = __uint_as_float(e.z); int my_g = (int)e.y, my_p = (int)e.w;
             // (depths are positive and surfel ids non-negative: the (t, id) order is the order of the packed 64-bit keys)
@@ -465,17 +489,35 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 s_f[rank] = my_t; s_i[32 + rank] = my_g; s_f[64 + rank] = my_a; s_i[96 + rank] = my_p;
                 __syncwarp();
                 my_t = s_f[lane]; my_g = s_i[32 + lane]; my_a = s_f[64 + lane]; my_p = s_i[96 + lane];
+#if !IRGS_FULL_CHAIN_SMEM
                 __syncwarp();
+#endif
             }
             // transmittance chain in the reference's sequential order
             float Tc = __shfl_sync(FULL, T, L);
             int n_comp = KB;
             bool term = false;
+#if IRGS_FULL_CHAIN_SMEM
+            // (the ordered alphas are still in the scratch row: four per broadcast load instead of one shuffle each)
+            for (int i = 0; i < KB && !term; i += 4) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(ws.scratch + 64 + i);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!term) {
+                        Tc *= (1.f - av[u]);
+                        if (Tc < T_min) { n_comp = i + u + 1; term = true; }
+                    }
+                }
+            }
+            __syncwarp();   // the scratch row may be overwritten from here on
+#else
             for (int i = 0; i < KB; ++i) {
                 const float ai = __shfl_sync(FULL, my_a, i);
                 Tc *= (1.f - ai);
                 if (Tc < T_min) { n_comp = i + 1; term = true; break; }
             }
+#endif
             // terminated: keep the composited prefix and clip the walk to it; otherwise split the depth range at the
             // KB/2-th candidate and leave the rest of the ray to a following pass
             // (a row that terminates only at its very last entry cannot be trimmed: it is split like any other)
@@ -552,7 +594,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             }
             const unsigned long long my_key = ((unsigned long long)__float_as_uint(my_t) << 32) | (unsigned)my_g;
             // (the same loop through shared memory -- one 64-bit load per step, addresses differing by segment -- measured 3 % slower
-            //  than the two shuffles; only the full-row sort above, whose loads are broadcasts, gains from it)
+            //  than the two shuffles; only the full-row sort above, whose loads are broadcasts, gains from it.  Ranking by depth alone
+            //  -- one shuffle per step, the (t, id) loop only after a tie -- also measured 3 % slower: profiles/r02_sweeps.txt)
             int rank = 0;
             for (int j = 0; j < maxn; ++j) {
                 const int src = (seg_lo + j) & 31;

@@ -324,6 +324,11 @@ int irgs_normalize_outputs_backward(int64_t n_rays, int S, float threshold, cons
  * "gen_in_kernel": 0 (default) incident / camera rays of a forward call are written to an internal scratch block by a small
  * kernel and read back by the forward kernel (measured faster: DRAM is idle, the persistent walk is not), 1 generates them
  * inside the forward kernel (24 B per ray of a call less memory).  The backward always regenerates them in its kernels.
+ * "color_cache": entries per ray (default 32, 0 = off, at most hit_cap) of the replay's colour cache: a forward call that saves
+ * hit lists also leaves the SH colour of each ray's first entries (12 B each) in a block owned by the handle, one per stream
+ * (n_rays x entries x 12 B, kept until a larger call needs more); the irgs_trace_backward* call on the same stream whose `hits`
+ * pointer is the one that forward wrote reads them instead of gathering a 192-byte SH row per hit.  Any other backward (another
+ * stream, a forward in between, a copied list) gathers as before: same results either way.
  * Returns non-zero for unknown names. */
 int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 
@@ -332,7 +337,7 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value);
 int64_t irgs_stride_multiplier(int64_t n_rays);
 
 /* Introspection (tests, diagnostics): "tree_depth" (levels of the PLOC tree of the last build; 0 = Karras tree), "ploc_iterations",
- * "n_slots" (streams seen so far), "n_surfels", "pack_epoch", "grazing_pairs" / "grazing_pairs_compositing" (statistics build).
+ * "n_slots" (streams seen so far), "n_surfels", "pack_epoch", "color_cache_bytes" (size of the colour-cache blocks), "grazing_pairs" / "grazing_pairs_compositing" (statistics build).
  * -1 for unknown names. */
 int64_t irgs_get_info(irgs_tracer_t *h, const char *name);
 

@@ -121,6 +121,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
         cudaFree(h->cand[i]);
         cudaFree(h->inc_pts[i]);
         cudaFree(h->ray_scratch[i]);
+        cudaFree(h->hit_rgb[i]);
     }
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
@@ -686,6 +687,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->gen_in_kernel = value ? 1 : 0;
         return 0;
     }
+    if (strcmp(name, "color_cache") == 0) {
+        h->color_cache = value < 0 ? 0 : (value > 96 ? 96 : (int)value);
+        return 0;
+    }
     if (strcmp(name, "bwd_mode") == 0) {
         h->bwd_mode = (value == 1 || value == 2) ? (int)value : 0;
         return 0;
@@ -700,6 +705,11 @@ int64_t irgs_get_info(irgs_tracer_t *h, const char *name) {
     if (strcmp(name, "n_slots") == 0) return h->n_slots;
     if (strcmp(name, "n_surfels") == 0) return h->built ? h->n : 0;
     if (strcmp(name, "pack_epoch") == 0) return h->pack_epoch;
+    if (strcmp(name, "color_cache_bytes") == 0) {
+        int64_t b = 0;
+        for (int i = 0; i < irgs_tracer::MAX_SLOTS; ++i) b += 4 * h->hit_rgb_floats[i];
+        return b;
+    }
     if (strcmp(name, "grazing_pairs") == 0 || strcmp(name, "grazing_pairs_compositing") == 0) {
         // statistics of the last forward with irgs_set_stats(h, 1): ray / surfel pairs with |n.d| < 1e-3 that cross the surfel's
         // support geometrically (dropped by the hit test; the reference evaluates them with its clamped depth), and how many of

@@ -105,6 +105,15 @@ struct irgs_tracer {
     int64_t rsort_cap[MAX_SLOTS] = {};
     float *ray_scratch[MAX_SLOTS] = {};     // generated rays of a forward call, materialised per stream slot (o[3n] d[3n])
     int64_t ray_scratch_cap[MAX_SLOTS] = {};
+    // Colour cache of the backward replay, per stream slot: the forward kernel leaves the SH colour of a ray's first `hit_rgb_cc`
+    // composited hits here (12 B each) when it saves hit lists; a backward on the same stream whose hit-list pointer is the one
+    // the slot's last saving forward wrote reads them instead of gathering a 192-byte SH row per hit (launch_trace_backward).
+    float *hit_rgb[MAX_SLOTS] = {};
+    int64_t hit_rgb_floats[MAX_SLOTS] = {};     // allocated size
+    const void *hit_rgb_key[MAX_SLOTS] = {};    // hit-list pointer of the forward whose colours the block holds (nullptr: none)
+    int64_t hit_rgb_rays[MAX_SLOTS] = {};       // rays of that forward
+    int hit_rgb_cc[MAX_SLOTS] = {};             // entries per ray of that forward
+    int color_cache = 32;                       // entries per ray for the next forward calls (irgs_set_option("color_cache"); 0: off)
     long long pack_epoch = 0;               // bumped by every pack of the records and by every build / refit
     int contiguous_outputs = 0;             // the caller allocates a call's outputs as ONE block whenever they are back to back
     int skip_next_pack = 0;                 // the next irgs_trace_backward* reuses the records as they are (irgs_set_option)
@@ -167,6 +176,8 @@ struct TraceArgs {
     float *color, *normal, *feature, *depth, *alpha;
     int32_t *hit_count, *hits;
     int hit_cap;
+    float *hit_rgb;   // colour cache of the stream slot ([n_rays, rgb_cap, 3]) or nullptr; set by the launchers, not by the ABI
+    int rgb_cap;
     // fused incident-ray generation: when gen_pos != nullptr the rays are not read from rays_o / rays_d
     // but generated from (shading point, normal, azimuth) and the sample index: ray = point * gen_S + sample
     const float *gen_pos, *gen_nrm, *gen_azim;   // [P,3], [P,3], [P] or nullptr (no random rotation)

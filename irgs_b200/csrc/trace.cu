@@ -431,9 +431,13 @@ __global__ void __launch_bounds__(FTB, IRGS_BWD_BLOCKS) trace_backward_flat_kern
         int g = 0;
         if (act) {
             g = g_cur;
-            float Y[16];   // (only for the colour here: the SH gradient row re-derives the basis when it is written, so that sixteen
-                           //  registers are not held across the segmented scans in between)
-            sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
+            // the hit's colour: from the forward's colour cache (12 B, three streamed loads next to the neighbouring hits' of the ray)
+            // or -- hits beyond the cached entries, or no valid cache -- from the surfel's SH row (192 B gather + 48 fma)
+            const bool cached = a.hit_rgb != nullptr && k < a.rgb_cap;
+            if (cached) {
+                const float *hc = a.hit_rgb + ((size_t)ray * a.rgb_cap + k) * 3;
+                c[0] = __ldcs(hc); c[1] = __ldcs(hc + 1); c[2] = __ldcs(hc + 2);
+            }
             // the surfel's packed record (re-packed from the saved inputs before this launch): two 32-byte loads
             float4 q0, q1, q2, q3;
             const SurfelRec *rec = p.recs + pos_cur;
@@ -454,7 +458,12 @@ __global__ void __launch_bounds__(FTB, IRGS_BWD_BLOCKS) trace_backward_flat_kern
             pu = dot3_rn(ax, ay, az, px, py, pz); pv = dot3_rn(bx, by, bz, px, py, pz);
             G = __expf(__fmul_rn(-0.5f, __fadd_rn(__fmul_rn(pu, pu), __fmul_rn(pv, pv))));
             alpha = fminf(0.99f, __fmul_rn(op, G));
-            sh_color(a.shs, a.K, a.deg, g, Y, c);
+            if (!cached) {
+                float Y[16];   // (only for the colour here: the SH gradient row re-derives the basis when it is written, so that
+                               //  sixteen registers are not held across the segmented scans in between)
+                sh_basis(a.deg, ro.dx, ro.dy, ro.dz, Y);
+                sh_color(a.shs, a.K, a.deg, g, Y, c);
+            }
             if (FEAT) {
 #pragma unroll
                 for (int j = 0; j < NFMAX; ++j)
@@ -959,9 +968,19 @@ static void set_carveout(Kern kern, int pct) {
     if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 }
 
-int launch_trace_backward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
+int launch_trace_backward(irgs_tracer *h, const TraceArgs &a_in, cudaStream_t s) {
     const int slot = slot_for(h, s);
     if (slot < 0) return 1;
+    // colour cache: valid when the last forward that saved hit lists on THIS stream wrote exactly this list (same stream = the
+    // kernels run in the order of the calls, so a later forward cannot overwrite the block before this replay has read it)
+    TraceArgs a = a_in;
+    a.hit_rgb = nullptr; a.rgb_cap = 0;
+    if (a.hits != nullptr) {
+        std::lock_guard<std::mutex> lock(h->slot_mutex);
+        if (h->hit_rgb[slot] != nullptr && h->hit_rgb_key[slot] == a.hits && h->hit_rgb_rays[slot] == a.n_rays && h->color_cache > 0) {
+            a.hit_rgb = h->hit_rgb[slot]; a.rgb_cap = h->hit_rgb_cc[slot];
+        }
+    }
     KParams p = make_params(h, a, slot);
     const bool feat = a.S > 0;
     if (a.hits != nullptr && a.hit_count != nullptr) {

@@ -651,6 +651,10 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                         if (j < a.S) f[j] = my_w * __ldg(a.features + (size_t)my_g * a.S + j);
                 }
                 if (a.hits != nullptr && total_o + k < a.hit_cap) a.hits[ray_o * a.hit_cap + total_o + k] = my_g;
+                if (a.hit_rgb != nullptr && total_o + k < a.rgb_cap) {   // colour cache of the backward replay (streamed: read once)
+                    float *hc = a.hit_rgb + ((size_t)ray_o * a.rgb_cap + total_o + k) * 3;
+                    __stcs(hc, c[0]); __stcs(hc + 1, c[1]); __stcs(hc + 2, c[2]);
+                }
             }
             // Sequential accumulation in depth order, exactly like the reference's loop (and the oracle's): one lane per
             // (ray, output channel) adds that ray's n_comp terms one after the other to the running value in global
@@ -795,6 +799,31 @@ int launch_trace_forward(irgs_tracer *h, const TraceArgs &a, cudaStream_t s) {
         p.a.gen_pos = nullptr; p.a.cam_W = 0;
     }
     p.nodes = h->qnodes; p.nodes4 = h->qnodes4; p.qframe = h->scene + 12; p.recs = h->recs; p.inv_order = h->inv_order; p.counter = h->counter + slot; p.stats = h->stats;
+    // Colour cache for the backward replay (internal.cuh): a call that saves hit lists also leaves the colours of each ray's first
+    // color_cache hits in a block of this stream slot.  Failing to get the memory only means the backward gathers SH rows.
+    p.a.hit_rgb = nullptr; p.a.rgb_cap = 0;
+    if (a.hits != nullptr && a.hit_count != nullptr && h->color_cache > 0) {
+        const int cc = h->color_cache < a.hit_cap ? h->color_cache : a.hit_cap;
+        const int64_t need = a.n_rays * cc * 3;
+        std::lock_guard<std::mutex> lock(h->slot_mutex);
+        if (need > h->hit_rgb_floats[slot]) {
+            IRGS_CHECK(cudaStreamSynchronize(s));   // earlier users of the old block all ran on this stream
+            if (h->hit_rgb[slot]) cudaFree(h->hit_rgb[slot]);
+            h->hit_rgb[slot] = nullptr; h->hit_rgb_floats[slot] = 0; h->hit_rgb_key[slot] = nullptr;
+            if (cudaMalloc(&h->hit_rgb[slot], sizeof(float) * (size_t)need) == cudaSuccess) h->hit_rgb_floats[slot] = need;
+            else { h->hit_rgb[slot] = nullptr; cudaGetLastError(); }
+        }
+        if (h->hit_rgb[slot] != nullptr && cc > 0) {
+            for (int i = 0; i < irgs_tracer::MAX_SLOTS; ++i)
+                if (h->hit_rgb_key[i] == a.hits) h->hit_rgb_key[i] = nullptr;   // that list is being overwritten
+            h->hit_rgb_key[slot] = a.hits; h->hit_rgb_rays[slot] = a.n_rays; h->hit_rgb_cc[slot] = cc;
+            p.a.hit_rgb = h->hit_rgb[slot]; p.a.rgb_cap = cc;
+        }
+    } else if (a.hits != nullptr) {
+        std::lock_guard<std::mutex> lock(h->slot_mutex);
+        for (int i = 0; i < irgs_tracer::MAX_SLOTS; ++i)
+            if (h->hit_rgb_key[i] == a.hits) h->hit_rgb_key[i] = nullptr;
+    }
     const bool stats = h->stats_enabled != 0;
     if (stats) IRGS_CHECK(cudaMemsetAsync(h->stats, 0, 8 * sizeof(unsigned long long), s));
     // (generated rays -- a.gen_pos -- have no ray arrays to take sort keys from and arrive grouped per shading point anyway)

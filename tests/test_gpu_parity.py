@@ -247,6 +247,42 @@ def _translucent(inp, opacity=0.04):
     out["opacity"] = torch.full_like(inp["opacity"], opacity)
     return out
 
+@pytest.mark.parametrize("translucent", [False, True])
+def test_colour_cache_of_the_replay_equals_the_sh_gather(small_scene, translucent):
+    """The forward leaves the colours of each ray's first `color_cache` hits in a block of its stream slot and the replay reads
+    them instead of gathering SH rows; hits beyond the cached entries (cache of 4; lists longer than 32 in the translucent scene)
+    and calls without a valid cache (option 0; a second forward on the same stream in between) gather.  All of them are the
+    same numbers: the colour is the forward's own, and what the gather recomputes is the same arithmetic."""
+    sc, inp = small_scene
+    if translucent:
+        inp = _translucent(inp)
+    o, d = _rays(inp, "secondary")
+    gout = _gout(o.shape[0], inp["features"].shape[1])
+    res, used = [], []
+    for cc in (32, 0, 4):
+        tr = _tracer(_gpu(inp))
+        tr.set_option("color_cache", cc)
+        res.append(_cuda_fwd_bwd(tr, inp, o, d, gout)[1])
+        used.append(tr.get_info("color_cache_bytes"))
+    assert used[0] == o.shape[0] * 32 * 12 and used[1] == 0 and used[2] == o.shape[0] * 4 * 12
+    # a forward of OTHER rays on the same stream between a forward and its backward: the block holds the wrong call's colours,
+    # the replay must notice (hit-list pointer) and gather
+    tr = _tracer(_gpu(inp))
+    leaf = {k: inp[k].to(DEV).clone().requires_grad_(True) for k in KEYS}
+    ro, rd = o.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    outs = tr.trace(ro, rd, *[leaf[k] for k in KEYS], synth.ALPHA_MIN)
+    o2, d2 = _rays(inp, "secondary", seed=12)
+    outs2 = tr.trace(o2.to(DEV).requires_grad_(True), d2.to(DEV), *[leaf[k] for k in KEYS], synth.ALPHA_MIN)
+    names = ("color", "normal", "feature", "depth", "alpha")
+    sum((t * gout[n].to(DEV)).sum() for n, t in zip(names, outs)).backward()
+    res.append(dict(rays_o=ro.grad.cpu().numpy(), rays_d=rd.grad.cpu().numpy(), **{k: leaf[k].grad.cpu().numpy() for k in KEYS}))
+    del outs2
+    for k in res[0]:
+        scale = np.abs(res[0][k]).max() + 1e-30
+        for other in res[1:]:
+            assert np.abs(res[0][k] - other[k]).max() <= 1e-5 * scale, k  # float atomics: order noise only
+
+
 
 @pytest.mark.parametrize("translucent", [False, True])
 def test_hit_parallel_backward_equals_thread_per_ray_replay_and_oracle(small_scene, translucent):

@@ -51,6 +51,13 @@ constexpr int MIN_ACTIVE = IRGS_MIN_ACTIVE;
 #define IRGS_PQ 16
 #endif
 constexpr int PQ = IRGS_PQ;               // pending-leaf queue entries per lane
+// Row stride of the queue: a lane pushes into its own column, but the LEAF sub-phase pops the entries of ONE owner with
+// consecutive lanes -- with rows of 32 words they all sit in the owner's bank (an m-way conflict for m pending leaves); rows of
+// 33 words skew the columns over the banks
+#ifndef IRGS_PS
+#define IRGS_PS 33
+#endif
+constexpr int PS = IRGS_PS;
 #ifndef IRGS_FETCH_MIN
 #define IRGS_FETCH_MIN 4
 #endif
@@ -83,10 +90,16 @@ constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide
 enum { PH_FETCH = 0, PH_TRAV = 1, PH_COMP = 2, PH_FULL = 3 };
 constexpr int CUR_NONE = INT_MIN;
 
+// Row stride of the accumulation scratch: the lanes that add up one ray's channels read [channel][hit] with the SAME hit index --
+// a stride of 32 words put all channels of a ray into one bank (8-way conflicts on every step of the accumulation loop)
+#ifndef IRGS_CS
+#define IRGS_CS 33
+#endif
+constexpr int CS = IRGS_CS;
 template <int NF>   // feature channels the variant is built for: 0, 4 (base colour + roughness: relight, primary pass) or 12
 struct WarpSmem {
-    float scratch[(8 + NF) * 32];   // co-operative sort (4 x 32) / accumulation scratch (one row per output channel)
-    int pend[PQ * 32];        // pending leaves [entry][lane]
+    float scratch[(8 + NF) * CS];   // co-operative sort (4 x 32) / accumulation scratch (one row of CS words per output channel)
+    int pend[PQ * PS];        // pending leaves [entry][lane], rows of PS words
     int stack[SSTK * 32];     // traversal stack [entry][lane]
     // per-segment table of the packed COMP phase
     int seg_lo[32], seg_nc[32];
@@ -237,7 +250,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     float tn;
                     const bool hit = slab(r, c[k], t_lo, t_hi, tn);
                     const int ref = (int)c[k].w;
-                    if (hit && ref < 0) { pend[pn * 32] = ref; ++pn; }
+                    if (hit && ref < 0) { pend[pn * PS] = ref; ++pn; }
                     inner[k] = hit && ref >= 0;
                     tk[k] = inner[k] ? tn : INFINITY;
                 }
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if ((in_mask >> k) & 1u) ws.stack[(s0 + __popc(in_mask & ((1u << k) - 1u))) * 32 + owner] = ref[k];
-                    if ((lf_mask >> k) & 1u) ws.pend[(q0 + __popc(lf_mask & ((1u << k) - 1u))) * 32 + owner] = ref[k];
+                    if ((lf_mask >> k) & 1u) ws.pend[(q0 + __popc(lf_mask & ((1u << k) - 1u))) * PS + owner] = ref[k];
                 }
             }
             // the owners take the totals of their group (held by its last lane) and pop the next node
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                 q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
                 int leaf = 0;
                 if (has) {
-                    leaf = ~ws.pend[(o_pn - 1 - (idx - o_start)) * 32 + owner];   // popped from the top
+                    leaf = ~ws.pend[(o_pn - 1 - (idx - o_start)) * PS + owner];   // popped from the top
                     ldg256_stream(p.recs + leaf, q0, q1);
                     if (!LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, q2, q3);
                     if (STATS) ++st_leaf;
@@ -662,13 +675,13 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             // into passes and of the acceleration structure's topology.
             {
                 float *s_c = ws.scratch;   // [channel][lane]
-                s_c[0 * 32 + lane] = c0; s_c[1 * 32 + lane] = c1; s_c[2 * 32 + lane] = c2c;
-                s_c[3 * 32 + lane] = n0; s_c[4 * 32 + lane] = n1; s_c[5 * 32 + lane] = n2;
-                s_c[6 * 32 + lane] = dd; s_c[7 * 32 + lane] = oo;
+                s_c[0 * CS + lane] = c0; s_c[1 * CS + lane] = c1; s_c[2 * CS + lane] = c2c;
+                s_c[3 * CS + lane] = n0; s_c[4 * CS + lane] = n1; s_c[5 * CS + lane] = n2;
+                s_c[6 * CS + lane] = dd; s_c[7 * CS + lane] = oo;
                 if (FEAT) {
 #pragma unroll
                     for (int j = 0; j < NF; ++j)
-                        if (j < a.S) s_c[(8 + j) * 32 + lane] = f[j];
+                        if (j < a.S) s_c[(8 + j) * CS + lane] = f[j];
                 }
                 // per-segment table, written by the first lane of each segment
                 if (act && k == 0) {
@@ -693,7 +706,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     // the outputs are pre-zeroed: a ray's first pass adds to 0 without reading them back (a dependent L2 access)
                     // (L2-only __ldcg / __stcg here measured 12 % SLOWER on the C3 step: profiles/r01_sweeps.txt)
                     float accv = (slo & 256) ? 0.f : *dst;
-                    for (int i = 0; i < nc; ++i) accv += s_c[ch * 32 + lo + i];
+                    for (int i = 0; i < nc; ++i) accv += s_c[ch * CS + lo + i];
                     *dst = accv;
                 }
             }

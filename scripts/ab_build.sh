@@ -18,7 +18,7 @@ for f in $all; do
     $NV $defs -c $f.cu -o $o &
   else
     o=../../build/obj/base_$f.o
-    if [[ ! -f $o || $f.cu -nt $o ]]; then $NV -c $f.cu -o $o & fi
+    if [[ ! -f $o || $f.cu -nt $o || internal.cuh -nt $o || trace_common.cuh -nt $o || shade_math.cuh -nt $o ]]; then $NV -c $f.cu -o $o & fi
   fi
   objs="$objs $o"
 done

@@ -710,6 +710,14 @@ int64_t irgs_get_info(irgs_tracer_t *h, const char *name) {
         for (int i = 0; i < irgs_tracer::MAX_SLOTS; ++i) b += 4 * h->hit_rgb_floats[i];
         return b;
     }
+    if (strcmp(name, "comp_stats") == 0 || strcmp(name, "full_rows") == 0) {
+        // statistics build: "comp_stats" = sum over the packed compositing rounds of (longest segment << 32 | candidates),
+        // "full_rows" = rounds << 32 | full-row sorts
+        DeviceGuard guard(h->device);
+        unsigned long long v = 0;
+        if (cudaMemcpy(&v, h->stats + (strcmp(name, "comp_stats") == 0 ? 6 : 7), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int64_t)v;
+    }
     if (strcmp(name, "grazing_pairs") == 0 || strcmp(name, "grazing_pairs_compositing") == 0) {
         // statistics of the last forward with irgs_set_stats(h, 1): ray / surfel pairs with |n.d| < 1e-3 that cross the surfel's
         // support geometrically (dropped by the hit test; the reference evaluates them with its clamped depth), and how many of

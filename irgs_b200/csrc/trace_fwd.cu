@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
     const float alpha_min = a.alpha_min, T_min = a.T_min;
     const int back_culling = a.back_culling;
     uint4 *warp_cand = cand_base + ((size_t)blockIdx.x * TB + (tid & ~31)) * KB;   // rows of this warp's 32 lanes
-    unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0, st_graze = 0, st_graze_comp = 0;
+    unsigned long long st_nodes = 0, st_leaf = 0, st_hits = 0, st_pass = 0, st_graze = 0, st_graze_comp = 0, st_comp = 0, st_full = 0;
 
     int phase = PH_FETCH;
     bool pool_empty = false;  // warp-uniform: the global counter has run past the last ray (the queue may still hold some)
@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         while (work != 0u) {
             const int L = __ffs(work) - 1;
             work &= work - 1u;
+            if (STATS && lane == 0) ++st_full;
             // lane i takes candidate i, ranks it by (t, surfel id), and the candidates are permuted into depth order
             __syncwarp();  // lane L's appended candidates are visible to the whole warp
             // (requesting the next waiting row before this one is sorted measured nothing: profiles/r02_sweeps.txt)
@@ -587,6 +588,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const int c2 = in_group ? cnt : 0;
             const int start2 = incl - c2;
             const int maxn = __reduce_max_sync(FULL, c2);
+            if (STATS && lane == 0) { st_comp += ((unsigned long long)maxn << 32) + (unsigned long long)gtotal; st_full += 1ull << 32; }   // sum of the longest segment | candidates; rounds
             // candidate of this lane: owner = number of lanes whose inclusive count is <= lane
             const bool act = (int)lane < gtotal;
             int owner = 0;
@@ -608,7 +610,8 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const unsigned long long my_key = ((unsigned long long)__float_as_uint(my_t) << 32) | (unsigned)my_g;
             // (the same loop through shared memory -- one 64-bit load per step, addresses differing by segment -- measured 3 % slower
             //  than the two shuffles; only the full-row sort above, whose loads are broadcasts, gains from it.  Ranking by depth alone
-            //  -- one shuffle per step, the (t, id) loop only after a tie -- also measured 3 % slower: profiles/r02_sweeps.txt)
+            //  -- one shuffle per step, the (t, id) loop only after a tie -- also measured 3 % slower; so did nothing at all a special
+            //  case for rounds that hold ONE ray, ranked and chained through broadcast loads like a full row: profiles/r02_sweeps.txt)
             int rank = 0;
             for (int j = 0; j < maxn; ++j) {
                 const int src = (seg_lo + j) & 31;
@@ -737,6 +740,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
         atomicAdd(p.stats + 0, st_nodes); atomicAdd(p.stats + 1, st_leaf);
         atomicAdd(p.stats + 2, st_hits); atomicAdd(p.stats + 3, st_pass);
         atomicAdd(p.stats + 4, st_graze); atomicAdd(p.stats + 5, st_graze_comp);
+        atomicAdd(p.stats + 6, st_comp); atomicAdd(p.stats + 7, st_full);
     }
 }
 

@@ -550,19 +550,26 @@ def run_ours(args):
     # the kernel on its own: ONE extra step on a single stream right after the timed region, CUDA events around every
     # forward launch and around the step (in the timed region consecutive chunks alternate between two streams, where
     # the launch durations overlap each other and the other stream's backward)
-    del fwd_events[:]
     saved_side = side[:]
     del side[1:]
-    sync_all()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    step(True)
-    s1.record()
-    sync_all()
+    # (three such steps, the fastest one reported: the first single-stream step can pay one-off costs of the new allocation
+    #  pattern -- two chunks' outputs live on ONE stream -- that have nothing to do with the kernel)
+    serial_step_ms, fwd_ms, fwd_rays = None, 0.0, 0
+    for _ in range(3):
+        del fwd_events[:]
+        sync_all()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step(True)
+        s1.record()
+        sync_all()
+        if rank == 0 and os.environ.get("IRGS_BENCH_VERBOSE"):
+            print("serial step: forward launches [ms]", ["%.2f" % a.elapsed_time(b) for a, b, _ in fwd_events], file=sys.stderr)
+        if serial_step_ms is None or s0.elapsed_time(s1) < serial_step_ms:
+            serial_step_ms = s0.elapsed_time(s1)
+            fwd_ms = sum(a.elapsed_time(b) for a, b, _ in fwd_events)
+            fwd_rays = sum(n for _, _, n in fwd_events)
     side[:] = saved_side
-    serial_step_ms = s0.elapsed_time(s1)
-    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in fwd_events)
-    fwd_rays = sum(n for _, _, n in fwd_events)
     checksum = float(grads["shs"].abs().sum().item())
 
     # the same step with the rays generated inside the kernels (trace_incident) from the per-pixel
@@ -779,7 +786,7 @@ def run_ours(args):
                      "ncu_counters": counters,
                      "kernel_ms_per_step": fwd_ms, "serial_step_ms": serial_step_ms,
                      "kernel_share_of_step": fwd_ms / serial_step_ms,
-                     "timing": "one extra single-stream step right after the timed region, CUDA events around each forward "
+                     "timing": "the fastest of three extra single-stream steps right after the timed region, CUDA events around each forward "
                                "launch on its stream; in the timed region (streams = %d) the summed launch durations are %.1f ms "
                                "per step" % (args.streams, ovl_fwd_ms),
                      "note": "algorithmic bytes follow BASELINE.md section 4 on the oracle's canonical LBVH; most node and "

@@ -7,4 +7,4 @@ python scripts/ncu_phases.py $R > profiles/r${ROUND:-02}_fwd_phases_final.txt
 python scripts/ncu_regions.py $R trace_backward_flat 0.6 > profiles/r${ROUND:-02}_bwd_flat_regions.txt
 python scripts/launch_summary.py gpurun_out/final_launches.csv > profiles/r${ROUND:-02}_step_launches.txt
 cp gpurun_out/final_launches.csv profiles/r${ROUND:-02}_step_launches.csv
-python scripts/ncu_summary.py $R ${RAYS_PER_LAUNCH:-16777216}
+python scripts/ncu_summary.py $R ${RAYS_PER_LAUNCH:-16384000}

@@ -662,6 +662,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
         h->bwd_carveout_pct = value < 0 ? -1 : (value > 100 ? 100 : (int)value);
         return 0;
     }
+    if (strcmp(name, "fwd_blocks_per_sm") == 0) {
+        h->fwd_blocks_per_sm = value < 0 ? 0 : (value > 32 ? 32 : (int)value);
+        return 0;
+    }
     if (strcmp(name, "smem_carveout_pct") == 0) {
         h->carveout_pct = value < 0 ? -1 : (value > 100 ? 100 : (int)value);
         return 0;

@@ -121,6 +121,7 @@ struct irgs_tracer {
     void *inc_pts[MAX_SLOTS] = {};          // per-point records of generated incident rays (IncPoint[inc_cap]), per stream slot
     int64_t inc_cap[MAX_SLOTS] = {};
     int bwd_carveout_pct = -1;              // backward replay kernel: carve-out hint in percent (-1: the driver's default)
+    int fwd_blocks_per_sm = 0;              // forward kernel: resident blocks per SM of the persistent grid (0: what the occupancy allows)
     int carveout_pct = -1;                  // forward kernel: shared-memory carve-out hint in percent (-1: what the resident blocks need)
     int64_t stride_rays_max = 1 << 19;      // forward calls with at most this many rays start them in a stride order (0: never)
     int sort_rays_min = 0;                  // forward calls with at least this many rays are coherence-sorted (0: never;

@@ -748,6 +748,7 @@ template <typename Kern>
 static int launch_fwd(irgs_tracer *h, int slot, Kern kern, const KParams &p, int64_t n_rays, cudaStream_t s) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    if (h->fwd_blocks_per_sm > 0 && h->fwd_blocks_per_sm < per_sm) per_sm = h->fwd_blocks_per_sm;   // irgs_set_option: experiments
     int grid = h->sm_count * per_sm;
     // Shared-memory carve-out: exactly what the resident blocks need, so that the rest of the 256 KB stays L1 cache (the top
     // levels of the tree are read by every ray; with the default maximum carve-out the L1 hit rate of the walk was 3.8 %).

@@ -15,6 +15,7 @@ def factory(sc, inp):
 sc, inp, tr, ro, rd = bench.build_workload(A, dev, 0, 1, factory)
 leaf = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "ru", "rv", "normals", "shs")}
 args = (leaf["means3D"], leaf["opacity"], leaf["ru"], leaf["rv"], leaf["normals"], None, leaf["shs"], synth.ALPHA_MIN)
+if os.environ.get("BPS"): tr.set_option("fwd_blocks_per_sm", int(os.environ["BPS"]))
 for n in (1 << 14, 1 << 16, 1 << 18, 1 << 20, 1 << 22):
     gout = bench.make_gout(n, dev)
     bf = bb = 1e9
@@ -28,6 +29,7 @@ for n in (1 << 14, 1 << 16, 1 << 18, 1 << 20, 1 << 22):
         bf = min(bf, e0.elapsed_time(e1)); bb = min(bb, e1.elapsed_time(e2))
         for v in leaf.values(): v.grad = None
     print(f"n={n:8d} fwd {bf:7.3f} ms ({n/bf/1e3:6.1f} Mrays/s)  bwd {bb:7.3f} ms  fwd+bwd {n/(bf+bb)/1e3:6.1f} Mrays/s")
+if os.environ.get("BPS"): sys.exit(0)
 # where does the small-call floor come from: host enqueue time vs device time
 import time
 n = 1 << 16

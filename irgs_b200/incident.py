@@ -18,7 +18,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .raytracer import GRAD_STRIDE, _alloc_outputs, _ptr, _stream
+from .raytracer import GRAD_STRIDE, _alloc_outputs, _ptr, _reuse_records, _stream
 
 
 class IncidentDesc(ctypes.Structure):
@@ -97,6 +97,7 @@ class _IncidentTrace(torch.autograd.Function):
             _ptr(hit_count), _ptr(hits), cap, alpha_min, tracer.transmittance_min, int(back_culling), _stream(dev)))
         tracer.last_hit_count = hit_count
         ctx.tracer, ctx.cap = tracer, cap
+        ctx.pack_epoch = impl.lib.irgs_get_info(impl.h, b"pack_epoch") if any(ctx.needs_input_grad) else -1
         ctx.cfg = (sample_num, t_min, alpha_min, deg, back_culling, tracer.transmittance_min, azimuth is not None)
         ctx.save_for_backward(position, normals_pt, azimuth if azimuth is not None else position[:0], means3D, opacity, ru,
                               rv, normals, features, shs, color, normal, feature, depth, alpha, hit_count,
@@ -127,6 +128,7 @@ class _IncidentTrace(torch.autograd.Function):
         have_list = ctx.cap > 0
         desc = _desc(position, normals_pt, azimuth if has_azim else None, sample_num, t_min)
         null = ctypes.c_void_p(0)
+        _reuse_records(ctx, impl)
         _lib.check(impl.lib.irgs_trace_backward_incident(
             impl.h, ctypes.byref(desc), S, K, deg, _ptr(means3D), _ptr(opacity), _ptr(ru), _ptr(rv), _ptr(normals),
             _ptr(features), _ptr(shs), _ptr(color), _ptr(normal), _ptr(feature), _ptr(depth), _ptr(alpha),

@@ -19,7 +19,7 @@ import math
 import torch
 
 from . import _lib
-from .raytracer import GRAD_STRIDE, _alloc_outputs, _ptr, _stream
+from .raytracer import GRAD_STRIDE, _alloc_outputs, _ptr, _reuse_records, _stream
 
 
 class CameraDesc(ctypes.Structure):
@@ -87,6 +87,7 @@ class _CameraTrace(torch.autograd.Function):
             int(back_culling), _stream(dev)))
         tracer.last_hit_count = hit_count
         ctx.tracer, ctx.cam, ctx.cap = tracer, cam, cap
+        ctx.pack_epoch = impl.lib.irgs_get_info(impl.h, b"pack_epoch") if any(ctx.needs_input_grad) else -1
         ctx.cfg = (alpha_min, deg, back_culling, tracer.transmittance_min)
         ctx.save_for_backward(means3D, opacity, ru, rv, normals, features, shs, *outs, hit_count, hits if hits is not None else hit_count)
         ctx.mark_non_differentiable(hit_count)
@@ -108,6 +109,7 @@ class _CameraTrace(torch.autograd.Function):
             fused, gfeat = torch.zeros(N, GRAD_STRIDE, device=dev), torch.zeros(N, S, device=dev)
         have, null = ctx.cap > 0, ctypes.c_void_p(0)
         desc = cam.desc()
+        _reuse_records(ctx, impl)
         _lib.check(impl.lib.irgs_trace_backward_camera(
             impl.h, ctypes.byref(desc), S, K, deg, _ptr(means3D), _ptr(opacity), _ptr(ru), _ptr(rv), _ptr(normals), _ptr(features),
             _ptr(shs), _ptr(color), _ptr(normal), _ptr(feature), _ptr(depth), _ptr(alpha), _ptr(hit_count) if have else null,

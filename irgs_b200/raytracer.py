@@ -76,6 +76,14 @@ class _Impl:
             pass
 
 
+def _reuse_records(ctx, impl):
+    """Backward of a node whose forward recorded ctx.pack_epoch: if nothing has packed or rebuilt since (autograd itself guarantees
+    that the saved arrays are unmodified) the packed records are still the ones of these arrays and the next backward call skips
+    its own pack."""
+    if impl.lib.irgs_get_info(impl.h, b"pack_epoch") == getattr(ctx, "pack_epoch", -1):
+        impl.lib.irgs_set_option(impl.h, b"skip_next_pack", 1)
+
+
 class _GaussianTrace(torch.autograd.Function):
     """raytracer.py:5-66."""
 
@@ -125,10 +133,7 @@ class _GaussianTrace(torch.autograd.Function):
             fused = torch.zeros(N, GRAD_STRIDE, device=dev, dtype=torch.float32)
             gfeat = torch.zeros(N, S, device=dev, dtype=torch.float32)
         have_list = ctx.cap > 0
-        if impl.lib.irgs_get_info(impl.h, b"pack_epoch") == ctx.pack_epoch:
-            # nothing has packed or rebuilt since this node's forward (autograd itself guarantees that the saved arrays are
-            # unmodified): the records are still the ones of these arrays
-            impl.lib.irgs_set_option(impl.h, b"skip_next_pack", 1)
+        _reuse_records(ctx, impl)
         _lib.check(impl.lib.irgs_trace_backward(
             impl.h, B, S, K, ctx.deg, _ptr(rays_o), _ptr(rays_d), _ptr(means3D), _ptr(opacity), _ptr(ru), _ptr(rv),
             _ptr(normals), _ptr(features), _ptr(shs), _ptr(color), _ptr(normal), _ptr(feature), _ptr(depth),

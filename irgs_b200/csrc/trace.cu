@@ -389,21 +389,41 @@ __global__ void __launch_bounds__(FTB, IRGS_BWD_BLOCKS) trace_backward_flat_kern
 #ifndef IRGS_BWD_PIPELINE
 #define IRGS_BWD_PIPELINE 1   // 0: every round fetches its own ids and positions (comparison builds)
 #endif
+#ifndef IRGS_BWD_LOCATE_ONCE
+#define IRGS_BWD_LOCATE_ONCE 1   // 0: a round locates its own hits again although the id fetch two rounds earlier already did
+#endif
+#if IRGS_BWD_LOCATE_ONCE
+    // (owner, index) of a flat position is found once, when its id is requested two rounds ahead, and carried to the round that uses it
+    int own_c, kk_c, own_n, kk_n;
+    int g_cur, g_nxt;
+    { const bool in = locate(lane, own_c, kk_c); g_cur = in ? __ldg(a.hits + (ray0 + own_c) * a.hit_cap + kk_c) : 0; }
+    { const bool in = locate(32 + lane, own_n, kk_n); g_nxt = in ? __ldg(a.hits + (ray0 + own_n) * a.hit_cap + kk_n) : 0; }
+#else
     int g_cur = fetch_id(lane), g_nxt = fetch_id(32 + lane);
+#endif
     int pos_cur = lane < total ? __ldg(p.inv_order + g_cur) : 0;
     for (int base = 0; base < total; base += 32) {
         const int idx = base + lane;
         const bool act = idx < total;
 #if IRGS_BWD_PIPELINE
         const int pos_nxt = idx + 32 < total ? __ldg(p.inv_order + g_nxt) : 0;   // next round's leaf positions
+#if IRGS_BWD_LOCATE_ONCE
+        int own_2, kk_2, g_nxt2;                                                    // ids of the round after next
+        { const bool in = locate(idx + 64, own_2, kk_2); g_nxt2 = in ? __ldg(a.hits + (ray0 + own_2) * a.hit_cap + kk_2) : 0; }
+#else
         const int g_nxt2 = fetch_id(idx + 64);                                     // ids of the round after next
+#endif
 #else
         const int pos_nxt = 0, g_nxt2 = 0;
         g_cur = fetch_id(idx);
         pos_cur = act ? __ldg(p.inv_order + g_cur) : 0;
 #endif
+#if IRGS_BWD_LOCATE_ONCE && IRGS_BWD_PIPELINE
+        const int owner = own_c, k_loc = kk_c;
+#else
         int owner, k_loc;
         locate(idx, owner, k_loc);
+#endif
         const int n_o = __shfl_sync(FULL, c_eff, owner);
         const int k = k_loc;
         const int64_t ray = ray0 + owner;
@@ -653,6 +673,9 @@ __global__ void __launch_bounds__(FTB, IRGS_BWD_BLOCKS) trace_backward_flat_kern
             }
         }
         g_cur = g_nxt; pos_cur = pos_nxt; g_nxt = g_nxt2;
+#if IRGS_BWD_LOCATE_ONCE && IRGS_BWD_PIPELINE
+        own_c = own_n; kk_c = kk_n; own_n = own_2; kk_n = kk_2;
+#endif
     }
     if (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until it has been read
     if (valid && cnt <= a.hit_cap) {  // rays with longer lists are written by the re-trace kernel

@@ -84,6 +84,9 @@ constexpr int DRAIN_SP_MAX = SSTK - 3 * DRAIN_G - 1;   // deepest stack the wide
 #ifndef IRGS_FULL_CHAIN_SMEM
 #define IRGS_FULL_CHAIN_SMEM 1    // 0: the full-row transmittance chain through one shuffle per candidate (comparison builds)
 #endif
+#ifndef IRGS_LEAF_PIPELINE
+#define IRGS_LEAF_PIPELINE 1      // 0: every leaf round locates its own items first (comparison builds)
+#endif
 #ifndef IRGS_LEAF_PACK
 #define IRGS_LEAF_PACK 1          // 0: seven shuffles of per-owner integers and window ids per leaf round instead of two
 #endif
@@ -384,9 +387,42 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
             const int start = incl - m;
             const int n_items = __shfl_sync(FULL, incl, 31);
             __syncwarp();   // queue columns written in the NODE sub-phase are read by other lanes below
+#if IRGS_LEAF_PIPELINE
+            // item -> (owner, leaf) is static for the whole batch (queues and prefix sums do not change inside it): the item of the
+            // NEXT round is located while this round's record loads are in flight, so that a round starts with its loads instead
+            // of seven dependent shuffles and a shared-memory read
+            auto locate_item = [&](int idx, int &owner_out, unsigned &pk_out, int &leaf_out) {
+                const bool in = idx < n_items;
+                int o = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, o + step - 1);
+                    if (v <= idx) o += step;
+                }
+                o = in ? o : (int)lane;
+                const unsigned pk = __shfl_sync(FULL, (unsigned)start | ((unsigned)m << 10) | ((unsigned)pn << 16), o);
+                owner_out = o; pk_out = pk;
+                leaf_out = in ? ~ws.pend[((int)((pk >> 16) & 63u) - 1 - (idx - (int)(pk & 1023u))) * PS + o] : 0;   // popped from the top
+            };
+            int owner_n, leaf_n; unsigned pk_n;
+            locate_item((int)lane, owner_n, pk_n, leaf_n);
+#endif
             for (int base = 0; base < n_items; base += 32) {
                 const int idx = base + (int)lane;
                 const bool has = idx < n_items;
+#if IRGS_LEAF_PIPELINE
+                const int owner = owner_n, leaf = leaf_n;
+                const int o_start = (int)(pk_n & 1023u), o_m = (int)((pk_n >> 10) & 63u);
+                float4 q0, q1, q2, q3;
+                q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has) {
+                    ldg256_stream(p.recs + leaf, q0, q1);
+                    if (!LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, q2, q3);
+                    if (STATS) ++st_leaf;
+                }
+                if (base + 32 < n_items) locate_item(idx + 32, owner_n, pk_n, leaf_n);
+                const int o_cnt = __shfl_sync(FULL, cnt, owner);   // (changes from round to round: fetched where it is used)
+#else
                 int owner = 0;
 #pragma unroll
                 for (int step = 16; step >= 1; step >>= 1) {
@@ -412,6 +448,7 @@ __global__ void __launch_bounds__(TB, IRGS_FWD_BLOCKS) trace_forward_kernel(cons
                     if (!LEAF_2STAGE) ldg256_stream(&p.recs[leaf].r2, q2, q3);
                     if (STATS) ++st_leaf;
                 }
+#endif
                 RayCtx ro;
                 ro.ox = __shfl_sync(FULL, r.ox, owner); ro.oy = __shfl_sync(FULL, r.oy, owner); ro.oz = __shfl_sync(FULL, r.oz, owner);
                 ro.dx = __shfl_sync(FULL, r.dx, owner); ro.dy = __shfl_sync(FULL, r.dy, owner); ro.dz = __shfl_sync(FULL, r.dz, owner);

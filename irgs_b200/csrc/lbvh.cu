@@ -370,7 +370,10 @@ __global__ void hierarchy_kernel(const uint32_t *__restrict__ codes, int n, Node
 // iterations of four small kernels at build time; refits (update_bvh) are unaffected.
 // Nodes are numbered from the top down as they are created (the last merge, the root, gets index 0), children of
 // neighbouring clusters next to each other.
-constexpr int PLOC_R = 8;
+#ifndef IRGS_PLOC_R
+#define IRGS_PLOC_R 8
+#endif
+constexpr int PLOC_R = IRGS_PLOC_R;
 constexpr int PLOC_TB = 256;     // nearest-neighbour search block
 constexpr int PLOC_SB = 1024;    // compaction block
 

@@ -111,7 +111,7 @@ int irgs_tracer_destroy(irgs_tracer_t *h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->qnodes4); cudaFree(h->even); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
+    cudaFree(h->nodes); cudaFree(h->qnodes); cudaFree(h->qnodes4); cudaFree(h->even); cudaFree(h->wide_kids); cudaFree(h->wide_counts); cudaFree(h->boxes); cudaFree(h->codes); cudaFree(h->codes_alt); cudaFree(h->order);
     cudaFree(h->order_alt); cudaFree(h->leaf_parent); cudaFree(h->node_parent); cudaFree(h->flags);
     cudaFree(h->ploc_cid); cudaFree(h->ploc_box); cudaFree(h->ploc_nn); cudaFree(h->ploc_counts); cudaFree(h->ploc_offs); cudaFree(h->ploc_totals);
     cudaFree(h->radix_hist); cudaFree(h->scene); cudaFree(h->recs); cudaFree(h->inv_order); cudaFree(h->counter); cudaFree(h->stats);
@@ -677,6 +677,10 @@ int irgs_set_option(irgs_tracer_t *h, const char *name, int64_t value) {
     if (strcmp(name, "slot") == 0) return 0;   // accepted for compatibility: slots follow the stream of each call now
     if (strcmp(name, "builder") == 0) {   // takes effect at the next build_bvh / build_from_surfels
         h->builder = value == 1 ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "wide_fold") == 0) {   // takes effect at the next build_bvh / build_from_surfels
+        h->wide_fold = value == 1 ? 1 : 0;
         return 0;
     }
     if (strcmp(name, "contiguous_outputs") == 0) {

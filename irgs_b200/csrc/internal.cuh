@@ -49,11 +49,13 @@ struct __align__(16) QNode {
 static_assert(sizeof(QNode) == 32, "quantised node must be 32 bytes");
 #define IRGS_CHILD_NONE INT_MIN
 
-// 4-wide traversal node of the forward kernel: a binary node at EVEN depth together with its two children (every other
-// level of the binary tree is folded away), i.e. up to four grandchildren, each in the same 16-byte form as a QNode child
-// (six 16-bit planes + reference).  One visit = two 256-bit loads from one 64-byte line and four slab tests; the chain
-// of dependent node fetches of a ray is half as long as on the binary tree (model on the C3 rays: 52.5 -> 26.0 visits).
-// Stored at the index of the binary node it was made from (odd-depth entries are unused), so references stay valid.
+// 4-wide traversal node of the forward kernel: up to four subtrees of the binary tree, each in the same 16-byte form as a QNode
+// child (six 16-bit planes + reference).  One visit = two 256-bit loads from one 64-byte line and four slab tests; the chain of
+// dependent node fetches of a ray is about half as long as on the binary tree.  Which subtrees a wide node holds is decided at
+// build time (lbvh.cu): by default a GREEDY COLLAPSE -- start from the two children of a binary node and, while a slot is free,
+// replace the internal child with the largest surface area by its own two children -- or, irgs_set_option("wide_fold", 1), the
+// fixed fold of every other level (a node at even depth + its two children: a slot stays empty wherever a child is a leaf).
+// A wide node is stored at the index of the binary node it starts from (the other entries are unused), so references stay valid.
 struct __align__(32) QNode4 {
     uint4 c[4];
 };
@@ -68,8 +70,12 @@ struct irgs_tracer {
     int64_t cap = 0;       // allocated capacity (surfels)
     irgs::Node *nodes = nullptr;        // [max(n-1,1)] float bounds (refit works on these)
     irgs::QNode *qnodes = nullptr;      // [max(n-1,1)] quantised binary nodes (re-trace backward, intersection test)
-    irgs::QNode4 *qnodes4 = nullptr;    // [max(n-1,1)] 4-wide nodes the forward walk reads (valid at even-depth indices)
-    int *even = nullptr;                // [n] 1 where the binary node's depth is even (a wide node lives there)
+    irgs::QNode4 *qnodes4 = nullptr;    // [max(n-1,1)] 4-wide nodes the forward walk reads (valid where `even` is set)
+    int *even = nullptr;                // [n] 1 where a wide node lives at the binary node's index (greedy collapse: its wide roots; fixed fold: even depth)
+    int4 *wide_kids = nullptr;          // [n] greedy collapse: per wide root, the four slots as binary parent * 2 + side (-1: empty); frozen by the build
+    int *wide_counts = nullptr;         // queue lengths of the collapse waves
+    int wide_fold = 0;                  // irgs_set_option("wide_fold"): 0 greedy collapse (default), 1 fixed fold of every other level; next build
+    int wide_fold_built = 0;            // what the current structure was built with
     float *boxes = nullptr;             // [n,6] unpadded per-surfel bounds, surfel order
     uint32_t *codes = nullptr, *codes_alt = nullptr;  // [n]
     int *order = nullptr, *order_alt = nullptr;       // [n] leaf position -> surfel id

@@ -375,6 +375,7 @@ __global__ void hierarchy_kernel(const uint32_t *__restrict__ codes, int n, Node
 #endif
 constexpr int PLOC_R = IRGS_PLOC_R;
 constexpr int PLOC_TB = 256;     // nearest-neighbour search block
+constexpr int WIDE_WAVES = 96;   // waves of the greedy collapse into 4-wide nodes (>= the depth of any tree the walk's stack accepts)
 constexpr int PLOC_SB = 1024;    // compaction block
 
 struct __align__(16) PlocBox { float4 lo, hi; };
@@ -737,7 +738,73 @@ __device__ __forceinline__ uint4 quant_child(const float *b, int ref, const floa
     return make_uint4(q[0] | (q[3] << 16), q[1] | (q[4] << 16), q[2] | (q[5] << 16), (unsigned)ref);
 }
 
-// Bounds part (every build and refit): one thread per even-depth binary node gathers its (up to four) grandchildren.
+// Topology part, default (build only): GREEDY COLLAPSE of the binary tree into 4-wide nodes.  A wide node starts as the two children
+// of its binary node; while it has a free slot, the internal child with the largest surface area is replaced by its own two
+// children.  The internal children that remain become wide nodes themselves.  Unlike the fixed fold of every other level, which
+// leaves a slot empty wherever a child is a leaf (and two where both are), this fills the nodes wherever the subtree allows: fewer
+// wide nodes, fewer visits.  Top-down in waves: wave w turns the wide roots at wide depth w into their child lists (`kids`: for each
+// slot the binary parent * 2 + side that holds the slot's bounds and reference, -1 = empty) and queues the next wave.
+__device__ __forceinline__ int slot_ref(const Node *__restrict__ nodes, int desc) {
+    const int4 d = nodes[desc >> 1].d;
+    return (desc & 1) ? d.y : d.x;
+}
+__global__ void wide_init_kernel(int *__restrict__ frontier, int *__restrict__ counts, int n_counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_counts) counts[i] = i == 0 ? 1 : 0;
+    if (i == 0) frontier[0] = 0;   // the root
+}
+__global__ void wide_collapse_kernel(const Node *__restrict__ nodes, const int *__restrict__ fin, const int *__restrict__ cnt_in,
+                                     int *__restrict__ fout, int *__restrict__ cnt_out, int4 *__restrict__ kids,
+                                     int *__restrict__ is_root) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *cnt_in) return;
+    const int n = fin[i];
+    int desc[4] = {2 * n, 2 * n + 1, -1, -1};
+    int m = 2;
+    while (m < 4) {
+        int best = -1;
+        float best_a = -1.f;
+        for (int k = 0; k < m; ++k) {
+            const float *b = reinterpret_cast<const float *>(nodes + (desc[k] >> 1)) + 6 * (desc[k] & 1);
+            if (slot_ref(nodes, desc[k]) >= 0 && b[0] < IRGS_EMPTY_FAR) {
+                const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+                const float ar = dx * dy + dy * dz + dz * dx;
+                if (ar > best_a) { best_a = ar; best = k; }
+            }
+        }
+        if (best < 0) break;
+        const int ref = slot_ref(nodes, desc[best]);
+        desc[best] = 2 * ref;
+        desc[m++] = 2 * ref + 1;
+    }
+    kids[n] = make_int4(desc[0], desc[1], desc[2], desc[3]);
+    is_root[n] = 1;
+    for (int k = 0; k < m; ++k) {
+        const int ref = slot_ref(nodes, desc[k]);
+        if (ref >= 0) fout[atomicAdd(cnt_out, 1)] = ref;   // (a subtree of invisible surfels is never entered, but gets valid nodes too)
+    }
+}
+
+// Bounds part of the greedy collapse (every build and refit): one thread per wide root quantises the slots of its child list.
+__global__ void quantize_wide_kids_kernel(const Node *__restrict__ nodes, const int *__restrict__ is_root,
+                                          const int4 *__restrict__ kids, int n_int, const float *__restrict__ scene,
+                                          QNode4 *__restrict__ wide) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_int || !is_root[i]) return;
+    const int4 kd = kids[i];
+    const int desc[4] = {kd.x, kd.y, kd.z, kd.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint4 out = make_uint4(0u, 0u, 0u, (unsigned)IRGS_CHILD_NONE);
+        if (desc[k] >= 0) {
+            const float *b = reinterpret_cast<const float *>(nodes + (desc[k] >> 1)) + 6 * (desc[k] & 1);
+            out = quant_child(b, slot_ref(nodes, desc[k]), scene);
+        }
+        wide[i].c[k] = out;
+    }
+}
+
+// Fixed fold (irgs_set_option("wide_fold", 1)), bounds part (every build and refit): one thread per even-depth binary node gathers its (up to four) grandchildren.
 __global__ void quantize_wide_kernel(const Node *__restrict__ nodes, const int *__restrict__ even, int n_int,
                                      const float *__restrict__ scene, QNode4 *__restrict__ wide) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -781,7 +848,7 @@ int lbvh_reserve(irgs_tracer *h, int64_t n) {
         !realloc_dev(h->flags, (size_t)c) || !realloc_dev(h->recs, (size_t)c) || !realloc_dev(h->inv_order, (size_t)c) || !realloc_dev(h->ploc_cid, (size_t)c * 2) ||
         !realloc_dev(h->ploc_box, (size_t)c * 2 * 8) || !realloc_dev(h->ploc_nn, (size_t)c) ||
         !realloc_dev(h->ploc_counts, (size_t)(c / PLOC_SB + 2)) || !realloc_dev(h->ploc_offs, (size_t)(c / PLOC_SB + 2) * 2) ||
-        !realloc_dev(h->ploc_totals, 2))
+        !realloc_dev(h->ploc_totals, 2) || !realloc_dev(h->wide_kids, (size_t)c) || !realloc_dev(h->wide_counts, (size_t)WIDE_WAVES + 2))
         return 1;
     int64_t tiles = (c + RS_TILE - 1) / RS_TILE;
     if (!realloc_dev(h->radix_hist, (size_t)tiles * 256)) return 1;
@@ -827,8 +894,11 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
             hierarchy_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->codes, n, h->nodes, h->leaf_parent, h->node_parent);
             count_launch();
         }
-        depth_parity_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->node_parent, n_int, h->even);
-        count_launch();
+        h->wide_fold_built = h->wide_fold;
+        if (h->wide_fold_built) {
+            depth_parity_kernel<<<(n_int + 255) / 256, 256, 0, s>>>(h->node_parent, n_int, h->even);
+            count_launch();
+        }
     }
     IRGS_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(int) * (size_t)n, s));
     refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->boxes, h->order, h->leaf_parent, h->node_parent, n, scene_i, h->nodes,
@@ -836,7 +906,24 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
     const int n_internal = n > 1 ? n - 1 : 1;
     quant_frame_kernel<<<1, 32, 0, s>>>(h->scene);
     quantize_nodes_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, n_internal, h->scene, h->qnodes);
-    quantize_wide_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, h->even, n_internal, h->scene, h->qnodes4);
+    if (h->wide_fold_built) {
+        quantize_wide_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, h->even, n_internal, h->scene, h->qnodes4);
+    } else {
+        if (!refit_only) {
+            // the collapse needs the bounds the refit just wrote; one wave per level of the wide tree, whose depth is at most the
+            // binary tree's (PLOC: measured at build time; Karras: <= 62).  Waves past the last level find an empty queue.
+            IRGS_CHECK(cudaMemsetAsync(h->even, 0, sizeof(int) * (size_t)n_internal, s));
+            wide_init_kernel<<<1, 128, 0, s>>>(h->ploc_cid, h->wide_counts, WIDE_WAVES + 2);
+            const int waves = (h->tree_depth > 0 ? h->tree_depth : 62) + 1;
+            for (int w = 0; w < waves && w < WIDE_WAVES; ++w) {
+                int *fin = h->ploc_cid + (size_t)(w & 1) * (size_t)h->cap, *fout = h->ploc_cid + (size_t)((w + 1) & 1) * (size_t)h->cap;
+                wide_collapse_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, fin, h->wide_counts + w, fout,
+                                                                                h->wide_counts + w + 1, h->wide_kids, h->even);
+            }
+            count_launch(1 + waves);
+        }
+        quantize_wide_kids_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, h->even, h->wide_kids, n_internal, h->scene, h->qnodes4);
+    }
     count_launch(4);
     IRGS_CHECK(cudaGetLastError());
     h->built = true;

@@ -9,6 +9,7 @@ dev = torch.device("cuda:0")
 class A: surfels=300000; img=int(os.environ.get("IMG", 128)); spp=256
 def factory(sc, inp):
     tr = GaussianTracer(transmittance_min=synth.T_MIN, device=dev)
+    if os.environ.get("WIDE_FOLD"): tr.set_option("wide_fold", int(os.environ["WIDE_FOLD"]))
     tr.build_from_surfels(inp["means3D"], inp["opacity"], inp["ru"], inp["rv"], inp["normals"], synth.ALPHA_MIN)
     return tr
 sc, inp, tr, ro, rd = bench.build_workload(A, dev, 0, 1, factory)

@@ -24,12 +24,29 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile the library unless it is up to date.  Safe under several processes at once (one rank per GPU under torchrun, each
+    importing the package): one process holds a lock file while it compiles into a temporary file that is renamed over the library
+    atomically, the others wait for the lock and then find the library up to date -- nobody ever maps a half-written file."""
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("IRGS_NVCC_DEFS", "").split()  # tuning experiments only, e.g. "-DIRGS_MIN_ACTIVE=16"
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():   # somebody else built it while this process waited
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            extra = os.environ.get("IRGS_NVCC_DEFS", "").split()  # tuning experiments only, e.g. "-DIRGS_MIN_ACTIVE=16"
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+            try:
+                subprocess.check_call(cmd, cwd=CSRC)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

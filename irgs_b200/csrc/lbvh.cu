@@ -914,7 +914,8 @@ int lbvh_build(irgs_tracer *h, bool refit_only, cudaStream_t s) {
             // binary tree's (PLOC: measured at build time; Karras: <= 62).  Waves past the last level find an empty queue.
             IRGS_CHECK(cudaMemsetAsync(h->even, 0, sizeof(int) * (size_t)n_internal, s));
             wide_init_kernel<<<1, 128, 0, s>>>(h->ploc_cid, h->wide_counts, WIDE_WAVES + 2);
-            const int waves = (h->tree_depth > 0 ? h->tree_depth : 62) + 1;
+            // (a PLOC tree that was kept has the depth measured at build time; everything else is the Karras tree: <= 62 levels)
+            const int waves = ((h->builder == 0 && h->tree_depth > 0 && h->tree_depth <= 60) ? h->tree_depth : 62) + 2;
             for (int w = 0; w < waves && w < WIDE_WAVES; ++w) {
                 int *fin = h->ploc_cid + (size_t)(w & 1) * (size_t)h->cap, *fout = h->ploc_cid + (size_t)((w + 1) & 1) * (size_t)h->cap;
                 wide_collapse_kernel<<<(n_internal + 255) / 256, 256, 0, s>>>(h->nodes, fin, h->wide_counts + w, fout,

@@ -18,8 +18,17 @@ _LIB = None
 def build(force=False):
     so = os.path.join(_DIR, "liboracle.so")
     src = os.path.join(_DIR, "surfel_oracle.c")
-    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
-        subprocess.check_call(["make", "-s", "-C", _DIR, "liboracle.so"])
+    def stale():
+        return not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so))
+    if force or stale():
+        import fcntl
+        with open(so + ".lock", "w") as lock:   # several processes may import the checker at once: one of them builds
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.check_call(["make", "-s", "-C", _DIR, "liboracle.so"])
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 

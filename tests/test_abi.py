@@ -151,3 +151,35 @@ def test_stride_start_order_is_a_bijection_in_32_bits():
         i = np.arange(n, dtype=np.uint32)
         perm = (i * np.uint32(m)) % np.uint32(n)                    # the kernel's arithmetic
         assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32)), n
+
+
+def test_concurrent_builds_never_expose_a_partial_library(tmp_path):
+    """One rank per GPU imports the package under torchrun; when the library is stale every rank wants to build it.  The build
+    holds a lock and renames a finished temporary file over the library, so a process that loads it while another one compiles
+    never maps a half-written file (seen once as `file too short` on four of eight ranks).  A slow fake compiler stands in for nvcc."""
+    import shutil
+    import subprocess
+    import sys
+    from irgs_b200 import build as b
+    assert os.path.exists(b.LIB)
+    keep = tmp_path / "lib.keep"
+    shutil.copy(b.LIB, keep)
+    fake = tmp_path / "nvcc"
+    fake.write_text("#!/bin/bash\nout=\"\"\nwhile [ $# -gt 0 ]; do if [ \"$1\" = \"-o\" ]; then out=\"$2\"; fi; shift; done\n"
+                    f"head -c 65536 {keep} > \"$out\"\nsleep 0.4\ncat {keep} > \"$out\"\n")
+    fake.chmod(0o755)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import ctypes, sys; sys.path.insert(0, %r); from irgs_b200 import build as b; b.build(force=True); "
+            "lib = ctypes.CDLL(b.LIB); lib.irgs_last_error; print('ok')" % root)
+    env = dict(os.environ, NVCC=str(fake))
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for _ in range(4)]
+    try:
+        for p in procs:
+            out, err = p.communicate(timeout=120)
+            assert p.returncode == 0 and "ok" in out, err[-2000:]
+        assert open(b.LIB, "rb").read() == open(keep, "rb").read()
+        assert not [f for f in os.listdir(os.path.dirname(b.LIB)) if f.endswith(".tmp")]
+    finally:
+        if not os.path.exists(b.LIB) or os.path.getsize(b.LIB) != os.path.getsize(keep):
+            shutil.copy(keep, b.LIB)

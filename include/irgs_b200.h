@@ -315,6 +315,9 @@ int irgs_normalize_outputs_backward(int64_t n_rays, int S, float threshold, cons
  * candidate scratch) looked up from the call's own `stream`, so a backward uses the slot of the stream it runs on ("slot" is
  * still accepted and ignored).  A handle is not thread-safe beyond that: do not build / refit while traces are in flight.
  * "builder": 0 (default) PLOC clustering over the Morton order, 1 Karras LBVH; takes effect at the next build.
+ * "wide_fold": 0 (default) the 4-wide traversal nodes are a greedy collapse of the binary tree (the internal child with the largest
+ * surface area is expanded while a node has a free slot), 1 the fixed fold of every other level; takes effect at the next build.
+ * "fwd_blocks_per_sm": resident blocks per SM of the forward kernel's persistent grid (0 = what the occupancy allows; experiments).
  * "contiguous_outputs": 1 = the caller promises that whenever a forward call's output arrays are back to back in memory (color,
  * normal, feature, depth, alpha, hit_count) they are views of ONE allocation; they are then zero-filled with a single memset
  * instead of six (default 0: arrays that merely happen to be adjacent may belong to different allocations).
